@@ -1,0 +1,91 @@
+"""
+ctypes binding of `libecgvit_b200.so` (C ABI declared in include/ecgvit_b200.h).
+
+There is no fallback: if the library is missing the import of any compute entry point raises, and every
+non-zero return code raises RuntimeError with the library's own message.
+"""
+import ctypes
+import os
+from ctypes import c_int, c_int64, c_float, c_void_p, c_char_p, POINTER, Structure
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG_DIR, 'libecgvit_b200.so')
+
+F32, BF16 = 0, 1
+EPI_STORE, EPI_BIAS_RES, EPI_BIAS_GELU, EPI_DGELU, EPI_ATOMIC_F32 = 0, 1, 2, 3, 4
+REDUCTION = {'mean': 0, 'sum': 1, 'none': 2}
+
+
+class GemmArgs(Structure):
+    """mirror of `ecgvit_gemm_args`"""
+    _fields_ = [
+        ('M', c_int), ('N', c_int), ('K', c_int),
+        ('A', c_void_p), ('lda', c_int64), ('a_kmajor', c_int),
+        ('B', c_void_p), ('ldb', c_int64), ('b_kmajor', c_int),
+        ('epilogue', c_int),
+        ('out', c_void_p), ('ldo', c_int64),
+        ('out2', c_void_p), ('aux', c_void_p), ('bias', c_void_p),
+        ('dtype', c_int), ('split_k', c_int), ('reserved', c_int),
+    ]
+
+
+# name -> argtypes; restype is int unless listed in _RESTYPES
+SIGNATURES = {
+    'ecgvit_abi_version': [],
+    'ecgvit_last_error': [],
+    'ecgvit_device_ok': [],
+    'ecgvit_patchify': [c_void_p, c_void_p, c_int, c_int, c_int64, c_int, c_int, c_int, c_void_p],
+    'ecgvit_embed_assemble': [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    'ecgvit_embed_assemble_bwd': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                  c_void_p],
+    'ecgvit_layernorm_fwd': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float,
+                             c_int, c_void_p],
+    'ecgvit_layernorm_bwd': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                             c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
+    'ecgvit_gemm': [POINTER(GemmArgs), c_void_p],
+    'ecgvit_attention_fwd': [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p],
+    'ecgvit_attention_bwd': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float,
+                             c_int, c_void_p],
+    'ecgvit_head_fwd': [c_void_p] * 11 + [c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p],
+    'ecgvit_head_bwd': [c_void_p] * 15 + [c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p],
+    'ecgvit_colsum': [c_void_p, c_void_p, c_int, c_int, c_int64, c_int, c_void_p],
+    'ecgvit_grad_sumsq': [c_void_p, c_int64, c_void_p, c_void_p, c_void_p],
+    'ecgvit_adamw_step': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p],
+    'ecgvit_grad_scale_by_clip': [c_void_p, c_int64, c_void_p, c_void_p, c_void_p],
+    'ecgvit_cast_f32_to_bf16': [c_void_p, c_void_p, c_int64, c_void_p],
+}
+_RESTYPES = {'ecgvit_last_error': c_char_p}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once); raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f'{LIB_PATH} is missing: build it with `python -c "import __graft_entry__ as g; g.build()"` '
+                f'(there is no CPU / PyTorch fallback for the ECG-ViT kernels)')
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+            fn.argtypes = argtypes
+            fn.restype = _RESTYPES.get(name, c_int)
+        _lib = lib
+    return _lib
+
+
+def last_error():
+    msg = load().ecgvit_last_error()
+    return msg.decode() if msg else ''
+
+
+def check(rc, what=''):
+    if rc != 0:
+        raise RuntimeError(f'ecgvit_b200 {what} failed (code {rc}): {last_error()}')
+
+
+def ptr(t):
+    """device pointer of a torch tensor (or None)"""
+    return None if t is None else t.data_ptr()

@@ -1,0 +1,195 @@
+// Shared helpers for the ecgvit_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/ecgvit_b200.h"
+
+namespace ecgvit {
+
+// ---- error plumbing -------------------------------------------------------------------------------
+char *last_error_buffer();  // thread-local, 512 bytes (api.cu)
+
+inline int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(last_error_buffer(), 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+inline int check_launch(const char *what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail((int)e, "%s: %s", what, cudaGetErrorString(e));
+    return 0;
+}
+
+#define ECGVIT_REQUIRE(cond, ...) \
+    do { if (!(cond)) return ::ecgvit::fail(-1, __VA_ARGS__); } while (0)
+
+inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+
+int sm_count();  // cached multiprocessor count of the current device (api.cu)
+
+// ---- element type helpers -------------------------------------------------------------------------
+typedef __nv_bfloat16 bf16;
+
+template <typename T> struct Vec8;  // 8 consecutive elements
+template <> struct Vec8<float> { float4 a, b; };
+template <> struct Vec8<bf16> { uint4 v; };
+
+__device__ __forceinline__ float to_f32(float x) { return x; }
+__device__ __forceinline__ float to_f32(bf16 x) { return __bfloat162float(x); }
+template <typename T> __device__ __forceinline__ T from_f32(float x);
+template <> __device__ __forceinline__ float from_f32<float>(float x) { return x; }
+template <> __device__ __forceinline__ bf16 from_f32<bf16>(float x) { return __float2bfloat16_rn(x); }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t *>(&h);
+}
+__device__ __forceinline__ void unpack_bf16x2(uint32_t u, float &lo, float &hi) {
+    lo = __uint_as_float(u << 16);
+    hi = __uint_as_float(u & 0xffff0000u);
+}
+
+// load / store 8 consecutive elements (16-byte aligned for bf16, 32-byte for float) as fp32
+__device__ __forceinline__ void load8(const float *p, float v[8]) {
+    float4 a = *reinterpret_cast<const float4 *>(p), b = *reinterpret_cast<const float4 *>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void load8(const bf16 *p, float v[8]) {
+    uint4 u = *reinterpret_cast<const uint4 *>(p);
+    unpack_bf16x2(u.x, v[0], v[1]); unpack_bf16x2(u.y, v[2], v[3]);
+    unpack_bf16x2(u.z, v[4], v[5]); unpack_bf16x2(u.w, v[6], v[7]);
+}
+__device__ __forceinline__ void store8(float *p, const float v[8]) {
+    *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4 *>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void store8(bf16 *p, const float v[8]) {
+    uint4 u;
+    u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+    u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4 *>(p) = u;
+}
+// 4-wide variants
+__device__ __forceinline__ void load4(const float *p, float v[4]) {
+    float4 a = *reinterpret_cast<const float4 *>(p);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+}
+__device__ __forceinline__ void load4(const bf16 *p, float v[4]) {
+    uint2 u = *reinterpret_cast<const uint2 *>(p);
+    unpack_bf16x2(u.x, v[0], v[1]); unpack_bf16x2(u.y, v[2], v[3]);
+}
+__device__ __forceinline__ void store4(float *p, const float v[4]) {
+    *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void store4(bf16 *p, const float v[4]) {
+    uint2 u;
+    u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+    *reinterpret_cast<uint2 *>(p) = u;
+}
+
+// ---- reductions -----------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// ---- GELU (exact, erf) ----------------------------------------------------------------------------
+// kExact: libdevice erff (parity mode, fp32).  Otherwise Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7,
+// far below bf16 resolution): one MUFU.RCP + one MUFU.EX2 + a degree-5 Horner.
+template <bool kExact> __device__ __forceinline__ void gelu_parts(float u, float &cdf, float &pdf) {
+    const float x = u * 0.70710678118654752f;  // u / sqrt(2)
+    if (kExact) {
+        cdf = 0.5f * (1.0f + erff(x));
+        pdf = 0.39894228040143268f * expf(-0.5f * u * u);
+    } else {
+        const float ax = fabsf(x);
+        const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+        const float e = exp2f(-1.4426950408889634f * ax * ax);  // exp(-x^2) = exp(-u^2/2)
+        float poly = fmaf(1.061405429f, t, -1.453152027f);
+        poly = fmaf(poly, t, 1.421413741f);
+        poly = fmaf(poly, t, -0.284496736f);
+        poly = fmaf(poly, t, 0.254829592f);
+        const float erf_abs = 1.0f - poly * t * e;
+        cdf = 0.5f * (1.0f + copysignf(erf_abs, x));
+        pdf = 0.39894228040143268f * e;
+    }
+}
+template <bool kExact> __device__ __forceinline__ float gelu_fwd(float u) {
+    float cdf, pdf;
+    gelu_parts<kExact>(u, cdf, pdf);
+    return u * cdf;
+}
+template <bool kExact> __device__ __forceinline__ float gelu_grad(float u) {
+    float cdf, pdf;
+    gelu_parts<kExact>(u, cdf, pdf);
+    return fmaf(u, pdf, cdf);
+}
+
+// ---- GEMM epilogue parameters shared by the tcgen05 and FFMA kernels -----------------------------
+struct EpiParams {
+    void *out;
+    void *out2;
+    const void *aux;
+    const float *bias;
+    int64_t ldo;
+};
+
+// Applies epilogue MODE to NV (4 or 8) consecutive accumulator columns of one row and stores them.
+// `col` is a multiple of NV and the caller guarantees row/col are in bounds.
+template <int MODE, typename T, int NV, bool kExactGelu>
+__device__ __forceinline__ void epilogue_store(const EpiParams &p, int64_t row, int col, float acc[NV]) {
+    const int64_t off = row * p.ldo + col;
+    if (MODE == ECGVIT_EPI_ATOMIC_F32) {
+        float *o = reinterpret_cast<float *>(p.out) + off;
+#pragma unroll
+        for (int i = 0; i < NV; i += 4)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + i), "f"(acc[i]),
+                         "f"(acc[i + 1]), "f"(acc[i + 2]), "f"(acc[i + 3])
+                         : "memory");
+        return;
+    }
+    if (MODE != ECGVIT_EPI_DGELU && p.bias != nullptr) {
+#pragma unroll
+        for (int i = 0; i < NV; i += 4) {
+            const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + col + i));
+            acc[i] += b.x; acc[i + 1] += b.y; acc[i + 2] += b.z; acc[i + 3] += b.w;
+        }
+    }
+    T *o = reinterpret_cast<T *>(p.out) + off;
+    if (MODE == ECGVIT_EPI_BIAS_RES) {
+        float r[NV];
+        if (NV == 8) load8(reinterpret_cast<const T *>(p.aux) + off, r);
+        else load4(reinterpret_cast<const T *>(p.aux) + off, r);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) acc[i] += r[i];
+    } else if (MODE == ECGVIT_EPI_DGELU) {
+        float u[NV];
+        if (NV == 8) load8(reinterpret_cast<const T *>(p.aux) + off, u);
+        else load4(reinterpret_cast<const T *>(p.aux) + off, u);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) acc[i] *= gelu_grad<kExactGelu>(u[i]);
+    } else if (MODE == ECGVIT_EPI_BIAS_GELU) {
+        float h[NV];
+        // the saved pre-activation is what backward differentiates, so round it first (bf16 mode)
+#pragma unroll
+        for (int i = 0; i < NV; ++i) h[i] = gelu_fwd<kExactGelu>(to_f32(from_f32<T>(acc[i])));
+        T *o2 = reinterpret_cast<T *>(p.out2) + off;
+        if (NV == 8) store8(o2, h); else store4(o2, h);
+    }
+    if (NV == 8) store8(o, acc); else store4(o, acc);
+}
+
+}  // namespace ecgvit

@@ -1,0 +1,377 @@
+// HBM-bound kernels of the ECG-ViT step: patch gather, CLS/pos assemble, LayerNorm fwd/bwd, column sums, casts.
+// All use 128-bit accesses and warp-shuffle reductions; statistics are fp32.
+#include "common.cuh"
+
+namespace ecgvit {
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------------
+// patchify: a[(b*n+w), t*C+c] = x[b, c, w*P+t]     (einops 'b c (h p1) (w p2) -> b (h w) (p1 p2 c)', h=p1=1)
+// one CTA per (b, w): coalesced reads along t per lead, transposed through smem, coalesced writes.
+template <typename T>
+__global__ void patchify_kernel(const float *__restrict__ x, T *__restrict__ a, int C, int64_t x_ld, int n_patch,
+                                int P) {
+    extern __shared__ float tile[];  // [P*C] in output order
+    const int w = blockIdx.x % n_patch;
+    const int b = blockIdx.x / n_patch;
+    const int PC = P * C;
+    const float *xb = x + (int64_t)b * C * x_ld + (int64_t)w * P;
+    for (int i = threadIdx.x; i < PC; i += blockDim.x) {
+        const int c = i / P, t = i - c * P;
+        tile[t * C + c] = xb[(int64_t)c * x_ld + t];
+    }
+    __syncthreads();
+    T *out = a + (int64_t)blockIdx.x * PC;
+    for (int i = threadIdx.x; i < PC; i += blockDim.x) out[i] = from_f32<T>(tile[i]);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// tok[b,0,:] = cls + pos[0];  tok[b,1+w,:] = e[b*n+w,:] + pos[1+w,:]
+template <typename T>
+__global__ void embed_assemble_kernel(const T *__restrict__ e, const float *__restrict__ cls,
+                                      const float *__restrict__ pos, T *__restrict__ tok, int B, int n_patch, int d) {
+    const int N = n_patch + 1;
+    const int vec_per_row = d / 8;
+    const int64_t total = (int64_t)B * N * vec_per_row;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % vec_per_row) * 8;
+        const int64_t r = i / vec_per_row;
+        const int j = (int)(r % N);
+        const int64_t b = r / N;
+        float v[8], p[8];
+        load8(pos + (int64_t)j * d + c, p);
+        if (j == 0) load8(cls + c, v);
+        else load8(e + (b * n_patch + (j - 1)) * d + c, v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] += p[k];
+        store8(tok + r * d + c, v);
+    }
+}
+
+// backward: one CTA column-slab per token position j; each thread owns one column and walks the batch.
+template <typename T>
+__global__ void embed_assemble_bwd_kernel(const T *__restrict__ dtok, T *__restrict__ de, float *__restrict__ dcls,
+                                          float *__restrict__ dpos, float *__restrict__ dbias, int B, int n_patch,
+                                          int d) {
+    const int N = n_patch + 1;
+    const int j = blockIdx.x;
+    const int col = blockIdx.y * blockDim.x + threadIdx.x;
+    if (col >= d) return;
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) {
+        const T g = dtok[((int64_t)b * N + j) * d + col];
+        s += to_f32(g);
+        if (j > 0) de[((int64_t)b * n_patch + (j - 1)) * d + col] = g;
+    }
+    dpos[(int64_t)j * d + col] += s;
+    if (j == 0) dcls[col] += s;
+    else atomicAdd(dbias + col, s);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// LayerNorm forward: one warp per row, row kept in registers (d <= 1024, d % 8 == 0)
+constexpr int LN_MAXV = 4;  // 4 x 8 elements per lane
+
+template <typename T>
+__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const T *__restrict__ x, const float *__restrict__ gamma,
+                                                             const float *__restrict__ beta, T *__restrict__ y,
+                                                             float *__restrict__ mean_out, float *__restrict__ rstd_out,
+                                                             int M, int d, float eps) {
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    const float inv_d = 1.0f / (float)d;
+    for (int64_t row = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < M;
+         row += (int64_t)gridDim.x * warps_per_block) {
+        const T *xr = x + row * d;
+        float v[LN_MAXV][8];
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < LN_MAXV; ++i) {
+            const int c = (i * 32 + lane) * 8;
+            if (c < d) {
+                load8(xr + c, v[i]);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) s += v[i][k];
+            }
+        }
+        const float mean = warp_sum(s) * inv_d;
+        float sq = 0.f;
+#pragma unroll
+        for (int i = 0; i < LN_MAXV; ++i) {
+            const int c = (i * 32 + lane) * 8;
+            if (c < d) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { const float t = v[i][k] - mean; sq += t * t; }
+            }
+        }
+        const float rstd = rsqrtf(warp_sum(sq) * inv_d + eps);
+        T *yr = y + row * d;
+#pragma unroll
+        for (int i = 0; i < LN_MAXV; ++i) {
+            const int c = (i * 32 + lane) * 8;
+            if (c < d) {
+                float g[8], b[8], o[8];
+                load8(gamma + c, g);
+                load8(beta + c, b);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) o[k] = fmaf((v[i][k] - mean) * rstd, g[k], b[k]);
+                store8(yr + c, o);
+            }
+        }
+        if (lane == 0) {
+            if (mean_out) mean_out[row] = mean;
+            if (rstd_out) rstd_out[row] = rstd;
+        }
+    }
+}
+
+// LayerNorm backward (+ residual-gradient add, + column sums of the result for the bias gradient upstream)
+template <typename T>
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const T *__restrict__ dy, const T *__restrict__ x,
+                                                             const float *__restrict__ gamma,
+                                                             const float *__restrict__ mean_in,
+                                                             const float *__restrict__ rstd_in, const T *dres, T *dx,
+                                                             float *__restrict__ dgamma, float *__restrict__ dbeta,
+                                                             float *__restrict__ dcolsum, int M, int d) {
+    extern __shared__ float red[];  // [3][d]
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int warps_per_block = blockDim.x >> 5;
+    const float inv_d = 1.0f / (float)d;
+
+    float acc_g[LN_MAXV][8], acc_b[LN_MAXV][8], acc_c[LN_MAXV][8], gam[LN_MAXV][8];
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+        const int c = (i * 32 + lane) * 8;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { acc_g[i][k] = 0.f; acc_b[i][k] = 0.f; acc_c[i][k] = 0.f; gam[i][k] = 0.f; }
+        if (c < d) load8(gamma + c, gam[i]);
+    }
+    for (int i = threadIdx.x; i < 3 * d; i += blockDim.x) red[i] = 0.f;
+    __syncthreads();
+
+    for (int64_t row = (int64_t)blockIdx.x * warps_per_block + warp; row < M;
+         row += (int64_t)gridDim.x * warps_per_block) {
+        const float mean = mean_in[row], rstd = rstd_in[row];
+        float g[LN_MAXV][8], xh[LN_MAXV][8];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < LN_MAXV; ++i) {
+            const int c = (i * 32 + lane) * 8;
+            if (c < d) {
+                float dyv[8], xv[8];
+                load8(dy + row * d + c, dyv);
+                load8(x + row * d + c, xv);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    xh[i][k] = (xv[k] - mean) * rstd;
+                    g[i][k] = dyv[k] * gam[i][k];
+                    s1 += g[i][k];
+                    s2 = fmaf(g[i][k], xh[i][k], s2);
+                    acc_g[i][k] = fmaf(dyv[k], xh[i][k], acc_g[i][k]);
+                    acc_b[i][k] += dyv[k];
+                }
+            }
+        }
+        s1 = warp_sum(s1) * inv_d;
+        s2 = warp_sum(s2) * inv_d;
+#pragma unroll
+        for (int i = 0; i < LN_MAXV; ++i) {
+            const int c = (i * 32 + lane) * 8;
+            if (c < d) {
+                float o[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) o[k] = rstd * (g[i][k] - s1 - xh[i][k] * s2);
+                if (dres != nullptr) {
+                    float r[8];
+                    load8(dres + row * d + c, r);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) o[k] += r[k];
+                }
+                store8(dx + row * d + c, o);
+                if (dcolsum != nullptr) {
+                    // sum what downstream kernels will read (the rounded value in bf16 mode)
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) acc_c[i][k] += to_f32(from_f32<T>(o[k]));
+                }
+            }
+        }
+    }
+    // block reduce through shared memory, then one atomic per column per CTA
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+        const int c = (i * 32 + lane) * 8;
+        if (c < d) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                atomicAdd(&red[c + k], acc_g[i][k]);
+                atomicAdd(&red[d + c + k], acc_b[i][k]);
+                if (dcolsum != nullptr) atomicAdd(&red[2 * d + c + k], acc_c[i][k]);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < d; i += blockDim.x) {
+        atomicAdd(dgamma + i, red[i]);
+        atomicAdd(dbeta + i, red[d + i]);
+        if (dcolsum != nullptr) atomicAdd(dcolsum + i, red[2 * d + i]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// out[n] += sum_m x[m, n]; block = 32 column-vectors (8 wide) x 8 row lanes; grid.y splits the rows
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T *__restrict__ x, float *__restrict__ out, int M, int N,
+                                                      int64_t ld, int rows_per_block) {
+    __shared__ float red[8][32 * 8 + 1];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = (blockIdx.x * 32 + tx) * 8;
+    const int r0 = blockIdx.y * rows_per_block;
+    const int r1 = min(r0 + rows_per_block, M);
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    if (c < N) {
+        for (int r = r0 + ty; r < r1; r += 8) {
+            float v[8];
+            load8(x + (int64_t)r * ld + c, v);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] += v[k];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) red[ty][tx * 8 + k] = acc[k];
+    __syncthreads();
+    const int col_local = threadIdx.x;  // 256 columns per block
+    float s = 0.f;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) s += red[y][col_local];
+    const int col = blockIdx.x * 256 + col_local;
+    if (col < N) atomicAdd(out + col, s);
+}
+
+__global__ void cast_f32_bf16_kernel(const float *__restrict__ src, bf16 *__restrict__ dst, int64_t n) {
+    const int64_t n8 = n / 8;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+        float v[8];
+        load8(src + i * 8, v);
+        store8(dst + i * 8, v);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (int64_t i = n8 * 8; i < n; ++i) dst[i] = __float2bfloat16_rn(src[i]);
+}
+
+inline int grid_for(int64_t work_items, int threads, int max_blocks_per_sm = 8) {
+    int64_t g = (work_items + threads - 1) / threads;
+    const int64_t cap = (int64_t)sm_count() * max_blocks_per_sm;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+}  // namespace
+}  // namespace ecgvit
+
+using namespace ecgvit;
+
+extern "C" {
+
+int ecgvit_patchify(const float *x, void *a, int B, int C, int64_t x_ld, int n_patch, int P, int dtype,
+                    void *stream) {
+    ECGVIT_REQUIRE(x && a && B > 0 && C > 0 && n_patch > 0 && P > 0, "patchify: bad arguments");
+    ECGVIT_REQUIRE(x_ld >= (int64_t)n_patch * P, "patchify: x_ld=%lld shorter than n_patch*P=%d", (long long)x_ld,
+                   n_patch * P);
+    const size_t smem = (size_t)P * C * sizeof(float);
+    ECGVIT_REQUIRE(smem <= 48 * 1024, "patchify: patch of %d x %d elements exceeds 48 KB staging", P, C);
+    const int grid = B * n_patch;
+    if (dtype == ECGVIT_BF16)
+        patchify_kernel<bf16><<<grid, 256, smem, as_stream(stream)>>>(x, (bf16 *)a, C, x_ld, n_patch, P);
+    else if (dtype == ECGVIT_F32)
+        patchify_kernel<float><<<grid, 256, smem, as_stream(stream)>>>(x, (float *)a, C, x_ld, n_patch, P);
+    else return fail(-1, "patchify: unknown dtype %d", dtype);
+    return check_launch("patchify");
+}
+
+int ecgvit_embed_assemble(const void *e, const float *cls, const float *pos, void *tok, int B, int n_patch, int d,
+                          int dtype, void *stream) {
+    ECGVIT_REQUIRE(e && cls && pos && tok && B > 0 && n_patch > 0, "embed_assemble: bad arguments");
+    ECGVIT_REQUIRE(d % 8 == 0, "embed_assemble: d=%d must be a multiple of 8", d);
+    const int64_t total = (int64_t)B * (n_patch + 1) * (d / 8);
+    const int grid = grid_for(total, 256);
+    if (dtype == ECGVIT_BF16)
+        embed_assemble_kernel<bf16><<<grid, 256, 0, as_stream(stream)>>>((const bf16 *)e, cls, pos, (bf16 *)tok, B, n_patch, d);
+    else if (dtype == ECGVIT_F32)
+        embed_assemble_kernel<float><<<grid, 256, 0, as_stream(stream)>>>((const float *)e, cls, pos, (float *)tok, B, n_patch, d);
+    else return fail(-1, "embed_assemble: unknown dtype %d", dtype);
+    return check_launch("embed_assemble");
+}
+
+int ecgvit_embed_assemble_bwd(const void *dtok, void *de, float *dcls, float *dpos, float *dbias, int B,
+                              int n_patch, int d, int dtype, void *stream) {
+    ECGVIT_REQUIRE(dtok && de && dcls && dpos && dbias && B > 0 && n_patch > 0 && d > 0, "embed_assemble_bwd: bad arguments");
+    dim3 grid(n_patch + 1, (d + 127) / 128);
+    if (dtype == ECGVIT_BF16)
+        embed_assemble_bwd_kernel<bf16><<<grid, 128, 0, as_stream(stream)>>>((const bf16 *)dtok, (bf16 *)de, dcls, dpos, dbias, B, n_patch, d);
+    else if (dtype == ECGVIT_F32)
+        embed_assemble_bwd_kernel<float><<<grid, 128, 0, as_stream(stream)>>>((const float *)dtok, (float *)de, dcls, dpos, dbias, B, n_patch, d);
+    else return fail(-1, "embed_assemble_bwd: unknown dtype %d", dtype);
+    return check_launch("embed_assemble_bwd");
+}
+
+int ecgvit_layernorm_fwd(const void *x, const float *gamma, const float *beta, void *y, float *mean, float *rstd,
+                         int M, int d, float eps, int dtype, void *stream) {
+    ECGVIT_REQUIRE(x && gamma && beta && y && M > 0, "layernorm_fwd: bad arguments");
+    ECGVIT_REQUIRE(d % 8 == 0 && d <= 8 * 32 * LN_MAXV, "layernorm_fwd: d=%d must be a multiple of 8 and <= %d", d,
+                   8 * 32 * LN_MAXV);
+    const int grid = grid_for((int64_t)M * 32, 256);
+    if (dtype == ECGVIT_BF16)
+        layernorm_fwd_kernel<bf16><<<grid, 256, 0, as_stream(stream)>>>((const bf16 *)x, gamma, beta, (bf16 *)y, mean, rstd, M, d, eps);
+    else if (dtype == ECGVIT_F32)
+        layernorm_fwd_kernel<float><<<grid, 256, 0, as_stream(stream)>>>((const float *)x, gamma, beta, (float *)y, mean, rstd, M, d, eps);
+    else return fail(-1, "layernorm_fwd: unknown dtype %d", dtype);
+    return check_launch("layernorm_fwd");
+}
+
+int ecgvit_layernorm_bwd(const void *dy, const void *x, const float *gamma, const float *mean, const float *rstd,
+                         const void *dres, void *dx, float *dgamma, float *dbeta, float *dcolsum, int M, int d,
+                         int dtype, void *stream) {
+    ECGVIT_REQUIRE(dy && x && gamma && mean && rstd && dx && dgamma && dbeta && M > 0, "layernorm_bwd: bad arguments");
+    ECGVIT_REQUIRE(d % 8 == 0 && d <= 8 * 32 * LN_MAXV, "layernorm_bwd: d=%d must be a multiple of 8 and <= %d", d,
+                   8 * 32 * LN_MAXV);
+    const int grid = grid_for((int64_t)M * 32, 256, 2);
+    const size_t smem = 3 * (size_t)d * sizeof(float);
+    if (dtype == ECGVIT_BF16)
+        layernorm_bwd_kernel<bf16><<<grid, 256, smem, as_stream(stream)>>>((const bf16 *)dy, (const bf16 *)x, gamma, mean, rstd, (const bf16 *)dres, (bf16 *)dx, dgamma, dbeta, dcolsum, M, d);
+    else if (dtype == ECGVIT_F32)
+        layernorm_bwd_kernel<float><<<grid, 256, smem, as_stream(stream)>>>((const float *)dy, (const float *)x, gamma, mean, rstd, (const float *)dres, (float *)dx, dgamma, dbeta, dcolsum, M, d);
+    else return fail(-1, "layernorm_bwd: unknown dtype %d", dtype);
+    return check_launch("layernorm_bwd");
+}
+
+int ecgvit_colsum(const void *x, float *out, int M, int N, int64_t ld, int dtype, void *stream) {
+    ECGVIT_REQUIRE(x && out && M > 0 && N > 0, "colsum: bad arguments");
+    ECGVIT_REQUIRE(N % 8 == 0 && ld % 8 == 0, "colsum: N=%d and ld=%lld must be multiples of 8", N, (long long)ld);
+    const int col_blocks = (N + 255) / 256;
+    int row_blocks = (sm_count() * 4 + col_blocks - 1) / col_blocks;
+    if (row_blocks > (M + 63) / 64) row_blocks = (M + 63) / 64;
+    if (row_blocks < 1) row_blocks = 1;
+    const int rows_per_block = (M + row_blocks - 1) / row_blocks;
+    dim3 grid(col_blocks, (M + rows_per_block - 1) / rows_per_block);
+    if (dtype == ECGVIT_BF16)
+        colsum_kernel<bf16><<<grid, 256, 0, as_stream(stream)>>>((const bf16 *)x, out, M, N, ld, rows_per_block);
+    else if (dtype == ECGVIT_F32)
+        colsum_kernel<float><<<grid, 256, 0, as_stream(stream)>>>((const float *)x, out, M, N, ld, rows_per_block);
+    else return fail(-1, "colsum: unknown dtype %d", dtype);
+    return check_launch("colsum");
+}
+
+int ecgvit_cast_f32_to_bf16(const float *src, void *dst, int64_t n, void *stream) {
+    ECGVIT_REQUIRE(src && dst && n >= 0, "cast: bad arguments");
+    if (n == 0) return 0;
+    const int grid = grid_for(n / 8 + 1, 256);
+    cast_f32_bf16_kernel<<<grid, 256, 0, as_stream(stream)>>>(src, (bf16 *)dst, n);
+    return check_launch("cast_f32_to_bf16");
+}
+
+}  // extern "C"

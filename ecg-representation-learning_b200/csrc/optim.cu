@@ -1,0 +1,149 @@
+// Fused global-norm gradient clipping + AdamW over FLAT fp32 buffers (all 140 parameter tensors of the model
+// live in one contiguous allocation, so "multi-tensor" is a single launch).
+// Replaces nn.utils.clip_grad_norm_(params, 1.0, error_if_nonfinite=True) (~300 launches) and
+// torch.optim.AdamW.step (~1.1 k launches) of /root/reference/ecg_transformer/models/train.py:281-282.
+// HBM-bound: 28 B/param algorithmic (p, m, v read+write, g read) + 2 B/param for the bf16 weight shadow.
+#include "common.cuh"
+
+namespace ecgvit {
+
+namespace {
+
+enum { H_LR = 0, H_BETA1, H_BETA2, H_EPS, H_WD, H_BC1, H_BC2, H_MAXNORM, H_GSCALE };
+enum { S_SUMSQ = 0, S_NONFINITE, S_NORM };
+
+__global__ void __launch_bounds__(256) grad_sumsq_kernel(const float *__restrict__ g, int64_t n,
+                                                          const float *__restrict__ hyper, float *__restrict__ stats) {
+    __shared__ float red[8];
+    const float gs = hyper[H_GSCALE];
+    const int64_t n4 = n / 4;
+    float s = 0.f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(g) + i);
+        const float a = v.x * gs, b = v.y * gs, c = v.z * gs, d = v.w * gs;
+        s = fmaf(a, a, s); s = fmaf(b, b, s); s = fmaf(c, c, s); s = fmaf(d, d, s);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (int64_t i = n4 * 4; i < n; ++i) { const float a = g[i] * gs; s = fmaf(a, a, s); }
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float t = threadIdx.x < 8 ? red[threadIdx.x] : 0.f;
+        t = warp_sum(t);
+        if (threadIdx.x == 0) {
+            atomicAdd(&stats[S_SUMSQ], t);
+            if (!isfinite(t)) stats[S_NONFINITE] = 1.0f;
+        }
+    }
+}
+
+__device__ __forceinline__ float clip_coef_from(const float *hyper, const float *stats, float &total_norm) {
+    total_norm = sqrtf(stats[S_SUMSQ]);
+    const float max_norm = hyper[H_MAXNORM];
+    if (max_norm <= 0.f) return 1.0f;
+    return fminf(max_norm / (total_norm + 1e-6f), 1.0f);
+}
+
+template <bool kShadow>
+__global__ void __launch_bounds__(256) adamw_kernel(float *__restrict__ p, float *__restrict__ m,
+                                                     float *__restrict__ v, const float *__restrict__ g,
+                                                     bf16 *__restrict__ shadow, int64_t n,
+                                                     const float *__restrict__ hyper, float *__restrict__ stats) {
+    float total_norm;
+    const float clip = clip_coef_from(hyper, stats, total_norm);
+    if (blockIdx.x == 0 && threadIdx.x == 0) stats[S_NORM] = total_norm;
+    // error_if_nonfinite: leave parameters and state untouched; the host raises when it polls the flag
+    if (!isfinite(total_norm)) return;
+    const float lr = hyper[H_LR], beta1 = hyper[H_BETA1], beta2 = hyper[H_BETA2], eps = hyper[H_EPS];
+    const float decay = 1.0f - lr * hyper[H_WD];
+    const float step_size = lr / hyper[H_BC1];
+    const float inv_bc2_sqrt = 1.0f / sqrtf(hyper[H_BC2]);
+    const float gmul = hyper[H_GSCALE] * clip;
+    const int64_t n4 = n / 4;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 g4 = __ldg(reinterpret_cast<const float4 *>(g) + i);
+        float4 p4 = reinterpret_cast<float4 *>(p)[i], m4 = reinterpret_cast<float4 *>(m)[i],
+               v4 = reinterpret_cast<float4 *>(v)[i];
+        float pp[4] = {p4.x, p4.y, p4.z, p4.w}, mm[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
+        const float gg[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float gr = gg[k] * gmul;
+            pp[k] *= decay;
+            mm[k] = fmaf(gr - mm[k], 1.0f - beta1, mm[k]);
+            vv[k] = fmaf(vv[k], beta2, (1.0f - beta2) * gr * gr);
+            const float denom = sqrtf(vv[k]) * inv_bc2_sqrt + eps;
+            pp[k] -= step_size * (mm[k] / denom);
+        }
+        reinterpret_cast<float4 *>(p)[i] = make_float4(pp[0], pp[1], pp[2], pp[3]);
+        reinterpret_cast<float4 *>(m)[i] = make_float4(mm[0], mm[1], mm[2], mm[3]);
+        reinterpret_cast<float4 *>(v)[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+        if (kShadow) {
+            uint2 u;
+            u.x = pack_bf16x2(pp[0], pp[1]);
+            u.y = pack_bf16x2(pp[2], pp[3]);
+            reinterpret_cast<uint2 *>(shadow)[i] = u;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) grad_scale_kernel(float *__restrict__ g, int64_t n,
+                                                          const float *__restrict__ hyper, float *__restrict__ stats) {
+    float total_norm;
+    const float mul = clip_coef_from(hyper, stats, total_norm) * hyper[H_GSCALE];
+    if (blockIdx.x == 0 && threadIdx.x == 0) stats[S_NORM] = total_norm;
+    if (!isfinite(total_norm) || mul == 1.0f) return;
+    const int64_t n4 = n / 4;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 v = reinterpret_cast<float4 *>(g)[i];
+        v.x *= mul; v.y *= mul; v.z *= mul; v.w *= mul;
+        reinterpret_cast<float4 *>(g)[i] = v;
+    }
+}
+
+inline int flat_grid(int64_t n) {
+    int64_t blocks = (n / 4 + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+}  // namespace
+}  // namespace ecgvit
+
+using namespace ecgvit;
+
+extern "C" {
+
+int ecgvit_grad_sumsq(const float *g, int64_t n, const float *hyper, float *stats, void *stream) {
+    ECGVIT_REQUIRE(g && hyper && stats && n > 0, "grad_sumsq: bad arguments");
+    ECGVIT_REQUIRE((reinterpret_cast<uintptr_t>(g) & 15) == 0, "grad_sumsq: g must be 16-byte aligned");
+    cudaError_t e = cudaMemsetAsync(stats, 0, 4 * sizeof(float), as_stream(stream));
+    if (e != cudaSuccess) return fail((int)e, "grad_sumsq: memset: %s", cudaGetErrorString(e));
+    grad_sumsq_kernel<<<flat_grid(n), 256, 0, as_stream(stream)>>>(g, n, hyper, stats);
+    return check_launch("grad_sumsq");
+}
+
+int ecgvit_adamw_step(float *p, float *m, float *v, const float *g, void *shadow_bf16, int64_t n,
+                      const float *hyper, float *stats, void *stream) {
+    ECGVIT_REQUIRE(p && m && v && g && hyper && stats && n > 0, "adamw_step: bad arguments");
+    ECGVIT_REQUIRE(n % 4 == 0, "adamw_step: flat length %lld must be a multiple of 4 (pad the flat buffer)", (long long)n);
+    ECGVIT_REQUIRE(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v) |
+                     reinterpret_cast<uintptr_t>(g)) & 15) == 0,
+                   "adamw_step: buffers must be 16-byte aligned");
+    if (shadow_bf16 != nullptr)
+        adamw_kernel<true><<<flat_grid(n), 256, 0, as_stream(stream)>>>(p, m, v, g, (bf16 *)shadow_bf16, n, hyper, stats);
+    else
+        adamw_kernel<false><<<flat_grid(n), 256, 0, as_stream(stream)>>>(p, m, v, g, nullptr, n, hyper, stats);
+    return check_launch("adamw_step");
+}
+
+int ecgvit_grad_scale_by_clip(float *g, int64_t n, const float *hyper, float *stats, void *stream) {
+    ECGVIT_REQUIRE(g && hyper && stats && n > 0 && n % 4 == 0, "grad_scale_by_clip: bad arguments");
+    grad_scale_kernel<<<flat_grid(n), 256, 0, as_stream(stream)>>>(g, n, hyper, stats);
+    return check_launch("grad_scale_by_clip");
+}
+
+}  // extern "C"

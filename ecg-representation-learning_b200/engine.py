@@ -1,0 +1,226 @@
+"""
+Step engine: owns the HBM workspaces of one (batch, length) shape and issues the kernel sequence of the
+ECG-ViT forward / backward / clip+AdamW through the C ABI (include/ecgvit_b200.h).
+
+Data layout in HBM (T = bf16 in performance mode, fp32 in parity mode; M = B * (n_patch + 1) token rows):
+  parameters / gradients / AdamW moments : three flat fp32 buffers, tensors at 256-byte aligned offsets
+  weight shadow                          : flat bf16 copy of the parameters (GEMM operands), written by AdamW
+  a_patch  [B*n_patch, P*C]  T           : gathered patches, time-major / lead-minor features
+  per layer: x_in [M,d], ln1 [M,d], qkv [M,3*inner], lse [B,H,N] f32, o [M,inner], y [M,d], ln2 [M,d],
+             u [M,mlp] (pre-GELU), h [M,mlp] (post-GELU), row statistics (mean, rstd) f32
+  backward scratch (shared by all layers): dres0/dres1 [M,d], dln [M,d], d_o [M,inner], dqkv [M,3*inner], du [M,mlp]
+Everything is row-major with the feature dimension contiguous, so every GEMM operand is either K-major or
+MN-major for TMA without a transposed copy.
+
+Reference semantics: forward = vit_pytorch.ViT.forward via ecg_vit.py:140-149; backward = autograd of it
+(train.py:280); optimizer = train.py:281-282.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import GemmArgs, F32, BF16, EPI_STORE, EPI_BIAS_RES, EPI_BIAS_GELU, EPI_DGELU, EPI_ATOMIC_F32
+
+LN_EPS = 1e-5  # nn.LayerNorm default
+
+
+class _Workspace:
+    pass
+
+
+class StepEngine:
+    def __init__(self, model):
+        self.model = model
+        self.lib = _lib.load()
+        self.ws = {}
+        self._cur = None
+
+    # ---- helpers ---------------------------------------------------------------------------------
+    @property
+    def _stream(self):
+        return torch.cuda.current_stream().cuda_stream
+
+    def _gemm(self, M, N, K, A, lda, a_k, B, ldb, b_k, epi, out, ldo, out2=None, aux=None, bias=None, split_k=1):
+        g = GemmArgs(M, N, K, A.data_ptr(), lda, a_k, B.data_ptr(), ldb, b_k, epi, out.data_ptr(), ldo,
+                     _lib.ptr(out2), _lib.ptr(aux), _lib.ptr(bias), self.model._dtype_code, split_k, 0)
+        _lib.check(self.lib.ecgvit_gemm(ctypes.byref(g), self._stream), 'gemm')
+
+    def workspace(self, B, L):
+        key = (B, L)
+        w = self.ws.get(key)
+        if w is not None:
+            return w
+        m = self.model
+        c = m.config
+        dev = m._flat_p.device
+        T = m._act_dtype
+        P, C, d, mlp = c.patch_size, c.num_channels, c.hidden_size, c.intermediate_size
+        H = c.num_attention_heads
+        inner = d  # dim_head = d // heads (ecg_vit.py:100)
+        assert L % P == 0, f'signal length {L} must be a multiple of patch_size {P}'
+        n = L // P
+        assert n + 1 <= m.vit.pos_embedding.shape[1], \
+            f'{n} patches exceed the positional table ({m.vit.pos_embedding.shape[1] - 1})'
+        N = n + 1
+        M = B * N
+        depth = c.num_hidden_layers
+        w = _Workspace()
+        w.B, w.L, w.n, w.N, w.M = B, L, n, N, M
+
+        def buf(*shape, dtype=T):
+            return torch.empty(*shape, device=dev, dtype=dtype)
+
+        w.a_patch = buf(B * n, P * C)
+        w.e = buf(B * n, d)
+        w.x = [buf(M, d) for _ in range(depth + 1)]  # x[l] = input of block l; x[depth] = encoder output
+        w.ln1 = [buf(M, d) for _ in range(depth)]
+        w.ln2 = [buf(M, d) for _ in range(depth)]
+        w.stat1 = [buf(2, M, dtype=torch.float32) for _ in range(depth)]
+        w.stat2 = [buf(2, M, dtype=torch.float32) for _ in range(depth)]
+        w.qkv = [buf(M, 3 * inner) for _ in range(depth)]
+        w.lse = [buf(B, H, N, dtype=torch.float32) for _ in range(depth)]
+        w.o = [buf(M, inner) for _ in range(depth)]
+        w.y = [buf(M, d) for _ in range(depth)]
+        w.u = [buf(M, mlp) for _ in range(depth)]
+        w.h = [buf(M, mlp) for _ in range(depth)]
+        # head
+        n_class = m.num_class
+        w.xn = buf(B, d, dtype=torch.float32)
+        w.hstat = buf(2, B, dtype=torch.float32)
+        w.logits = buf(B, n_class, dtype=torch.float32)
+        w.loss = buf(1, dtype=torch.float32)
+        w.loss_none = buf(B, n_class, dtype=torch.float32)
+        w.head_scratch = buf(B * d + B * n_class, dtype=torch.float32)
+        w.labels = buf(B, n_class, dtype=torch.float32)
+        # backward scratch
+        w.dres = [buf(M, d), buf(M, d)]
+        w.dln = buf(M, d)
+        w.d_o = buf(M, inner)
+        w.dqkv = buf(M, 3 * inner)
+        w.du = buf(M, mlp)
+        w.de = buf(B * n, d)
+        self.ws[key] = w
+        return w
+
+    # ---- forward ---------------------------------------------------------------------------------
+    def forward(self, sample_values, labels=None, reduction='mean'):
+        """sample_values: fp32 cuda [B, C, L]; returns (loss | None, logits) as views of workspace buffers."""
+        m, lib, st = self.model, self.lib, self._stream
+        c = m.config
+        dt = m._dtype_code
+        x = sample_values
+        assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 3, 'sample_values must be fp32 cuda [B, C, L]'
+        assert x.shape[1] == c.num_channels
+        if x.stride(2) != 1 or x.stride(0) != x.shape[1] * x.stride(1):
+            x = x.contiguous()
+        B, C, L = x.shape
+        w = self.workspace(B, L)
+        self._cur = w
+        P, d, mlp, H = c.patch_size, c.hidden_size, c.intermediate_size, c.num_attention_heads
+        inner, dh = d, d // H
+        n, N, M = w.n, w.N, w.M
+        wt = m._weights()  # GEMM operand views (bf16 shadow or fp32 master)
+        pf = m._params_f32()  # fp32 master views (biases, LayerNorm, cls, pos, head)
+
+        _lib.check(lib.ecgvit_patchify(x.data_ptr(), w.a_patch.data_ptr(), B, C, x.stride(1), n, P, dt, st), 'patchify')
+        # e = a_patch @ We^T + be
+        self._gemm(B * n, d, P * C, w.a_patch, P * C, 1, wt['embed.w'], P * C, 1, EPI_STORE, w.e, d,
+                   bias=pf['embed.b'])
+        _lib.check(lib.ecgvit_embed_assemble(w.e.data_ptr(), pf['cls'].data_ptr(), pf['pos'].data_ptr(),
+                                             w.x[0].data_ptr(), B, n, d, dt, st), 'embed_assemble')
+        scale = float(dh) ** -0.5
+        for l in range(c.num_hidden_layers):
+            p = f'l{l}.'
+            _lib.check(lib.ecgvit_layernorm_fwd(w.x[l].data_ptr(), pf[p + 'ln1.w'].data_ptr(), pf[p + 'ln1.b'].data_ptr(),
+                                                w.ln1[l].data_ptr(), w.stat1[l][0].data_ptr(), w.stat1[l][1].data_ptr(),
+                                                M, d, LN_EPS, dt, st), 'layernorm_fwd')
+            self._gemm(M, 3 * inner, d, w.ln1[l], d, 1, wt[p + 'qkv.w'], d, 1, EPI_STORE, w.qkv[l], 3 * inner)
+            _lib.check(lib.ecgvit_attention_fwd(w.qkv[l].data_ptr(), w.o[l].data_ptr(), w.lse[l].data_ptr(), B, N, H, dh,
+                                                scale, dt, st), 'attention_fwd')
+            self._gemm(M, d, inner, w.o[l], inner, 1, wt[p + 'out.w'], inner, 1, EPI_BIAS_RES, w.y[l], d,
+                       aux=w.x[l], bias=pf[p + 'out.b'])
+            _lib.check(lib.ecgvit_layernorm_fwd(w.y[l].data_ptr(), pf[p + 'ln2.w'].data_ptr(), pf[p + 'ln2.b'].data_ptr(),
+                                                w.ln2[l].data_ptr(), w.stat2[l][0].data_ptr(), w.stat2[l][1].data_ptr(),
+                                                M, d, LN_EPS, dt, st), 'layernorm_fwd')
+            self._gemm(M, mlp, d, w.ln2[l], d, 1, wt[p + 'ff1.w'], d, 1, EPI_BIAS_GELU, w.u[l], mlp,
+                       out2=w.h[l], bias=pf[p + 'ff1.b'])
+            self._gemm(M, d, mlp, w.h[l], mlp, 1, wt[p + 'ff2.w'], mlp, 1, EPI_BIAS_RES, w.x[l + 1], d,
+                       aux=w.y[l], bias=pf[p + 'ff2.b'])
+        red = _lib.REDUCTION[reduction]
+        loss_buf = None
+        if labels is not None:
+            assert labels.shape == (B, m.num_class)
+            w.labels.copy_(labels, non_blocking=True)  # also casts (the reference passes float multi-hot)
+            loss_buf = w.loss_none if reduction == 'none' else w.loss
+        _lib.check(lib.ecgvit_head_fwd(
+            w.x[c.num_hidden_layers].data_ptr(), pf['head.ln.w'].data_ptr(), pf['head.ln.b'].data_ptr(),
+            pf['head.w'].data_ptr(), pf['head.b'].data_ptr(), w.labels.data_ptr() if labels is not None else None,
+            w.xn.data_ptr(), w.hstat[0].data_ptr(), w.hstat[1].data_ptr(), w.logits.data_ptr(),
+            _lib.ptr(loss_buf), B, N, d, m.num_class, red, LN_EPS, dt, st), 'head_fwd')
+        w.reduction = reduction
+        loss = None
+        if labels is not None:
+            loss = w.loss_none if reduction == 'none' else w.loss[0]
+        return loss, w.logits
+
+    # ---- backward --------------------------------------------------------------------------------
+    def backward(self, grad_scale=1.0, zero_grads=True):
+        """Gradients of the last forward's loss w.r.t. every parameter, accumulated into the flat grad buffer."""
+        m, lib, st = self.model, self.lib, self._stream
+        c = m.config
+        dt = m._dtype_code
+        w = self._cur
+        assert w is not None, 'backward before forward'
+        assert w.reduction in ('mean', 'sum'), "backward needs loss_reduction 'mean' or 'sum'"
+        B, n, N, M = w.B, w.n, w.N, w.M
+        P, C, d, mlp, H = c.patch_size, c.num_channels, c.hidden_size, c.intermediate_size, c.num_attention_heads
+        inner, dh = d, d // H
+        depth = c.num_hidden_layers
+        wt, pf, gr = m._weights(), m._params_f32(), m._grads_f32()
+        if zero_grads:
+            m._flat_g.zero_()
+        dz, dy = w.dres[0], w.dres[1]
+        last = f'l{depth - 1}.'
+        _lib.check(lib.ecgvit_head_bwd(
+            w.x[depth].data_ptr(), pf['head.ln.w'].data_ptr(), pf['head.w'].data_ptr(), w.labels.data_ptr(),
+            w.xn.data_ptr(), w.hstat[0].data_ptr(), w.hstat[1].data_ptr(), w.logits.data_ptr(), dz.data_ptr(),
+            gr['head.w'].data_ptr(), gr['head.b'].data_ptr(), gr['head.ln.w'].data_ptr(), gr['head.ln.b'].data_ptr(),
+            gr[last + 'ff2.b'].data_ptr(), w.head_scratch.data_ptr(), B, N, d, m.num_class,
+            _lib.REDUCTION[w.reduction], float(grad_scale), dt, st), 'head_bwd')
+        scale = float(dh) ** -0.5
+        for l in range(depth - 1, -1, -1):
+            p = f'l{l}.'
+            # ---- feed-forward branch: x[l+1] = y + W2 gelu(W1 ln2(y) + b1) + b2
+            self._gemm(d, mlp, M, dz, d, 0, w.h[l], mlp, 0, EPI_ATOMIC_F32, gr[p + 'ff2.w'], mlp, split_k=0)
+            self._gemm(M, mlp, d, dz, d, 1, wt[p + 'ff2.w'], mlp, 0, EPI_DGELU, w.du, mlp, aux=w.u[l])
+            _lib.check(lib.ecgvit_colsum(w.du.data_ptr(), gr[p + 'ff1.b'].data_ptr(), M, mlp, mlp, dt, st), 'colsum')
+            self._gemm(mlp, d, M, w.du, mlp, 0, w.ln2[l], d, 0, EPI_ATOMIC_F32, gr[p + 'ff1.w'], d, split_k=0)
+            self._gemm(M, d, mlp, w.du, mlp, 1, wt[p + 'ff1.w'], d, 0, EPI_STORE, w.dln, d)
+            _lib.check(lib.ecgvit_layernorm_bwd(
+                w.dln.data_ptr(), w.y[l].data_ptr(), pf[p + 'ln2.w'].data_ptr(), w.stat2[l][0].data_ptr(),
+                w.stat2[l][1].data_ptr(), dz.data_ptr(), dy.data_ptr(), gr[p + 'ln2.w'].data_ptr(),
+                gr[p + 'ln2.b'].data_ptr(), gr[p + 'out.b'].data_ptr(), M, d, dt, st), 'layernorm_bwd')
+            # ---- attention branch: y = x + Wo attn(Wqkv ln1(x)) + bo
+            self._gemm(d, inner, M, dy, d, 0, w.o[l], inner, 0, EPI_ATOMIC_F32, gr[p + 'out.w'], inner, split_k=0)
+            self._gemm(M, inner, d, dy, d, 1, wt[p + 'out.w'], inner, 0, EPI_STORE, w.d_o, inner)
+            _lib.check(lib.ecgvit_attention_bwd(w.qkv[l].data_ptr(), w.o[l].data_ptr(), w.d_o.data_ptr(),
+                                                w.lse[l].data_ptr(), w.dqkv.data_ptr(), B, N, H, dh, scale, dt, st),
+                       'attention_bwd')
+            self._gemm(3 * inner, d, M, w.dqkv, 3 * inner, 0, w.ln1[l], d, 0, EPI_ATOMIC_F32, gr[p + 'qkv.w'], d,
+                       split_k=0)
+            self._gemm(M, d, 3 * inner, w.dqkv, 3 * inner, 1, wt[p + 'qkv.w'], d, 0, EPI_STORE, w.dln, d)
+            below_bias = gr[f'l{l - 1}.ff2.b'] if l > 0 else None
+            _lib.check(lib.ecgvit_layernorm_bwd(
+                w.dln.data_ptr(), w.x[l].data_ptr(), pf[p + 'ln1.w'].data_ptr(), w.stat1[l][0].data_ptr(),
+                w.stat1[l][1].data_ptr(), dy.data_ptr(), dz.data_ptr(), gr[p + 'ln1.w'].data_ptr(),
+                gr[p + 'ln1.b'].data_ptr(), _lib.ptr(below_bias), M, d, dt, st), 'layernorm_bwd')
+            if m._after_layer_backward is not None:
+                m._after_layer_backward(l)
+        # ---- embedding: tok = [cls | a_patch We^T + be] + pos
+        _lib.check(lib.ecgvit_embed_assemble_bwd(dz.data_ptr(), w.de.data_ptr(), gr['cls'].data_ptr(),
+                                                 gr['pos'].data_ptr(), gr['embed.b'].data_ptr(), B, n, d, dt, st),
+                   'embed_assemble_bwd')
+        self._gemm(d, P * C, B * n, w.de, d, 0, w.a_patch, P * C, 0, EPI_ATOMIC_F32, gr['embed.w'], P * C, split_k=0)
+        if m._after_layer_backward is not None:
+            m._after_layer_backward(-1)

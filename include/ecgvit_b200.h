@@ -1,0 +1,140 @@
+/*
+ * ecgvit_b200.h -- C ABI of the B200-native ECG-ViT training-step kernels.
+ *
+ * The reference (StefanHeng/ECG-Representation-Learning) has NO plugin / operator / FFI layer
+ * (SURVEY.md 8b): its seam is the Python nn.Module API of `EcgVit`
+ * (ecg_transformer/models/ecg_vit.py:95-149) and the step of `MyTrainer.train`
+ * (ecg_transformer/models/train.py:268-283).  Each entry point below therefore cites the reference
+ * (or un-vendored third-party `vit-pytorch==0.33.2`, requirements.txt:174) op sequence it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes; every pointer is a DEVICE pointer unless stated otherwise;
+ *   - `dtype` selects the activation/operand type: ECGVIT_F32 (parity mode, FFMA contractions) or
+ *     ECGVIT_BF16 (performance mode, tcgen05 contractions, fp32 accumulation and statistics);
+ *   - parameters, optimizer state and gradients are always fp32;
+ *   - the caller owns all memory; nothing is allocated, freed or retained past the call;
+ *   - all work is stream-ordered on `stream` (a cudaStream_t cast to void*), no host sync, graph-capturable;
+ *   - return value: 0 = ok, negative = invalid argument (see ecgvit_last_error), positive = cudaError_t.
+ */
+#ifndef ECGVIT_B200_H
+#define ECGVIT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ECGVIT_ABI_VERSION 1
+
+enum { ECGVIT_F32 = 0, ECGVIT_BF16 = 1 };
+
+/* GEMM epilogues */
+enum {
+    ECGVIT_EPI_STORE = 0,      /* out = acc (+ bias)                                              */
+    ECGVIT_EPI_BIAS_RES = 1,   /* out = acc + bias + aux          (Linear + residual add)         */
+    ECGVIT_EPI_BIAS_GELU = 2,  /* out = acc + bias ; out2 = gelu_erf(out)                         */
+    ECGVIT_EPI_DGELU = 3,      /* out = acc * gelu_erf'(aux)                                      */
+    ECGVIT_EPI_ATOMIC_F32 = 4  /* out(fp32) += acc                (weight gradients, split-K)     */
+};
+
+enum { ECGVIT_REDUCTION_MEAN = 0, ECGVIT_REDUCTION_SUM = 1, ECGVIT_REDUCTION_NONE = 2 };
+
+int ecgvit_abi_version(void);
+/* thread-local message for the last non-zero return of any entry point */
+const char *ecgvit_last_error(void);
+/* 1 when the current device is sm_100 (B200) */
+int ecgvit_device_ok(void);
+
+/* ---- patch embedding: replaces einops Rearrange 'b c (h p1) (w p2) -> b (h w) (p1 p2 c)' of
+ *      vit_pytorch.ViT.to_patch_embedding[0] (call site ecg_vit.py:141).
+ *      a[(b*n_patch + w), t*C + c] = x[b, c, w*P + t]   (bit-exact gather; cast to dtype)
+ *      x is fp32 [B, C, x_ld] (x_ld >= n_patch*P elements per lead). */
+int ecgvit_patchify(const float *x, void *a, int B, int C, int64_t x_ld, int n_patch, int P, int dtype,
+                    void *stream);
+
+/* ---- CLS concat + positional add: replaces torch.cat(cls, x); x += pos_embedding[:, :n+1]
+ *      tok[b,0,:] = cls + pos[0];  tok[b,1+w,:] = e[b*n_patch+w,:] + pos[1+w]  (e already holds the bias) */
+int ecgvit_embed_assemble(const void *e, const float *cls, const float *pos, void *tok, int B, int n_patch,
+                          int d, int dtype, void *stream);
+/* backward of the above: de = dtok[:,1:,:]; dpos += sum_b dtok; dcls += sum_b dtok[:,0]; dbias += sum_{b,w} dtok[:,1:] */
+int ecgvit_embed_assemble_bwd(const void *dtok, void *de, float *dcls, float *dpos, float *dbias, int B,
+                              int n_patch, int d, int dtype, void *stream);
+
+/* ---- nn.LayerNorm(d, eps) forward (PreNorm.norm / mlp_head[0]); saves per-row mean and rstd (fp32) */
+int ecgvit_layernorm_fwd(const void *x, const float *gamma, const float *beta, void *y, float *mean,
+                         float *rstd, int M, int d, float eps, int dtype, void *stream);
+/* backward: dx = (dres ? dres : 0) + LN'(dy); dgamma += ..; dbeta += ..; if dcolsum: dcolsum += colsum(dx) */
+int ecgvit_layernorm_bwd(const void *dy, const void *x, const float *gamma, const float *mean,
+                         const float *rstd, const void *dres, void *dx, float *dgamma, float *dbeta,
+                         float *dcolsum, int M, int d, int dtype, void *stream);
+
+/* ---- dense contraction  C[m,n] = sum_k A(m,k) * B(n,k)  with fused epilogue.
+ *      Replaces nn.Linear forward / its autograd dgrad / wgrad (vit_pytorch Attention.to_qkv, to_out[0],
+ *      FeedForward.net[0], net[3], ViT.to_patch_embedding[1]).
+ *      a_kmajor=1: A stored row-major [M, K] with leading dimension lda (elements); 0: stored [K, M].
+ *      b_kmajor=1: B stored row-major [N, K] with leading dimension ldb;            0: stored [K, N].
+ *      dtype BF16 runs on tcgen05 (TMA-fed, TMEM accumulators); F32 runs on FFMA (parity mode). */
+typedef struct ecgvit_gemm_args {
+    int M, N, K;
+    const void *A;
+    int64_t lda;
+    int a_kmajor;
+    const void *B;
+    int64_t ldb;
+    int b_kmajor;
+    int epilogue;       /* ECGVIT_EPI_* */
+    void *out;
+    int64_t ldo;
+    void *out2;         /* BIAS_GELU: gelu output (same ld as out) */
+    const void *aux;    /* BIAS_RES: residual; DGELU: pre-activation (same ld as out) */
+    const float *bias;  /* fp32 [N] or NULL */
+    int dtype;
+    int split_k;        /* >1 only with ECGVIT_EPI_ATOMIC_F32 */
+    int reserved;
+} ecgvit_gemm_args;
+int ecgvit_gemm(const ecgvit_gemm_args *g, void *stream);
+
+/* ---- softmax attention on the packed projection: replaces chunk(3) + rearrange + q k^T * scale +
+ *      Softmax + attn v + rearrange back (vit_pytorch Attention.forward).
+ *      qkv [B*N, 3*H*dh] (q | k | v, each head-major), o [B*N, H*dh], lse [B, H, N] fp32. */
+int ecgvit_attention_fwd(const void *qkv, void *o, float *lse, int B, int N, int H, int dh, float scale,
+                         int dtype, void *stream);
+int ecgvit_attention_bwd(const void *qkv, const void *o, const void *d_o, const float *lse, void *dqkv,
+                         int B, int N, int H, int dh, float scale, int dtype, void *stream);
+
+/* ---- CLS pool + mlp_head (LayerNorm + Linear(d -> n_class)) + nn.BCEWithLogitsLoss (ecg_vit.py:118,148).
+ *      tok [B*N, d]; logits fp32 [B, n_class]; loss: scalar (mean / sum) or [B, n_class] (none).
+ *      labels may be NULL (logits only).  xn/mean/rstd are saved for backward. */
+int ecgvit_head_fwd(const void *tok, const float *gamma, const float *beta, const float *w, const float *b,
+                    const float *labels, float *xn, float *mean, float *rstd, float *logits, float *loss,
+                    int B, int N, int d, int n_class, int reduction, float eps, int dtype, void *stream);
+/* backward for reduction mean|sum with upstream gradient `grad_scale` (a host scalar, normally 1):
+ *      dlogits = grad_scale * (sigmoid(z) - y) [/ (B*n_class)];  dw += ..; db += ..; dgamma/dbeta += ..;
+ *      dtok is FULLY written: LN' rows at the CLS positions, zeros elsewhere; dcolsum += sum_b dtok[b,0,:] */
+int ecgvit_head_bwd(const void *tok, const float *gamma, const float *w, const float *labels, const float *xn,
+                    const float *mean, const float *rstd, const float *logits, void *dtok, float *dw,
+                    float *db, float *dgamma, float *dbeta, float *dcolsum, float *scratch, int B, int N, int d,
+                    int n_class, int reduction, float grad_scale, int dtype, void *stream);
+
+/* ---- column sum  out[n] += sum_m x[m, n]   (bias gradients) */
+int ecgvit_colsum(const void *x, float *out, int M, int N, int64_t ld, int dtype, void *stream);
+
+/* ---- nn.utils.clip_grad_norm_ (train.py:281) + torch.optim.AdamW.step (train.py:242-244,282) on flat
+ *      fp32 buffers.  hyper (device, fp32[16]):
+ *        [0] lr  [1] beta1  [2] beta2  [3] eps  [4] weight_decay  [5] 1-beta1^t  [6] 1-beta2^t
+ *        [7] max_grad_norm (<=0: no clipping)  [8] grad_scale (1/world for DDP sum-allreduce)
+ *      stats (device, fp32[4]): [0] sum of squares of (grad_scale*g)  [1] non-finite flag  [2] total_norm (written by adamw) */
+int ecgvit_grad_sumsq(const float *g, int64_t n, const float *hyper, float *stats, void *stream);
+int ecgvit_adamw_step(float *p, float *m, float *v, const float *g, void *shadow_bf16, int64_t n,
+                      const float *hyper, float *stats, void *stream);
+/* in-place  g *= clip_coef  for API-compatible clip_grad_norm_ on a flat buffer */
+int ecgvit_grad_scale_by_clip(float *g, int64_t n, const float *hyper, float *stats, void *stream);
+
+/* ---- fp32 -> bf16 cast of a flat buffer (weight shadows) */
+int ecgvit_cast_f32_to_bf16(const float *src, void *dst, int64_t n, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ECGVIT_B200_H */

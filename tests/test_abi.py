@@ -1,0 +1,50 @@
+"""CPU tier: the C-ABI library loads without a GPU and exports every symbol include/ecgvit_b200.h declares."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+
+HEADER = os.path.join(ROOT, 'include', 'ecgvit_b200.h')
+
+
+def _declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    return sorted(set(re.findall(r'\b(ecgvit_[a-z0-9_]+)\s*\(', src)))
+
+
+def test_header_declares_the_expected_surface():
+    syms = _declared_symbols()
+    for s in ('ecgvit_gemm', 'ecgvit_patchify', 'ecgvit_layernorm_fwd', 'ecgvit_layernorm_bwd', 'ecgvit_attention_fwd',
+              'ecgvit_attention_bwd', 'ecgvit_head_fwd', 'ecgvit_head_bwd', 'ecgvit_grad_sumsq', 'ecgvit_adamw_step'):
+        assert s in syms
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    import ecg_b200
+    lib = ecg_b200._lib.load()
+    raw = ctypes.CDLL(ecg_b200._lib.LIB_PATH)
+    for s in _declared_symbols():
+        assert hasattr(raw, s), f'{s} declared in the header but not exported'
+    assert set(_declared_symbols()) == set(ecg_b200._lib.SIGNATURES), 'ctypes table and header disagree'
+    assert lib.ecgvit_abi_version() == 1
+
+
+def test_gemm_args_struct_layout_matches_header():
+    import ecg_b200
+    g = ecg_b200._lib.GemmArgs
+    # int M,N,K | ptr A | i64 lda | int a_kmajor | ptr B | i64 ldb | int b_kmajor, epilogue | ptr out | i64 ldo | 3 ptr | 3 int
+    assert g.A.offset == 16 and g.lda.offset == 24 and g.B.offset == 40 and g.out.offset == 64
+    assert g.bias.offset == 96 and g.dtype.offset == 104 and ctypes.sizeof(g) == 120
+
+
+def test_argument_validation_returns_error_without_touching_the_gpu():
+    import ecg_b200
+    lib = ecg_b200._lib.load()
+    assert lib.ecgvit_gemm(None, None) != 0
+    assert 'null' in ecg_b200._lib.last_error()
+    with pytest.raises(RuntimeError):
+        ecg_b200._lib.check(lib.ecgvit_patchify(None, None, 0, 0, 0, 0, 0, 0, None), 'patchify')

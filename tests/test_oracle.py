@@ -1,0 +1,108 @@
+"""CPU tier: pins the travelling oracle against (a) the committed golden vectors generated through the reference's
+own wrapper and (b), where /root/reference exists, the reference wrapper itself."""
+import numpy as np
+import pytest
+import torch
+from torch import nn
+
+from conftest import GOLDEN_CFG
+from oracle import ref_shim
+from oracle.ecg_vit_oracle import (OracleConfig, OracleEcgVit, OracleTrainer, NAMED_SIZES, lr_lambda, patch_matrix,
+                                   synthetic_batch)
+
+
+def _load_state(model, golden, prefix):
+    sd = {k[len(prefix):]: torch.from_numpy(v) for k, v in golden.items() if k.startswith(prefix)}
+    model.load_state_dict(sd, strict=True)
+
+
+def test_oracle_reproduces_golden_forward_backward(golden):
+    m = OracleEcgVit(config=OracleConfig(**GOLDEN_CFG))
+    _load_state(m, golden, 'init/')
+    m.train()
+    x, y = torch.from_numpy(golden['x']), torch.from_numpy(golden['y'])
+    out = m(sample_values=x, labels=y)
+    out.loss.backward()
+    np.testing.assert_allclose(out.logits.detach().numpy(), golden['logits'], rtol=0, atol=1e-6)
+    assert abs(out.loss.item() - float(golden['loss'])) < 1e-6
+    for k, p in m.named_parameters():
+        np.testing.assert_allclose(p.grad.numpy(), golden['grad/' + k], rtol=0, atol=1e-7)
+
+
+def test_oracle_reproduces_golden_three_steps(golden):
+    m = OracleEcgVit(config=OracleConfig(**GOLDEN_CFG))
+    _load_state(m, golden, 'init/')
+    m.train()
+    x, y = torch.from_numpy(golden['x']), torch.from_numpy(golden['y'])
+    tr = OracleTrainer(m, learning_rate=3e-4, weight_decay=1e-2, schedule='constant', n_warmup=0)
+    for step in (1, 2, 3):
+        loss, _, norm = tr.step(x, y)
+        assert abs(float(loss) - float(golden[f'loss{step}'])) < 1e-6
+        assert abs(float(norm) - float(golden[f'norm{step}'])) < 1e-6
+        if step in (1, 3):
+            for k, v in m.state_dict().items():
+                np.testing.assert_allclose(v.numpy(), golden[f'step{step}/' + k], rtol=0, atol=1e-7)
+
+
+def test_oracle_eval_loss_none(golden):
+    m = OracleEcgVit(config=OracleConfig(**GOLDEN_CFG), loss_reduction='none')
+    _load_state(m, golden, 'step3/')
+    m.eval()
+    with torch.no_grad():
+        out = m(torch.from_numpy(golden['x']), torch.from_numpy(golden['y']))
+    np.testing.assert_allclose(out.loss.numpy(), golden['eval_loss_none'], rtol=0, atol=1e-6)
+
+
+def test_patch_matrix_matches_golden_index(golden):
+    idx = torch.arange(2 * 12 * 500, dtype=torch.float32).reshape(2, 12, 500)
+    assert np.array_equal(patch_matrix(idx, 50).numpy().astype(np.int32), golden['patch_index'])
+    # closed form: A[b*n+w, t*C+c] = x[b, c, w*P+t]
+    b, w, t, c = 1, 7, 13, 5
+    assert golden['patch_index'][b * 10 + w, t * 12 + c] == (b * 12 + c) * 500 + w * 50 + t
+
+
+def test_named_sizes_and_param_counts():
+    # SURVEY.md 8a-S cross-checks: cfg1 3 341 895 params / 52 tensors; base (2500/50) 85 584 455 / 140
+    c = OracleConfig(max_signal_length=2500, patch_size=50, hidden_size=256, num_hidden_layers=4,
+                     num_attention_heads=8, intermediate_size=1024)
+    m = OracleEcgVit(config=c)
+    assert sum(p.numel() for p in m.parameters()) == 3_341_895 and len(list(m.parameters())) == 52
+    assert NAMED_SIZES['base'] == (768, 12, 12, 3072)
+
+
+def test_lr_lambda_matches_transformers():
+    from transformers import get_constant_schedule_with_warmup, get_cosine_schedule_with_warmup
+    p = nn.Parameter(torch.zeros(1))
+    for name, mk in (('constant', lambda o: get_constant_schedule_with_warmup(o, num_warmup_steps=5)),
+                     ('cosine', lambda o: get_cosine_schedule_with_warmup(o, num_warmup_steps=5, num_training_steps=40))):
+        opt = torch.optim.AdamW([p], lr=1.0)
+        sch = mk(opt)
+        for s in range(45):
+            assert abs(opt.param_groups[0]['lr'] - lr_lambda(name, s, 5, 40)) < 1e-12
+            opt.step()
+            sch.step()
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason='/root/reference only exists in the build container')
+def test_oracle_matches_reference_wrapper():
+    """the restated wrapper == the reference's verbatim `EcgVit` on the same weights and inputs (bit-exact)"""
+    EcgVit, EcgVitConfig, get_train_args, _ = ref_shim.load_reference()
+    kw = dict(GOLDEN_CFG, hidden_size=128, num_hidden_layers=3, num_attention_heads=8, intermediate_size=256)
+    torch.manual_seed(5)
+    ref = EcgVit(config=EcgVitConfig(**kw))
+    ours = OracleEcgVit(config=OracleConfig(**kw))
+    assert list(ref.state_dict().keys()) == list(ours.state_dict().keys())
+    ours.load_state_dict(ref.state_dict(), strict=True)
+    x, y = synthetic_batch(3, length=500, seed=11)
+    a, b = ref(sample_values=x, labels=y), ours(sample_values=x, labels=y)
+    assert torch.equal(a.logits, b.logits) and torch.equal(a.loss, b.loss)
+    a.loss.backward()
+    b.loss.backward()
+    for (k, p), (_, q) in zip(ref.named_parameters(), ours.named_parameters()):
+        assert torch.equal(p.grad, q.grad), k
+    # named sizes and trainer defaults
+    for size, dims in NAMED_SIZES.items():
+        c = EcgVitConfig.from_defined(f'ecg-vit-{size}')
+        assert (c.hidden_size, c.num_hidden_layers, c.num_attention_heads, c.intermediate_size) == dims
+    args = get_train_args()
+    assert (args['learning_rate'], args['weight_decay'], args['warmup_ratio'], args['schedule']) == (3e-4, 1e-2, 0.05, 'cosine')
