@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""
+bench.py -- ECG-ViT training-step throughput (BASELINE.json metric: train samples/s on synthetic 12x2500, bf16).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--no-graph]
+
+One "step" = zero_grad + forward + backward + (bucketed grad all-reduce) + clip_grad_norm(1.0) + AdamW on one batch of
+synthetic signals (seed 77), i.e. /root/reference/ecg_transformer/models/train.py:271-283 without its logging.
+Workload at N=1: BASELINE.json configs[1] -- ECG-ViT base (d=768, 12 layers, 12 heads, patch 50), bf16, batch 256.
+For N>1 every rank keeps batch 256 (weak scaling; N=8 is configs[2]'s global batch 2048).
+
+Prints ONE JSON line (rank 0).  `value` = samples/s with inputs resident in HBM; `e2e` = the same through the public
+API from pinned HOST buffers (H2D of the batch + D2H of the loss inside the timed region); `roofline` = the tcgen05
+GEMM kernel family against the measured cuBLAS bf16 peak; `cpu_baseline` = the CPU oracle port on this box's cores.
+`--impl reference` times the reference's own CPU path (oracle port: the reference is pure Python over an un-vendored
+package and /root/reference does not exist on the GPU box) on the same model config, bounded batch.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'ecg_vit_base_bf16_train_samples_per_s'
+UNIT = 'samples/s'
+BASE_CFG = dict(max_signal_length=2500, patch_size=50, num_channels=12, hidden_size=768, num_hidden_layers=12,
+                num_attention_heads=12, intermediate_size=3072, hidden_dropout_prob=0.0,
+                attention_probs_dropout_prob=0.0)
+NUM_CLASS = 71
+
+
+def train_flops_per_sample(c):
+    """SURVEY.md 8d / BASELINE.md 3: 2 FLOP per MAC, contractions only, no input dgrad for the patch embedding"""
+    n_patch = c['max_signal_length'] // c['patch_size']
+    N = n_patch + 1
+    d, mlp, depth = c['hidden_size'], c['intermediate_size'], c['num_hidden_layers']
+    inner = d
+    f_embed = 2 * n_patch * (c['num_channels'] * c['patch_size']) * d
+    f_lin = 2 * N * (3 * d * inner + inner * d + 2 * d * mlp)
+    f_attn = 4 * N * N * inner
+    f_head = 2 * d * NUM_CLASS
+    return 3 * (depth * (f_lin + f_attn) + f_head) + 2 * f_embed
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(tflops_sustained=p['bf16_tflops_sustained'], tflops_burst=p['bf16_tflops'], hbm_gbs=p['hbm_gbs'],
+                    source='MEASURED_PEAKS.json')
+    return dict(tflops_sustained=1400.0, tflops_burst=1590.0, hbm_gbs=6650.0, source='B200_PROFILING.md fallback')
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)"""
+    FIELDS = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+              'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+              'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.FIELDS}', '--format=csv,noheader,nounits',
+                                          '-lms', '100', '-i', str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(',')]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); power.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[3:7]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        # "under load" = samples at or above the median power draw
+        if sm:
+            thr = statistics.median(power)
+            loaded = [s for s, p in zip(sm, power) if p >= thr] or sm
+            return {'sm_mhz': statistics.median(loaded), 'sm_max_mhz': max(mx), 'reasons': sorted(reasons),
+                    'samples': len(sm), 'power_w_max': max(power)}
+        return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['no samples'], 'samples': 0}
+
+
+def cpu_reference_steps(cfg, batch, steps, warmup, threads=None):
+    """the reference path on host cores: oracle restatement of EcgVit/ViT + stock torch AdamW / clip_grad_norm_"""
+    import torch
+    from oracle.ecg_vit_oracle import OracleConfig, OracleEcgVit, OracleTrainer, synthetic_batch
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    torch.manual_seed(77)
+    model = OracleEcgVit(config=OracleConfig(**cfg)).train()
+    tr = OracleTrainer(model, learning_rate=3e-4, weight_decay=1e-2, schedule='constant')
+    x, y = synthetic_batch(batch, length=cfg['max_signal_length'])
+    for _ in range(warmup):
+        tr.step(x, y)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        tr.step(x, y)
+        times.append(time.perf_counter() - t0)
+    return times, torch.get_num_threads()
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    batch = args.ref_batch
+    times, threads = cpu_reference_steps(BASE_CFG, batch, args.steps, max(1, min(args.warmup, 2)))
+    ms = 1e3 * sum(times) / len(times)
+    value = batch / (ms / 1e3)
+    sample = (f'{args.steps} steps of the base model (fp32, stock torch AdamW + clip_grad_norm_) on a bounded batch of '
+              f'{batch} synthetic 12x2500 signals (the GPU arm uses 256 per step)')
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'ECG-ViT base (d=768, 12 layers, 12 heads, patch 50) pre-training step, 12x2500',
+                   'batch_per_step': batch, 'device': 'cpu'},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--batch', type=int, default=256, help='per-GPU batch')
+    ap.add_argument('--ref-batch', type=int, default=16, help='bounded CPU batch of the reference arm')
+    ap.add_argument('--no-graph', action='store_true', help='launch kernels from Python instead of one CUDA graph')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--profile-json', default=None, help='write the per-kernel event breakdown here')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference_arm(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    import ecg_b200
+    from ecg_b200 import _lib
+    from oracle.ecg_vit_oracle import synthetic_batch  # only the seeded input generator
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+    assert _lib.load().ecgvit_device_ok() == 1, 'bench.py needs an sm_100 (B200) device: there is no fallback path'
+
+    B = args.batch
+    torch.manual_seed(77)
+    model = ecg_b200.EcgVit(config=ecg_b200.EcgVitConfig(compute_dtype='bf16', **BASE_CFG)).to(dev).train()
+    use_graph = (not args.no_graph) and world == 1
+    trainer = ecg_b200.FusedTrainer(model, learning_rate=3e-4, weight_decay=1e-2, schedule='constant',
+                                    max_grad_norm=1.0, use_cuda_graph=use_graph)
+    xh, yh = synthetic_batch(B, length=BASE_CFG['max_signal_length'], seed=77 + rank)
+    xh, yh = xh.pin_memory(), yh.pin_memory()
+    x, y = xh.to(dev), yh.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    # ---- device-resident arm -------------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        trainer.step(x, y)
+    torch.cuda.synchronize()
+    n0 = _lib.launch_counter[0]
+    if not use_graph:
+        trainer.step(x, y)
+        launches_per_step = _lib.launch_counter[0] - n0
+    else:
+        launches_per_step = trainer.launches_per_step
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    total_ms = timed(lambda: trainer.step(x, y), args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    trainer.check_finite()
+    ms_per_step = total_ms / args.steps
+    value = world * B / (ms_per_step / 1e3)
+
+    # ---- end-to-end arm: pinned host batch -> H2D -> step -> D2H of the loss, every step -------------------
+    loss_host = torch.zeros(1).pin_memory()
+
+    def e2e_step():
+        xd = xh.to(dev, non_blocking=True)
+        yd = yh.to(dev, non_blocking=True)
+        loss, _ = trainer.step(xd, yd)
+        loss_host.copy_(loss.reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the caller reads the loss every step (train.py:278)
+
+    for _ in range(2):
+        e2e_step()
+    e2e_ms = timed(e2e_step, args.steps) / args.steps
+    e2e_value = world * B / (e2e_ms / 1e3)
+
+    # ---- roofline leg: per-call device times of one eager step (event after every entry-point call) ---------
+    roofline, kernels = None, None
+    if rank == 0:
+        peaks = measured_peaks()
+        eager = ecg_b200.FusedTrainer(model, use_cuda_graph=False)
+        eager._reducer = None
+        eager.world = 1
+        eager.step(x, y)
+        torch.cuda.synchronize()
+        _lib.profile[0] = []
+        start = torch.cuda.Event(enable_timing=True)
+        start.record()
+        eager.step(x, y)
+        torch.cuda.synchronize()
+        rec, _lib.profile[0] = _lib.profile[0], None
+        prev, agg = start, {}
+        gemm_flops = gemm_ms = 0.0
+        for name, meta, ev in rec:
+            dt_ms = prev.elapsed_time(ev)
+            prev = ev
+            a = agg.setdefault(name, [0, 0.0])
+            a[0] += 1
+            a[1] += dt_ms
+            if name == 'gemm':
+                M_, N_, K_, _epi = meta
+                gemm_flops += 2.0 * M_ * N_ * K_
+                gemm_ms += dt_ms
+        step_ms_eager = sum(v[1] for v in agg.values())
+        kernels = {k: {'calls': v[0], 'ms': round(v[1], 4), 'share': round(v[1] / step_ms_eager, 4)} for k, v in agg.items()}
+        achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12
+        n_gemm = agg['gemm'][0]
+        roofline = {
+            'kernel': 'gemm_tc_kernel (tcgen05.mma kind::f16, all fwd/dgrad/wgrad launches of one step)',
+            'bound': 'tensor', 'achieved': achieved, 'peak': peaks['tflops_sustained'], 'unit': 'TFLOP/s',
+            'frac': achieved / peaks['tflops_sustained'], 'traffic': None,
+            'peak_source': f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step), of measured",
+            'launches': n_gemm, 'avg_launch_ms': gemm_ms / n_gemm, 'flops_per_launch_avg': gemm_flops / n_gemm,
+            'step_share': gemm_ms / step_ms_eager,
+            'whole_step_tflops': world * B * train_flops_per_sample(BASE_CFG) / (ms_per_step * 1e-3) / 1e12 / world,
+            'whole_step_frac_of_nominal_2250': B * train_flops_per_sample(BASE_CFG) / (ms_per_step * 1e-3) / 2.25e15,
+        }
+        if args.profile_json:
+            with open(args.profile_json, 'w') as f:
+                json.dump({'kernels': kernels, 'roofline': roofline,
+                           'gemm_launches': [dict(M=m[0], N=m[1], K=m[2], epi=m[3]) for n_, m, _ in rec if n_ == 'gemm']}, f, indent=1)
+
+    # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload ---------------------------------
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cb = 8
+        times, threads = cpu_reference_steps(BASE_CFG, cb, steps=2, warmup=1)
+        v = cb / (sum(times) / len(times))
+        cpu_baseline = {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+                        'sample': f'2 timed steps (+1 warm-up) of the base model in fp32 on a batch of {cb} synthetic 12x2500 '
+                                  f'signals: oracle restatement + stock torch AdamW/clip_grad_norm_'}
+
+    if rank == 0:
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'bf16', 'data': 'synthetic',
+            'config': {'workload': 'ECG-ViT base (d=768, 12 layers, 12 heads, patch 50) bf16 pre-training step, '
+                                   'batch 256 per GPU, 12x2500 signals (BASELINE.json configs[1]; configs[2] at N=8)',
+                       'global_batch': world * B, 'per_gpu_batch': B, 'dropout': 0.0, 'parallelism': f'dp{world}',
+                       'l2': 'per-step working set (~4 GB of activations + 1.9 GB of optimizer traffic) exceeds the '
+                             '126 MB L2, no explicit flush',
+                       'cuda_graph': use_graph, 'optimizer': 'AdamW lr 3e-4 wd 1e-2, clip_grad_norm 1.0'},
+            'clocks': clocks,
+            'e2e': {'value': e2e_value, 'unit': UNIT, 'ms_per_step': e2e_ms,
+                    'h2d_bytes_per_step': world * (xh.numel() + yh.numel()) * 4, 'd2h_bytes_per_step': world * 4},
+            'gpu_launches': launches_per_step * args.steps,
+            'roofline': roofline, 'cpu_baseline': cpu_baseline, 'kernels': kernels,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -81,9 +81,26 @@ def last_error():
     return msg.decode() if msg else ''
 
 
+# kernels launched per successful entry-point call (memsets are not kernels); feeds bench.py's `gpu_launches`
+KERNELS_PER_CALL = {'head_fwd': 2, 'head_bwd': 3}
+launch_counter = [0]
+
+
 def check(rc, what=''):
     if rc != 0:
         raise RuntimeError(f'ecgvit_b200 {what} failed (code {rc}): {last_error()}')
+    launch_counter[0] += KERNELS_PER_CALL.get(what, 1)
+    if profile[0] is not None:
+        # one event after every call: on a single stream, consecutive event deltas are per-call device times
+        import torch
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        profile[0].append((what, profile_meta[0], e))
+        profile_meta[0] = None
+
+
+profile = [None]       # set to a list to record (name, meta, event) per entry-point call (bench.py roofline leg)
+profile_meta = [None]  # optional description of the next call (GEMM shape / epilogue)
 
 
 def ptr(t):

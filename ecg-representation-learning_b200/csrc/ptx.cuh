@@ -35,8 +35,12 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// Bounded spin: a protocol bug traps (-> "unspecified launch failure") instead of hanging the GPU.  A legitimate
+// wait in these kernels lasts microseconds; the bound is > 1 s of polling.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 26)) asm volatile("trap;");
     }
 }
 

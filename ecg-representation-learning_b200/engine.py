@@ -44,6 +44,8 @@ class StepEngine:
     def _gemm(self, M, N, K, A, lda, a_k, B, ldb, b_k, epi, out, ldo, out2=None, aux=None, bias=None, split_k=1):
         g = GemmArgs(M, N, K, A.data_ptr(), lda, a_k, B.data_ptr(), ldb, b_k, epi, out.data_ptr(), ldo,
                      _lib.ptr(out2), _lib.ptr(aux), _lib.ptr(bias), self.model._dtype_code, split_k, 0)
+        if _lib.profile[0] is not None:
+            _lib.profile_meta[0] = (M, N, K, epi)
         _lib.check(self.lib.ecgvit_gemm(ctypes.byref(g), self._stream), 'gemm')
 
     def workspace(self, B, L):

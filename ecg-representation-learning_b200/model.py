@@ -103,9 +103,10 @@ class _EcgVitFunction(torch.autograd.Function):
         loss, logits = model._engine.forward(sample_values, labels, model.loss_reduction)
         ctx.model = model
         ctx.ws = model._engine._cur
-        ctx.mark_non_differentiable(logits)
         # hand out copies: the workspace buffers are overwritten by the next forward
-        return loss.clone(), logits.clone()
+        loss, logits = loss.clone(), logits.clone()
+        ctx.mark_non_differentiable(logits)
+        return loss, logits
 
     @staticmethod
     def backward(ctx, grad_loss, _grad_logits):

@@ -64,6 +64,7 @@ class FusedTrainer:
         self._state_ready = False
         self._graph = None
         self._reducer = None
+        self.launches_per_step = None
 
     # ---- lazily created device state ---------------------------------------------------------------
     def _ensure_state(self, device):
@@ -144,8 +145,10 @@ class FusedTrainer:
             self.model._flat_p.copy_(snap[0]); self.exp_avg.copy_(snap[1]); self.exp_avg_sq.copy_(snap[2])
             self.model.sync_shadow(force=True)
             g = torch.cuda.CUDAGraph()
+            n0 = _lib.launch_counter[0]
             with torch.cuda.graph(g):
                 self._graph_out = self._device_step(self._static_x, self._static_y)
+            self.launches_per_step = _lib.launch_counter[0] - n0  # kernels of ours replayed by every graph launch
             self._graph, self._graph_key = g, key
         self._static_x.copy_(sample_values, non_blocking=True)
         self._static_y.copy_(labels, non_blocking=True)

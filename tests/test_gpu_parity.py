@@ -1,0 +1,253 @@
+"""GPU tier: the whole hot path (forward, backward, clip + AdamW, 3 steps) against the CPU oracle and the committed
+golden vectors.  Tolerances are BASELINE.json's: fp32 logits/loss <= 1e-5 relative; bf16 <= 1e-2 relative with
+per-parameter gradient cosine >= 0.999; patch indexing bit-exact (test_gpu_kernels.py)."""
+import numpy as np
+import pytest
+import torch
+from torch import nn
+
+pytestmark = pytest.mark.gpu
+
+from conftest import GOLDEN_CFG
+import ecg_b200
+from ecg_b200 import EcgVit, EcgVitConfig, FusedTrainer, FusedAdamW, clip_grad_norm_
+from oracle.ecg_vit_oracle import OracleConfig, OracleEcgVit, OracleTrainer, synthetic_batch
+
+FP32_TOL = 1e-5       # north_star: fp32 logits and loss within 1e-5 relative
+BF16_TOL = 1e-2       # north_star: bf16 within 1e-2 relative
+BF16_GRAD_COS = 0.999  # north_star: per-parameter gradient cosine
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def cosine(a, b):
+    a, b = a.detach().double().cpu().flatten(), b.detach().double().cpu().flatten()
+    return float((a @ b) / (a.norm() * b.norm()).clamp_min(1e-300))
+
+
+def make_pair(cfg, dtype, batch, seed=77, length=None):
+    torch.manual_seed(seed)
+    oracle = OracleEcgVit(config=OracleConfig(**cfg)).train()
+    model = EcgVit(config=EcgVitConfig(compute_dtype=dtype, **cfg))
+    model.load_state_dict(oracle.state_dict(), strict=True)
+    model.cuda().train()
+    x, y = synthetic_batch(batch, length=length or cfg['max_signal_length'], seed=seed)
+    return oracle, model, x, y
+
+
+def golden_model(golden, dtype):
+    model = EcgVit(config=EcgVitConfig(compute_dtype=dtype, **GOLDEN_CFG))
+    model.load_state_dict({k[5:]: torch.from_numpy(v) for k, v in golden.items() if k.startswith('init/')}, strict=True)
+    return model.cuda().train()
+
+
+# ---- golden vectors (generated through the reference's own wrapper) ------------------------------------------
+def test_fp32_matches_golden_forward_backward(golden):
+    model = golden_model(golden, 'fp32')
+    x, y = torch.from_numpy(golden['x']).cuda(), torch.from_numpy(golden['y']).cuda()
+    out = model(sample_values=x, labels=y)
+    assert isinstance(out, ecg_b200.ModelOutput)
+    out.loss.backward()
+    assert rel(out.logits, torch.from_numpy(golden['logits'])) < FP32_TOL
+    assert abs(float(out.loss) - float(golden['loss'])) < FP32_TOL * float(golden['loss'])
+    for k, p in model.named_parameters():
+        g = torch.from_numpy(golden['grad/' + k])
+        assert rel(p.grad, g) < 2e-4, (k, rel(p.grad, g))
+        assert cosine(p.grad, g) > 0.999999, k
+
+
+def test_fp32_matches_golden_three_steps(golden):
+    model = golden_model(golden, 'fp32')
+    x, y = torch.from_numpy(golden['x']).cuda(), torch.from_numpy(golden['y']).cuda()
+    tr = FusedTrainer(model, learning_rate=3e-4, weight_decay=1e-2, schedule='constant', max_grad_norm=1.0)
+    for step in (1, 2, 3):
+        loss, _ = tr.step(x, y)
+        assert abs(float(loss) - float(golden[f'loss{step}'])) < FP32_TOL * float(golden[f'loss{step}'])
+        assert abs(tr.grad_norm() - float(golden[f'norm{step}'])) < 1e-4 * float(golden[f'norm{step}'])
+        if step in (1, 3):
+            for k, v in model.state_dict().items():
+                assert rel(v, torch.from_numpy(golden[f'step{step}/' + k])) < FP32_TOL, (step, k)
+    tr.check_finite()
+
+
+def test_eval_loss_none_matches_golden(golden):
+    model = EcgVit(config=EcgVitConfig(compute_dtype='fp32', **GOLDEN_CFG), loss_reduction='none')
+    model.load_state_dict({k[6:]: torch.from_numpy(v) for k, v in golden.items() if k.startswith('step3/')}, strict=True)
+    model.cuda().eval()
+    with torch.no_grad():
+        out = model(torch.from_numpy(golden['x']).cuda(), torch.from_numpy(golden['y']).cuda())
+    assert out.loss.shape == (4, 71)
+    assert rel(out.loss, torch.from_numpy(golden['eval_loss_none'])) < FP32_TOL
+    assert rel(out.logits, torch.from_numpy(golden['eval_logits'])) < FP32_TOL
+    assert model(torch.from_numpy(golden['x']).cuda()).loss is None
+
+
+# ---- oracle on the same seeded inputs -------------------------------------------------------------------------
+CFG1 = dict(max_signal_length=2500, patch_size=50, num_channels=12, hidden_size=256, num_hidden_layers=4,
+            num_attention_heads=8, intermediate_size=1024, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+CFG_MID = dict(max_signal_length=2500, patch_size=50, num_channels=12, hidden_size=384, num_hidden_layers=3,
+               num_attention_heads=6, intermediate_size=1536, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+CFG_REFDEFAULT = dict(max_signal_length=2560, patch_size=64, num_channels=12, hidden_size=128, num_hidden_layers=2,
+                      num_attention_heads=4, intermediate_size=512, hidden_dropout_prob=0.0,
+                      attention_probs_dropout_prob=0.0)
+
+
+@pytest.mark.parametrize('cfg,batch', [(CFG1, 8), (CFG_REFDEFAULT, 5)])
+def test_fp32_parity_with_oracle_cfg1(cfg, batch):
+    """cfg1 of BASELINE.json (d=256, 4 layers, 8 heads, patch 50, 12x2500) and the reference's default 2560/64 geometry"""
+    oracle, model, x, y = make_pair(cfg, 'fp32', batch)
+    o = oracle(sample_values=x, labels=y)
+    o.loss.backward()
+    out = model(sample_values=x.cuda(), labels=y.cuda())
+    out.loss.backward()
+    assert rel(out.logits, o.logits) < FP32_TOL and rel(out.loss, o.loss) < FP32_TOL
+    for (k, p), (_, q) in zip(model.named_parameters(), oracle.named_parameters()):
+        assert rel(p.grad, q.grad) < 5e-4, (k, rel(p.grad, q.grad))
+        assert cosine(p.grad, q.grad) > 0.99999, k
+
+
+def test_fp32_three_steps_with_clipping_active():
+    oracle, model, x, y = make_pair(CFG_REFDEFAULT, 'fp32', 6, seed=5)
+    ot = OracleTrainer(oracle, learning_rate=1e-3, weight_decay=1e-2, schedule='cosine', n_warmup=1, n_step=3,
+                       max_grad_norm=0.05)
+    tr = FusedTrainer(model, learning_rate=1e-3, weight_decay=1e-2, schedule='cosine', n_warmup=1, n_step=3,
+                      max_grad_norm=0.05)
+    for _ in range(3):
+        o_loss, _, o_norm = ot.step(x, y)
+        loss, _ = tr.step(x.cuda(), y.cuda())
+        assert float(o_norm) > 0.05, 'test must exercise the clip'
+        assert rel(loss, o_loss) < FP32_TOL and abs(tr.grad_norm() - float(o_norm)) < 1e-4 * float(o_norm)
+    for k, v in model.state_dict().items():
+        assert rel(v, oracle.state_dict()[k]) < FP32_TOL, k
+
+
+def test_shorter_signal_uses_pos_embedding_slice():
+    """vit_pytorch slices pos_embedding[:, :n+1], so inputs shorter than max_signal_length are legal"""
+    oracle, model, x, y = make_pair(CFG_REFDEFAULT, 'fp32', 3, length=1280)
+    o = oracle(sample_values=x, labels=y)
+    out = model(sample_values=x.cuda(), labels=y.cuda())
+    assert rel(out.logits, o.logits) < FP32_TOL
+    o.loss.backward()
+    out.loss.backward()
+    g, go = model.vit.pos_embedding.grad, oracle.vit.pos_embedding.grad
+    assert rel(g, go) < 1e-4 and float(g[0, 21:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize('cfg,batch', [(CFG1, 16), (CFG_MID, 8), (GOLDEN_CFG, 4)])
+def test_bf16_parity_with_oracle(cfg, batch):
+    oracle, model, x, y = make_pair(cfg, 'bf16', batch)
+    o = oracle(sample_values=x, labels=y)
+    o.loss.backward()
+    out = model(sample_values=x.cuda(), labels=y.cuda())
+    out.loss.backward()
+    assert rel(out.logits, o.logits) < BF16_TOL, rel(out.logits, o.logits)
+    assert rel(out.loss, o.loss) < BF16_TOL
+    worst = min((cosine(p.grad, q.grad), k) for (k, p), (_, q) in zip(model.named_parameters(), oracle.named_parameters()))
+    assert worst[0] >= BF16_GRAD_COS, worst
+
+
+def test_bf16_three_steps_track_the_oracle():
+    oracle, model, x, y = make_pair(CFG1, 'bf16', 16)
+    ot, tr = OracleTrainer(oracle), FusedTrainer(model)
+    for _ in range(3):
+        o_loss, _, o_norm = ot.step(x, y)
+        loss, _ = tr.step(x.cuda(), y.cuda())
+        assert rel(loss, o_loss) < BF16_TOL
+        assert abs(tr.grad_norm() - float(o_norm)) < 3e-2 * float(o_norm)
+    tr.check_finite()
+    # the bf16 shadow the next forward reads is exactly the rounded fp32 master
+    assert torch.equal(model._shadow, model._flat_p.bfloat16())
+
+
+# ---- reference-style loop through the drop-in API ---------------------------------------------------------------
+def test_reference_style_loop_equals_fused_step():
+    """zero_grad / model(**inputs) / loss.backward() / clip_grad_norm_ / optimizer.step() / scheduler.step()
+    (train.py:271-283) through the nn.Module API gives the same parameters as FusedTrainer.step"""
+    from transformers import get_cosine_schedule_with_warmup
+    _, m1, x, y = make_pair(GOLDEN_CFG, 'fp32', 4)
+    _, m2, _, _ = make_pair(GOLDEN_CFG, 'fp32', 4)
+    inputs = dict(sample_values=x.cuda(), labels=y.cuda())
+    opt = FusedAdamW(m1, lr=3e-4, weight_decay=1e-2)
+    sch = get_cosine_schedule_with_warmup(opt, num_warmup_steps=1, num_training_steps=4)
+    tr = FusedTrainer(m2, learning_rate=3e-4, weight_decay=1e-2, schedule='cosine', n_warmup=1, n_step=4)
+    for _ in range(3):
+        opt.zero_grad()
+        out = m1(**inputs)
+        loss, logits = out  # tuple-unpack like EcgVitTrainModule (train.py:49)
+        loss.backward()
+        clip_grad_norm_(m1, max_norm=1.0, error_if_nonfinite=True)
+        opt.step()
+        sch.step()
+        tr.step(**inputs)
+    for (k, a), (_, b) in zip(m1.state_dict().items(), m2.state_dict().items()):
+        assert rel(a, b) < 1e-6, k
+
+
+def test_stock_torch_optimizer_also_works_and_shadow_follows():
+    """a user may keep torch.optim.AdamW + nn.utils.clip_grad_norm_: parameters stay views of the flat buffer and the
+    bf16 shadow is refreshed when their version counters move"""
+    oracle, model, x, y = make_pair(GOLDEN_CFG, 'bf16', 4)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-2, weight_decay=1e-2)
+    for _ in range(2):
+        opt.zero_grad()
+        model(sample_values=x.cuda(), labels=y.cuda()).loss.backward()
+        nn.utils.clip_grad_norm_(model.parameters(), 1.0, error_if_nonfinite=True)
+        opt.step()
+    out = model(sample_values=x.cuda(), labels=y.cuda())
+    assert torch.equal(model._shadow, model._flat_p.bfloat16())
+    oracle.load_state_dict(model.state_dict())
+    assert rel(out.logits, oracle(x, y).logits) < BF16_TOL
+
+
+def test_gradient_accumulation_semantics():
+    _, model, x, y = make_pair(GOLDEN_CFG, 'fp32', 4)
+    inputs = dict(sample_values=x.cuda(), labels=y.cuda())
+    model(**inputs).loss.backward()
+    g1 = [p.grad.clone() for p in model.parameters()]
+    model(**inputs).loss.backward()  # no zero_grad in between: autograd semantics are "accumulate"
+    for p, g in zip(model.parameters(), g1):
+        assert rel(p.grad, 2 * g) < 1e-5
+
+
+def test_cuda_graph_step_matches_eager_step():
+    _, m1, x, y = make_pair(GOLDEN_CFG, 'bf16', 4)
+    _, m2, _, _ = make_pair(GOLDEN_CFG, 'bf16', 4)
+    t1, t2 = FusedTrainer(m1, use_cuda_graph=False), FusedTrainer(m2, use_cuda_graph=True)
+    xs, ys = x.cuda(), y.cuda()
+    for i in range(4):
+        xi = xs * (1.0 + 0.1 * i)
+        l1, _ = t1.step(xi, ys)
+        l2, _ = t2.step(xi, ys)
+        assert abs(float(l1) - float(l2)) < 1e-3 * abs(float(l1))  # fp32 atomics reorder between runs
+    assert rel(m2._flat_p, m1._flat_p) < 1e-4
+
+
+# ---- full-size properties (cfg2 geometry; the oracle would take minutes on CPU) -----------------------------------
+def test_base_model_full_batch_properties():
+    cfg = dict(max_signal_length=2500, patch_size=50, num_channels=12, hidden_size=768, num_hidden_layers=12,
+               num_attention_heads=12, intermediate_size=3072, hidden_dropout_prob=0.0,
+               attention_probs_dropout_prob=0.0)
+    torch.manual_seed(0)
+    model = EcgVit(config=EcgVitConfig(compute_dtype='bf16', **cfg)).cuda().train()
+    x, y = synthetic_batch(256)
+    x, y = x.cuda(), y.cuda()
+    with torch.no_grad():
+        full = model(sample_values=x, labels=y).logits
+        # samples are independent: any sub-batch reproduces its rows of the full-batch logits
+        part = model(sample_values=x[64:96], labels=y[64:96]).logits
+        # permutation equivariance over the batch
+        perm = torch.randperm(256, device='cuda')
+        shuf = model(sample_values=x[perm], labels=y[perm]).logits
+    assert rel(part, full[64:96]) < 2e-3
+    assert rel(shuf, full[perm]) < 2e-3
+    # a training step leaves everything finite and moves the loss down on the same batch
+    tr = FusedTrainer(model, learning_rate=3e-4)
+    l0 = float(tr.step(x, y)[0])
+    for _ in range(4):
+        l = float(tr.step(x, y)[0])
+    tr.check_finite()
+    assert np.isfinite(l) and l < l0
+    assert torch.equal(model._shadow, model._flat_p.bfloat16())
