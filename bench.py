@@ -262,11 +262,14 @@ def main():
         eager.step(x, y)
         torch.cuda.synchronize()
         rec, _lib.profile[0] = _lib.profile[0], None
-        prev, agg = start, {}
+        prev, agg, gemm_rows = start, {}, []
         gemm_flops = gemm_ms = 0.0
         for name, meta, ev in rec:
             dt_ms = prev.elapsed_time(ev)
             prev = ev
+            if name == 'gemm':
+                gemm_rows.append(dict(M=meta[0], N=meta[1], K=meta[2], epi=meta[3], ms=round(dt_ms, 4),
+                                      tflops=round(2.0 * meta[0] * meta[1] * meta[2] / (dt_ms * 1e-3) / 1e12, 1)))
             a = agg.setdefault(name, [0, 0.0])
             a[0] += 1
             a[1] += dt_ms
@@ -291,7 +294,7 @@ def main():
         if args.profile_json:
             with open(args.profile_json, 'w') as f:
                 json.dump({'kernels': kernels, 'roofline': roofline,
-                           'gemm_launches': [dict(M=m[0], N=m[1], K=m[2], epi=m[3]) for n_, m, _ in rec if n_ == 'gemm']}, f, indent=1)
+                           'gemm_launches': gemm_rows}, f, indent=1)
 
     # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload ---------------------------------
     cpu_baseline = None

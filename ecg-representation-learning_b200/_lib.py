@@ -106,3 +106,12 @@ profile_meta = [None]  # optional description of the next call (GEMM shape / epi
 def ptr(t):
     """device pointer of a torch tensor (or None)"""
     return None if t is None else t.data_ptr()
+
+
+def adamw_hyper(lr, beta1, beta2, eps, weight_decay, step, max_norm, grad_scale):
+    """the 16-float `hyper` block of ecgvit_grad_sumsq / ecgvit_adamw_step (include/ecgvit_b200.h); derived scalars
+    are evaluated in double precision here, exactly where torch.optim.AdamW evaluates them"""
+    bc1, bc2 = 1.0 - beta1 ** step, 1.0 - beta2 ** step
+    vals = [lr, beta1, beta2, eps, weight_decay, bc1, bc2, max_norm, grad_scale,
+            1.0 - beta1, 1.0 - beta2, 1.0 - lr * weight_decay, lr / bc1, bc2 ** 0.5]
+    return vals + [0.0] * (16 - len(vals))

@@ -1,7 +1,348 @@
-// placeholder until the tensor-core attention kernel lands
+// Tensor-core softmax attention for short sequences (N <= 64 tokens: the 12x2500 / patch-50 geometry has N = 51),
+// bf16 operands, fp32 softmax statistics.  One CTA (4 warps) per (batch, head); each warp owns 16 query rows.
+//
+// The whole (b,h) problem lives in shared memory / registers, so the forward never materialises the [B,H,N,N]
+// probability tensor that vit_pytorch's Attention.forward writes, and the backward recomputes P from the saved
+// log-sum-exp.  q | k | v are read in place from the packed projection (no chunk / rearrange copies).
+//
+// At N = 51 attention is 1.1 % of the step's FLOPs: a 51-row problem cannot fill a 128-row
+// tcgen05 tile, so this kernel uses warp-level mma.sync m16n8k16 (HMMA); the tcgen05 budget goes to the GEMMs.
 #include "common.cuh"
+
 namespace ecgvit {
-bool attention_mma_supported(int, int) { return false; }
-int attention_fwd_mma(const void *, void *, float *, int, int, int, int, float, cudaStream_t) { return fail(-1, "attention_mma: not built"); }
-int attention_bwd_mma(const void *, const void *, const void *, const float *, void *, int, int, int, int, float, cudaStream_t) { return fail(-1, "attention_mma: not built"); }
+
+namespace {
+
+constexpr int NMAX = 64;  // padded sequence length handled by one CTA
+constexpr float LOG2E = 1.4426950408889634f;
+
+__device__ __forceinline__ void ldsm_x4(uint32_t r[4], const void *p) {
+    const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(p));
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
 }
+__device__ __forceinline__ void ldsm_x4_t(uint32_t r[4], const void *p) {
+    const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(p));
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+// D(16x8, fp32) += A(16x16, bf16, row) * B(16x8, bf16, col)
+__device__ __forceinline__ void mma16816(float c[4], const uint32_t a[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+                 "{%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ float quad_sum(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    return v;
+}
+__device__ __forceinline__ float quad_max(float v) {
+    v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+    v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+    return v;
+}
+
+// copy an [N x DH] head tile (row stride `ld` elements) into smem [NMAX][DH + 8], zero-filling rows >= N
+template <int DH>
+__device__ __forceinline__ void load_tile(bf16 (*dst)[DH + 8], const bf16 *src, int64_t ld, int N) {
+    constexpr int VPR = DH / 8;
+    for (int i = threadIdx.x; i < NMAX * VPR; i += blockDim.x) {
+        const int r = i / VPR, c = (i % VPR) * 8;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (r < N) v = *reinterpret_cast<const uint4 *>(src + (int64_t)r * ld + c);
+        *reinterpret_cast<uint4 *>(&dst[r][c]) = v;
+    }
+}
+
+// s[j][:] (16 rows x 64 keys, C-fragment layout) = X[m0:m0+16, :DH] * Y[:, :DH]^T, both row-major in smem
+template <int DH>
+__device__ __forceinline__ void rows_times_transposed(float s[8][4], bf16 (*X)[DH + 8], bf16 (*Y)[DH + 8], int m0,
+                                                      int n_tiles16, int lane) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s[j][i] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < DH / 16; ++kk) {
+        uint32_t a[4];
+        ldsm_x4(a, &X[m0 + (lane & 7) + ((lane >> 3) & 1) * 8][kk * 16 + (lane >> 4) * 8]);
+#pragma unroll
+        for (int np = 0; np < 4; ++np) {
+            if (np < n_tiles16) {
+                uint32_t b[4];
+                ldsm_x4(b, &Y[np * 16 + (lane & 7) + (lane >> 4) * 8][kk * 16 + ((lane >> 3) & 1) * 8]);
+                mma16816(s[2 * np], a, b[0], b[1]);
+                mma16816(s[2 * np + 1], a, b[2], b[3]);
+            }
+        }
+    }
+}
+
+// acc[DH/8][4] (16 rows x DH) += P(16 x 64, given as A fragments per 16-key tile) * Z[:, :DH], Z row-major [key][d]
+template <int DH>
+__device__ __forceinline__ void frag_times_rows(float acc[DH / 8][4], const uint32_t pa[4][4], bf16 (*Z)[DH + 8],
+                                                int n_tiles16, int lane) {
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+        if (kk < n_tiles16) {
+#pragma unroll
+            for (int dp = 0; dp < DH / 16; ++dp) {
+                uint32_t b[4];
+                ldsm_x4_t(b, &Z[kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8][dp * 16 + (lane >> 4) * 8]);
+                mma16816(acc[2 * dp], pa[kk], b[0], b[1]);
+                mma16816(acc[2 * dp + 1], pa[kk], b[2], b[3]);
+            }
+        }
+    }
+}
+
+// acc (16 rows j0.. x DH) += W^T[j0:j0+16, :] * Z, with W stored [q][key] (pitch 72) and Z stored [q][d]
+template <int DH>
+__device__ __forceinline__ void transposed_times_rows(float acc[DH / 8][4], bf16 (*W)[NMAX + 8], bf16 (*Z)[DH + 8],
+                                                      int j0, int n_tiles16, int lane) {
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+        if (kk < n_tiles16) {
+            uint32_t a[4];
+            const int mi = lane >> 3;
+            ldsm_x4_t(a, &W[kk * 16 + (lane & 7) + (mi >> 1) * 8][j0 + (mi & 1) * 8]);
+#pragma unroll
+            for (int dp = 0; dp < DH / 16; ++dp) {
+                uint32_t b[4];
+                ldsm_x4_t(b, &Z[kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8][dp * 16 + (lane >> 4) * 8]);
+                mma16816(acc[2 * dp], a, b[0], b[1]);
+                mma16816(acc[2 * dp + 1], a, b[2], b[3]);
+            }
+        }
+    }
+}
+
+template <int DH>
+__device__ __forceinline__ void store_rows(bf16 *dst, int64_t ld, float acc[DH / 8][4], int r0, int r1, int N, int t,
+                                           float mul0, float mul1) {
+#pragma unroll
+    for (int j = 0; j < DH / 8; ++j) {
+        const int c = 8 * j + 2 * t;
+        if (r0 < N) *reinterpret_cast<uint32_t *>(dst + (int64_t)r0 * ld + c) = pack_bf16x2(acc[j][0] * mul0, acc[j][1] * mul0);
+        if (r1 < N) *reinterpret_cast<uint32_t *>(dst + (int64_t)r1 * ld + c) = pack_bf16x2(acc[j][2] * mul1, acc[j][3] * mul1);
+    }
+}
+
+template <int DH>
+__global__ void __launch_bounds__(128) attention_fwd_mma_kernel(const bf16 *__restrict__ qkv, bf16 *__restrict__ o,
+                                                                 float *__restrict__ lse, int N, int H, float scale) {
+    __shared__ __align__(16) bf16 sQ[NMAX][DH + 8];
+    __shared__ __align__(16) bf16 sK[NMAX][DH + 8];
+    __shared__ __align__(16) bf16 sV[NMAX][DH + 8];
+    const int h = blockIdx.x % H, b = blockIdx.x / H;
+    const int inner = H * DH;
+    const int64_t ld = 3 * (int64_t)inner;
+    const bf16 *base = qkv + (int64_t)b * N * ld + (int64_t)h * DH;
+    load_tile<DH>(sQ, base, ld, N);
+    load_tile<DH>(sK, base + inner, ld, N);
+    load_tile<DH>(sV, base + 2 * inner, ld, N);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = warp * 16;
+    if (m0 >= N) return;
+    const int g = lane >> 2, t = lane & 3;
+    const int n_tiles16 = (N + 15) / 16;
+
+    float s[8][4];
+    rows_times_transposed<DH>(s, sQ, sK, m0, n_tiles16, lane);
+    const float sl2 = scale * LOG2E;
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = 8 * j + 2 * t;
+        if (c >= N) { s[j][0] = -INFINITY; s[j][2] = -INFINITY; }
+        if (c + 1 >= N) { s[j][1] = -INFINITY; s[j][3] = -INFINITY; }
+        mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
+        mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
+    }
+    mx0 = quad_max(mx0);
+    mx1 = quad_max(mx1);
+    float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        s[j][0] = exp2f((s[j][0] - mx0) * sl2); s[j][1] = exp2f((s[j][1] - mx0) * sl2);
+        s[j][2] = exp2f((s[j][2] - mx1) * sl2); s[j][3] = exp2f((s[j][3] - mx1) * sl2);
+        sum0 += s[j][0] + s[j][1];
+        sum1 += s[j][2] + s[j][3];
+    }
+    sum0 = quad_sum(sum0);
+    sum1 = quad_sum(sum1);
+    uint32_t pa[4][4];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+        pa[kk][0] = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
+        pa[kk][1] = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
+        pa[kk][2] = pack_bf16x2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+        pa[kk][3] = pack_bf16x2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+    }
+    float acc[DH / 8][4];
+#pragma unroll
+    for (int j = 0; j < DH / 8; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
+    frag_times_rows<DH>(acc, pa, sV, n_tiles16, lane);
+    const int r0 = m0 + g, r1 = r0 + 8;
+    bf16 *ob = o + (int64_t)b * N * inner + (int64_t)h * DH;
+    store_rows<DH>(ob, inner, acc, r0, r1, N, t, 1.0f / sum0, 1.0f / sum1);
+    if (t == 0) {
+        float *l = lse + ((int64_t)b * H + h) * N;
+        if (r0 < N) l[r0] = mx0 * scale + logf(sum0);
+        if (r1 < N) l[r1] = mx1 * scale + logf(sum1);
+    }
+}
+
+template <int DH>
+__global__ void __launch_bounds__(128) attention_bwd_mma_kernel(const bf16 *__restrict__ qkv, const bf16 *__restrict__ o,
+                                                                 const bf16 *__restrict__ d_o,
+                                                                 const float *__restrict__ lse, bf16 *__restrict__ dqkv,
+                                                                 int N, int H, float scale) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    typedef bf16(*TileD)[DH + 8];
+    typedef bf16(*TileN)[NMAX + 8];
+    TileD sQ = reinterpret_cast<TileD>(smem_raw);
+    TileD sK = sQ + NMAX, sV = sK + NMAX, sdO = sV + NMAX;
+    TileN sP = reinterpret_cast<TileN>(sdO + NMAX);
+    TileN sdS = sP + NMAX;
+
+    const int h = blockIdx.x % H, b = blockIdx.x / H;
+    const int inner = H * DH;
+    const int64_t ld = 3 * (int64_t)inner;
+    const bf16 *base = qkv + (int64_t)b * N * ld + (int64_t)h * DH;
+    const bf16 *ob = o + (int64_t)b * N * inner + (int64_t)h * DH;
+    load_tile<DH>(sQ, base, ld, N);
+    load_tile<DH>(sK, base + inner, ld, N);
+    load_tile<DH>(sV, base + 2 * inner, ld, N);
+    load_tile<DH>(sdO, d_o + (int64_t)b * N * inner + (int64_t)h * DH, inner, N);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = warp * 16;
+    const int g = lane >> 2, t = lane & 3;
+    const int n_tiles16 = (N + 15) / 16;
+    bf16 *dq = dqkv + (int64_t)b * N * ld + (int64_t)h * DH;
+    const bool active = m0 < N;  // this warp owns query rows (and, later, key rows) m0 .. m0+15
+
+    if (active) {
+        const int r0 = m0 + g, r1 = r0 + 8;
+        // D[r] = sum_d dO[r,d] * O[r,d]   (each quad splits the head dim)
+        float D0 = 0.f, D1 = 0.f;
+        for (int d = t * 2; d < DH; d += 8) {
+            if (r0 < N) {
+                const __nv_bfloat162 ov = *reinterpret_cast<const __nv_bfloat162 *>(ob + (int64_t)r0 * inner + d);
+                D0 += __bfloat162float(sdO[r0][d]) * __low2float(ov) + __bfloat162float(sdO[r0][d + 1]) * __high2float(ov);
+            }
+            if (r1 < N) {
+                const __nv_bfloat162 ov = *reinterpret_cast<const __nv_bfloat162 *>(ob + (int64_t)r1 * inner + d);
+                D1 += __bfloat162float(sdO[r1][d]) * __low2float(ov) + __bfloat162float(sdO[r1][d + 1]) * __high2float(ov);
+            }
+        }
+        D0 = quad_sum(D0);
+        D1 = quad_sum(D1);
+        const float *l = lse + ((int64_t)b * H + h) * N;
+        const float l0 = r0 < N ? l[r0] * LOG2E : 0.f, l1 = r1 < N ? l[r1] * LOG2E : 0.f;
+
+        float s[8][4], dp[8][4];
+        rows_times_transposed<DH>(s, sQ, sK, m0, n_tiles16, lane);    // S = Q K^T
+        rows_times_transposed<DH>(dp, sdO, sV, m0, n_tiles16, lane);  // dP = dO V^T
+        const float sl2 = scale * LOG2E;
+        uint32_t dsa[4][4];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = 8 * j + 2 * t;
+            float p[4], ds[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const bool valid = (c + (i & 1) < N) && ((i < 2 ? r0 : r1) < N);
+                p[i] = valid ? exp2f(s[j][i] * sl2 - (i < 2 ? l0 : l1)) : 0.f;
+                ds[i] = p[i] * (dp[j][i] - (i < 2 ? D0 : D1)) * scale;
+            }
+            const uint32_t p01 = pack_bf16x2(p[0], p[1]), p23 = pack_bf16x2(p[2], p[3]);
+            const uint32_t d01 = pack_bf16x2(ds[0], ds[1]), d23 = pack_bf16x2(ds[2], ds[3]);
+            *reinterpret_cast<uint32_t *>(&sP[r0][c]) = p01;
+            *reinterpret_cast<uint32_t *>(&sP[r1][c]) = p23;
+            *reinterpret_cast<uint32_t *>(&sdS[r0][c]) = d01;
+            *reinterpret_cast<uint32_t *>(&sdS[r1][c]) = d23;
+            dsa[j >> 1][(j & 1) * 2] = d01;
+            dsa[j >> 1][(j & 1) * 2 + 1] = d23;
+        }
+        // dQ = dS K
+        float acc[DH / 8][4];
+#pragma unroll
+        for (int j = 0; j < DH / 8; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
+        frag_times_rows<DH>(acc, dsa, sK, n_tiles16, lane);
+        store_rows<DH>(dq, ld, acc, r0, r1, N, t, 1.f, 1.f);
+    }
+    __syncthreads();
+    if (active) {
+        const int r0 = m0 + g, r1 = r0 + 8;  // now key rows
+        float acc[DH / 8][4];
+#pragma unroll
+        for (int j = 0; j < DH / 8; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
+        transposed_times_rows<DH>(acc, sdS, sQ, m0, n_tiles16, lane);  // dK = dS^T Q
+        store_rows<DH>(dq + inner, ld, acc, r0, r1, N, t, 1.f, 1.f);
+#pragma unroll
+        for (int j = 0; j < DH / 8; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
+        transposed_times_rows<DH>(acc, sP, sdO, m0, n_tiles16, lane);  // dV = P^T dO
+        store_rows<DH>(dq + 2 * inner, ld, acc, r0, r1, N, t, 1.f, 1.f);
+    }
+}
+
+template <int DH> constexpr size_t bwd_smem_bytes() {
+    return sizeof(bf16) * (4 * NMAX * (DH + 8) + 2 * NMAX * (NMAX + 8));
+}
+
+template <int DH>
+int launch_bwd(const void *qkv, const void *o, const void *d_o, const float *lse, void *dqkv, int B, int N, int H,
+               float scale, cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(attention_bwd_mma_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)bwd_smem_bytes<DH>());
+        if (e != cudaSuccess) return fail((int)e, "attention_bwd_mma: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        attr_set = true;
+    }
+    attention_bwd_mma_kernel<DH><<<B * H, 128, bwd_smem_bytes<DH>(), stream>>>(
+        (const bf16 *)qkv, (const bf16 *)o, (const bf16 *)d_o, lse, (bf16 *)dqkv, N, H, scale);
+    return check_launch("attention_bwd_mma");
+}
+
+}  // namespace
+
+bool attention_mma_supported(int N, int dh) { return N <= NMAX && (dh == 16 || dh == 32 || dh == 64); }
+
+int attention_fwd_mma(const void *qkv, void *o, float *lse, int B, int N, int H, int dh, float scale,
+                      cudaStream_t stream) {
+    const bf16 *q = (const bf16 *)qkv;
+    bf16 *op = (bf16 *)o;
+    switch (dh) {
+        case 16: attention_fwd_mma_kernel<16><<<B * H, 128, 0, stream>>>(q, op, lse, N, H, scale); break;
+        case 32: attention_fwd_mma_kernel<32><<<B * H, 128, 0, stream>>>(q, op, lse, N, H, scale); break;
+        case 64: attention_fwd_mma_kernel<64><<<B * H, 128, 0, stream>>>(q, op, lse, N, H, scale); break;
+        default: return fail(-1, "attention_fwd_mma: unsupported head dim %d", dh);
+    }
+    return check_launch("attention_fwd_mma");
+}
+
+int attention_bwd_mma(const void *qkv, const void *o, const void *d_o, const float *lse, void *dqkv, int B, int N,
+                      int H, int dh, float scale, cudaStream_t stream) {
+    switch (dh) {
+        case 16: return launch_bwd<16>(qkv, o, d_o, lse, dqkv, B, N, H, scale, stream);
+        case 32: return launch_bwd<32>(qkv, o, d_o, lse, dqkv, B, N, H, scale, stream);
+        case 64: return launch_bwd<64>(qkv, o, d_o, lse, dqkv, B, N, H, scale, stream);
+        default: return fail(-1, "attention_bwd_mma: unsupported head dim %d", dh);
+    }
+}
+
+}  // namespace ecgvit

@@ -9,7 +9,8 @@ namespace ecgvit {
 
 namespace {
 
-enum { H_LR = 0, H_BETA1, H_BETA2, H_EPS, H_WD, H_BC1, H_BC2, H_MAXNORM, H_GSCALE };
+enum { H_LR = 0, H_BETA1, H_BETA2, H_EPS, H_WD, H_BC1, H_BC2, H_MAXNORM, H_GSCALE,
+       H_ONE_MINUS_B1, H_ONE_MINUS_B2, H_DECAY, H_STEP_SIZE, H_BC2_SQRT };
 enum { S_SUMSQ = 0, S_NONFINITE, S_NORM };
 
 __global__ void __launch_bounds__(256) grad_sumsq_kernel(const float *__restrict__ g, int64_t n,
@@ -55,10 +56,11 @@ __global__ void __launch_bounds__(256) adamw_kernel(float *__restrict__ p, float
     if (blockIdx.x == 0 && threadIdx.x == 0) stats[S_NORM] = total_norm;
     // error_if_nonfinite: leave parameters and state untouched; the host raises when it polls the flag
     if (!isfinite(total_norm)) return;
-    const float lr = hyper[H_LR], beta1 = hyper[H_BETA1], beta2 = hyper[H_BETA2], eps = hyper[H_EPS];
-    const float decay = 1.0f - lr * hyper[H_WD];
-    const float step_size = lr / hyper[H_BC1];
-    const float inv_bc2_sqrt = 1.0f / sqrtf(hyper[H_BC2]);
+    // the derived scalars are computed by the host in double precision exactly like torch.optim.AdamW does
+    // (1 - beta in fp32 differs from fp32(1 - beta) by 1.3e-5 relative for beta2 = 0.999)
+    const float beta2 = hyper[H_BETA2], eps = hyper[H_EPS];
+    const float one_m_b1 = hyper[H_ONE_MINUS_B1], one_m_b2 = hyper[H_ONE_MINUS_B2];
+    const float decay = hyper[H_DECAY], step_size = hyper[H_STEP_SIZE], bc2_sqrt = hyper[H_BC2_SQRT];
     const float gmul = hyper[H_GSCALE] * clip;
     const int64_t n4 = n / 4;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
@@ -71,10 +73,10 @@ __global__ void __launch_bounds__(256) adamw_kernel(float *__restrict__ p, float
         for (int k = 0; k < 4; ++k) {
             const float gr = gg[k] * gmul;
             pp[k] *= decay;
-            mm[k] = fmaf(gr - mm[k], 1.0f - beta1, mm[k]);
-            vv[k] = fmaf(vv[k], beta2, (1.0f - beta2) * gr * gr);
-            const float denom = sqrtf(vv[k]) * inv_bc2_sqrt + eps;
-            pp[k] -= step_size * (mm[k] / denom);
+            mm[k] = fmaf(gr - mm[k], one_m_b1, mm[k]);            // exp_avg.lerp_(g, 1 - beta1)
+            vv[k] = fmaf(one_m_b2 * gr, gr, vv[k] * beta2);        // exp_avg_sq.mul_(beta2).addcmul_(g, g, 1 - beta2)
+            const float denom = sqrtf(vv[k]) / bc2_sqrt + eps;     // (exp_avg_sq.sqrt() / sqrt(bc2)).add_(eps)
+            pp[k] -= step_size * (mm[k] / denom);                  // addcdiv_(exp_avg, denom, -lr / bc1)
         }
         reinterpret_cast<float4 *>(p)[i] = make_float4(pp[0], pp[1], pp[2], pp[3]);
         reinterpret_cast<float4 *>(m)[i] = make_float4(mm[0], mm[1], mm[2], mm[3]);

@@ -14,7 +14,6 @@ import torch
 
 from . import _lib
 
-_H_LR, _H_B1, _H_B2, _H_EPS, _H_WD, _H_BC1, _H_BC2, _H_MAXNORM, _H_GSCALE = range(9)
 
 
 def _flat_grads(model):
@@ -45,7 +44,7 @@ def _scratch(model):
 
 def _upload(hyper, values):
     # pageable source: the driver stages the 64 bytes before returning, so the list can be reused immediately
-    hyper.copy_(torch.tensor(values + [0.0] * (16 - len(values)), dtype=torch.float32))
+    hyper.copy_(torch.tensor(values, dtype=torch.float32))
 
 
 def clip_grad_norm_(model, max_norm, norm_type=2.0, error_if_nonfinite=False):
@@ -55,7 +54,7 @@ def clip_grad_norm_(model, max_norm, norm_type=2.0, error_if_nonfinite=False):
     lib = _lib.load()
     g = _flat_grads(model)
     hyper, stats = _scratch(model)
-    _upload(hyper, [0.0, 0.0, 0.0, 0.0, 0.0, 1.0, 1.0, float(max_norm), 1.0])
+    _upload(hyper, _lib.adamw_hyper(0.0, 0.9, 0.999, 1e-8, 0.0, 1, float(max_norm), 1.0))
     st = torch.cuda.current_stream().cuda_stream
     _lib.check(lib.ecgvit_grad_sumsq(g.data_ptr(), g.numel(), hyper.data_ptr(), stats.data_ptr(), st), 'grad_sumsq')
     _lib.check(lib.ecgvit_grad_scale_by_clip(g.data_ptr(), g.numel(), hyper.data_ptr(), stats.data_ptr(), st),
@@ -91,9 +90,8 @@ class FusedAdamW(torch.optim.Optimizer):
         self._step += 1
         hyper, stats = _scratch(model)
         b1, b2 = grp['betas']
-        # [lr, beta1, beta2, eps, wd, 1-beta1^t, 1-beta2^t, max_norm (0: clipping is a separate call), grad_scale]
-        _upload(hyper, [grp['lr'], b1, b2, grp['eps'], grp['weight_decay'], 1.0 - b1 ** self._step,
-                        1.0 - b2 ** self._step, 0.0, 1.0])
+        # max_norm 0: clipping is a separate call in the reference loop
+        _upload(hyper, _lib.adamw_hyper(grp['lr'], b1, b2, grp['eps'], grp['weight_decay'], self._step, 0.0, 1.0))
         stats.zero_()
         st = torch.cuda.current_stream().cuda_stream
         _lib.check(_lib.load().ecgvit_adamw_step(model._flat_p.data_ptr(), self._m.data_ptr(), self._v.data_ptr(),

@@ -17,7 +17,6 @@ import torch
 
 from . import _lib
 
-_H_LR, _H_B1, _H_B2, _H_EPS, _H_WD, _H_BC1, _H_BC2, _H_MAXNORM, _H_GSCALE = range(9)
 
 
 def lr_multiplier(schedule, step, n_warmup, n_total):
@@ -88,10 +87,10 @@ class FusedTrainer:
     def _upload_hyper(self):
         t = self.step_count + 1  # AdamW's own step counter starts at 1
         b1, b2 = self.betas
-        vals = [self.current_lr(), b1, b2, self.eps, self.wd, 1.0 - b1 ** t, 1.0 - b2 ** t,
-                self.max_grad_norm if self.max_grad_norm is not None else 0.0, 1.0 / self.world]
+        vals = _lib.adamw_hyper(self.current_lr(), b1, b2, self.eps, self.wd, t,
+                                self.max_grad_norm if self.max_grad_norm is not None else 0.0, 1.0 / self.world)
         # pageable source: staged by the driver before the call returns, so no host buffer is ever live across steps
-        self.hyper.copy_(torch.tensor(vals + [0.0] * (16 - len(vals)), dtype=torch.float32))
+        self.hyper.copy_(torch.tensor(vals, dtype=torch.float32))
 
     # ---- the step ----------------------------------------------------------------------------------
     def _device_step(self, sample_values, labels):

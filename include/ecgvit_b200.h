@@ -124,6 +124,8 @@ int ecgvit_colsum(const void *x, float *out, int M, int N, int64_t ld, int dtype
  *      fp32 buffers.  hyper (device, fp32[16]):
  *        [0] lr  [1] beta1  [2] beta2  [3] eps  [4] weight_decay  [5] 1-beta1^t  [6] 1-beta2^t
  *        [7] max_grad_norm (<=0: no clipping)  [8] grad_scale (1/world for DDP sum-allreduce)
+ *        [9] 1-beta1  [10] 1-beta2  [11] 1-lr*weight_decay  [12] lr/(1-beta1^t)  [13] sqrt(1-beta2^t)
+ *        ([9..13] are derived by the host in double precision, as torch.optim.AdamW derives them)
  *      stats (device, fp32[4]): [0] sum of squares of (grad_scale*g)  [1] non-finite flag  [2] total_norm (written by adamw) */
 int ecgvit_grad_sumsq(const float *g, int64_t n, const float *hyper, float *stats, void *stream);
 int ecgvit_adamw_step(float *p, float *m, float *v, const float *g, void *shadow_bf16, int64_t n,

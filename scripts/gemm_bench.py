@@ -1,0 +1,79 @@
+"""Times every GEMM shape of the base-model step (B=256, M=13056) in isolation: CUDA events around back-to-back
+launches, inputs rotated over buffers larger than L2.  Usage: python scripts/gemm_bench.py [reps]"""
+import ctypes
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import ecg_b200
+from ecg_b200 import _lib as L
+
+lib = L.load()
+M, d, mlp, PC, Bn = 13056, 768, 3072, 600, 12800
+# name, (M, N, K), a_kmajor, b_kmajor, epilogue
+SHAPES = [
+    ('qkv_fwd', (M, 3 * d, d), 1, 1, L.EPI_STORE), ('out_fwd', (M, d, d), 1, 1, L.EPI_BIAS_RES),
+    ('ff1_fwd', (M, mlp, d), 1, 1, L.EPI_BIAS_GELU), ('ff2_fwd', (M, d, mlp), 1, 1, L.EPI_BIAS_RES),
+    ('ff2_dgrad', (M, mlp, d), 1, 0, L.EPI_DGELU), ('ff1_dgrad', (M, d, mlp), 1, 0, L.EPI_STORE),
+    ('out_dgrad', (M, d, d), 1, 0, L.EPI_STORE), ('qkv_dgrad', (M, d, 3 * d), 1, 0, L.EPI_STORE),
+    ('ff2_wgrad', (d, mlp, M), 0, 0, L.EPI_ATOMIC_F32), ('ff1_wgrad', (mlp, d, M), 0, 0, L.EPI_ATOMIC_F32),
+    ('out_wgrad', (d, d, M), 0, 0, L.EPI_ATOMIC_F32), ('qkv_wgrad', (3 * d, d, M), 0, 0, L.EPI_ATOMIC_F32),
+    ('embed_fwd', (Bn, d, PC), 1, 1, L.EPI_STORE), ('embed_wgrad', (d, PC, Bn), 0, 0, L.EPI_ATOMIC_F32),
+]
+reps = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+if len(sys.argv) > 2:
+    SHAPES = [s for s in SHAPES if s[0] in sys.argv[2].split(',')]
+with_cublas = os.environ.get('GEMM_BENCH_NO_CUBLAS') is None
+st = torch.cuda.current_stream().cuda_stream
+rows = []
+for name, (m, n, k), ak, bk, epi in SHAPES:
+    nbuf = 3
+    A = [torch.randn((m, k) if ak else (k, m), device='cuda').bfloat16() for _ in range(nbuf)]
+    B = [torch.randn((n, k) if bk else (k, n), device='cuda').bfloat16() for _ in range(nbuf)]
+    odt = torch.float32 if epi == L.EPI_ATOMIC_F32 else torch.bfloat16
+    out = [torch.zeros(m, n, device='cuda', dtype=odt) for _ in range(nbuf)]
+    out2 = [torch.zeros(m, n, device='cuda', dtype=torch.bfloat16) for _ in range(nbuf)]
+    aux = [torch.randn(m, n, device='cuda').bfloat16() for _ in range(nbuf)]
+    bias = torch.randn(n, device='cuda')
+
+    def launch(i):
+        j = i % nbuf
+        g = L.GemmArgs(m, n, k, A[j].data_ptr(), A[j].stride(0), ak, B[j].data_ptr(), B[j].stride(0), bk, epi,
+                       out[j].data_ptr(), n, out2[j].data_ptr(), aux[j].data_ptr(),
+                       bias.data_ptr() if epi != L.EPI_ATOMIC_F32 else None, L.BF16, 0, 0)
+        L.check(lib.ecgvit_gemm(ctypes.byref(g), st), 'gemm')
+
+    for i in range(3):
+        launch(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(reps):
+        launch(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    # cuBLAS on the same contraction, for reference only
+    Am = A[0] if ak else A[0].t()
+    Bm = B[0].t() if bk else B[0]
+    ms_cublas = float('nan')
+    if with_cublas:
+        for _ in range(3):
+            torch.matmul(Am, Bm)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            torch.matmul(Am, Bm)
+        e1.record()
+        torch.cuda.synchronize()
+        ms_cublas = e0.elapsed_time(e1) / reps
+    tf = 2.0 * m * n * k / (ms * 1e-3) / 1e12
+    rows.append(dict(name=name, M=m, N=n, K=k, ms=round(ms, 4), tflops=round(tf, 1),
+                     cublas_ms=round(ms_cublas, 4), cublas_tflops=round(2.0 * m * n * k / (ms_cublas * 1e-3) / 1e12, 1)))
+    print(rows[-1], flush=True)
+    del A, B, out, out2, aux
+os.makedirs('gpurun_out', exist_ok=True)
+json.dump(rows, open('gpurun_out/gemm_bench.json', 'w'), indent=1)

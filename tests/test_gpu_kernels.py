@@ -290,7 +290,7 @@ def test_clip_and_adamw_match_torch(lib, max_norm):
         else:
             norm = g.norm()
         opt.step()
-        hyper.copy_(torch.tensor([3e-4, 0.9, 0.999, 1e-8, 1e-2, 1 - 0.9 ** t, 1 - 0.999 ** t, max_norm, 1.0] + [0.0] * 7))
+        hyper.copy_(torch.tensor(L.adamw_hyper(3e-4, 0.9, 0.999, 1e-8, 1e-2, t, max_norm, 1.0)))
         L.check(lib.ecgvit_grad_sumsq(g.data_ptr(), n, hyper.data_ptr(), stats.data_ptr(), stream()), 'sumsq')
         L.check(lib.ecgvit_adamw_step(p.data_ptr(), m.data_ptr(), v.data_ptr(), g.data_ptr(), shadow.data_ptr(), n,
                                       hyper.data_ptr(), stats.data_ptr(), stream()), 'adamw')
@@ -308,7 +308,7 @@ def test_adamw_skips_update_on_nonfinite_gradients(lib):
     g = torch.randn(n, device='cuda')
     g[17] = float('inf')
     hyper, stats = torch.zeros(16, device='cuda'), torch.zeros(4, device='cuda')
-    hyper.copy_(torch.tensor([3e-4, 0.9, 0.999, 1e-8, 1e-2, 0.1, 0.001, 1.0, 1.0] + [0.0] * 7))
+    hyper.copy_(torch.tensor(L.adamw_hyper(3e-4, 0.9, 0.999, 1e-8, 1e-2, 1, 1.0, 1.0)))
     L.check(lib.ecgvit_grad_sumsq(g.data_ptr(), n, hyper.data_ptr(), stats.data_ptr(), stream()), 'sumsq')
     L.check(lib.ecgvit_adamw_step(p.data_ptr(), m.data_ptr(), v.data_ptr(), g.data_ptr(), None, n, hyper.data_ptr(),
                                   stats.data_ptr(), stream()), 'adamw')
