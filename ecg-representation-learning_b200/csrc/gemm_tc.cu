@@ -15,6 +15,7 @@
 #include "ptx.cuh"
 
 #include <cudaTypedefs.h>
+#include <stdlib.h>
 
 namespace ecgvit {
 
@@ -200,6 +201,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
 }
 
+#include "gemm_tc_pair.cuh"
+
 // ---- host side ------------------------------------------------------------------------------------
 PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
     static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
@@ -274,6 +277,62 @@ template <int BN> int dispatch(const ecgvit_gemm_args *g, int split_k, cudaStrea
                 g->b_kmajor, mode);
 }
 
+
+template <int BN, bool A_MN, bool B_MN, int MODE>
+int launch_pair(const ecgvit_gemm_args *g, int split_k, cudaStream_t stream) {
+    using Cfg = PairCfg<BN>;
+    CUtensorMap ta, tb;
+    int rc;
+    if (!A_MN) rc = make_tmap(&ta, g->A, g->K, g->M, g->lda, BK, BM);
+    else rc = make_tmap(&ta, g->A, g->M, g->K, g->lda, 64, BK);
+    if (rc) return rc;
+    if (!B_MN) rc = make_tmap(&tb, g->B, g->K, g->N, g->ldb, BK, Cfg::B_HALF);
+    else rc = make_tmap(&tb, g->B, g->N, g->K, g->ldb, 64, BK);
+    if (rc) return rc;
+    auto kern = gemm_tc2_kernel<BN, A_MN, B_MN, MODE>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute(gemm_tc2): %s", cudaGetErrorString(e));
+        attr_set = true;
+    }
+    const int tiles_m = (g->M + 2 * BM - 1) / (2 * BM), tiles_n = (g->N + BN - 1) / BN;
+    const int units = tiles_m * tiles_n * split_k;
+    const int clusters = sm_count() / 2;
+    const int grid = 2 * (units < clusters ? units : clusters);
+    EpiParams ep{g->out, g->out2, g->aux, g->bias, g->ldo};
+    kern<<<grid, kNumThreads, Cfg::SMEM_BYTES, stream>>>(ta, tb, g->M, g->N, g->K, split_k, ep);
+    return check_launch("gemm_tc2");
+}
+
+template <int BN> int dispatch_pair(const ecgvit_gemm_args *g, int split_k, cudaStream_t s) {
+    const bool a_mn = !g->a_kmajor, b_mn = !g->b_kmajor;
+    const int mode = g->epilogue;
+#define ECGVIT_CASE(AM, BMN, MODE) \
+    if (a_mn == AM && b_mn == BMN && mode == MODE) return launch_pair<BN, AM, BMN, MODE>(g, split_k, s);
+    ECGVIT_CASE(false, false, ECGVIT_EPI_STORE)
+    ECGVIT_CASE(false, false, ECGVIT_EPI_BIAS_RES)
+    ECGVIT_CASE(false, false, ECGVIT_EPI_BIAS_GELU)
+    ECGVIT_CASE(false, true, ECGVIT_EPI_STORE)
+    ECGVIT_CASE(false, true, ECGVIT_EPI_DGELU)
+    ECGVIT_CASE(true, true, ECGVIT_EPI_ATOMIC_F32)
+    ECGVIT_CASE(true, true, ECGVIT_EPI_STORE)
+    ECGVIT_CASE(true, false, ECGVIT_EPI_STORE)
+#undef ECGVIT_CASE
+    return fail(-1, "gemm(bf16): unsupported combination a_kmajor=%d b_kmajor=%d epilogue=%d", g->a_kmajor,
+                g->b_kmajor, mode);
+}
+
+// ECGVIT_GEMM_CTA_GROUP=1 selects the single-CTA kernel (kept for A/B measurements); default is the CTA pair
+int cta_group_setting() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("ECGVIT_GEMM_CTA_GROUP");
+        v = (e != nullptr && e[0] == '1') ? 1 : 2;
+    }
+    return v;
+}
+
 }  // namespace
 
 int gemm_bf16_tc(const ecgvit_gemm_args *g, cudaStream_t stream) {
@@ -291,12 +350,14 @@ int gemm_bf16_tc(const ecgvit_gemm_args *g, cudaStream_t stream) {
     ECGVIT_REQUIRE(split_k == 1 || g->epilogue == ECGVIT_EPI_ATOMIC_F32, "gemm: split_k needs the atomic epilogue");
     if (g->epilogue == ECGVIT_EPI_ATOMIC_F32 && g->split_k <= 0) {
         // auto: smallest split (>= 8 k blocks each) whose work units fill >= 90 % of their last wave
-        const long tiles = (long)((g->M + BM - 1) / BM) * ((g->N + 255) / 256);
+        const int pair = cta_group_setting() == 2 ? 2 : 1;  // work units are 256-row tiles run by CTA pairs
+        const int workers = sms / pair;
+        const long tiles = (long)((g->M + pair * BM - 1) / (pair * BM)) * ((g->N + 255) / 256);
         int best = 1;
         double best_eff = 0.0;
         for (int s = 1; s <= 32 && s * 8 <= kb_total; ++s) {
             const long units = tiles * s;
-            const double eff = (double)units / (double)(((units + sms - 1) / sms) * sms);
+            const double eff = (double)units / (double)(((units + workers - 1) / workers) * workers);
             if (eff > best_eff + 1e-9) { best_eff = eff; best = s; }
             if (eff >= 0.9) { best = s; break; }
         }
@@ -306,13 +367,23 @@ int gemm_bf16_tc(const ecgvit_gemm_args *g, cudaStream_t stream) {
     // every split must own at least one k block
     while (split_k > 1 && ((kb_total + split_k - 1) / split_k) * (split_k - 1) >= kb_total) --split_k;
 
-    // tile width: fewer, wider tiles unless the narrower tile wastes less of the last wave
-        auto cost = [&](int bn) {
+    // Tile width.  Narrow tiles stage more bytes per flop (a 128-wide single-CTA tile needs the full 128 B/clk of
+    // shared-memory bandwidth for operand reads alone), so they are only chosen when the wide tile would waste a
+    // large part of its last wave.
+    if (cta_group_setting() == 2) {
+        const int clusters = sms / 2;
+        auto waves2 = [&](int bn) {
+            const long units = (long)((g->M + 2 * BM - 1) / (2 * BM)) * ((g->N + bn - 1) / bn) * split_k;
+            return (units + clusters - 1) / clusters;
+        };
+        const bool use128 = (g->N <= 128) || (waves2(128) * 128 * 1.15 < waves2(256) * 256);
+        return use128 ? dispatch_pair<128>(g, split_k, stream) : dispatch_pair<256>(g, split_k, stream);
+    }
+    auto waves = [&](int bn) {
         const long units = (long)((g->M + BM - 1) / BM) * ((g->N + bn - 1) / bn) * split_k;
-        const long waves = (units + sms - 1) / sms;
-        return waves * bn;
+        return (units + sms - 1) / sms;
     };
-    const bool use128 = (g->N <= 128) || (cost(128) < cost(256));
+    const bool use128 = (g->N <= 128) || (waves(128) * 128 * 1.6 < waves(256) * 256);
     return use128 ? dispatch<128>(g, split_k, stream) : dispatch<256>(g, split_k, stream);
 }
 
