@@ -289,6 +289,14 @@ int launch_pair(const ecgvit_gemm_args *g, int split_k, cudaStream_t stream) {
     if (!B_MN) rc = make_tmap(&tb, g->B, g->K, g->N, g->ldb, BK, Cfg::B_HALF);
     else rc = make_tmap(&tb, g->B, g->N, g->K, g->ldb, 64, BK);
     if (rc) return rc;
+    // outputs leave through TMA stores of 32-row x 64-column (128-byte) swizzled tiles; TMA clips at M x N
+    CUtensorMap to, to2;
+    to = ta;
+    to2 = ta;
+    if (MODE != ECGVIT_EPI_ATOMIC_F32) {
+        if ((rc = make_tmap(&to, g->out, g->N, g->M, g->ldo, 64, 32))) return rc;
+        if (MODE == ECGVIT_EPI_BIAS_GELU && (rc = make_tmap(&to2, g->out2, g->N, g->M, g->ldo, 64, 32))) return rc;
+    }
     auto kern = gemm_tc2_kernel<BN, A_MN, B_MN, MODE>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -301,7 +309,7 @@ int launch_pair(const ecgvit_gemm_args *g, int split_k, cudaStream_t stream) {
     const int clusters = sm_count() / 2;
     const int grid = 2 * (units < clusters ? units : clusters);
     EpiParams ep{g->out, g->out2, g->aux, g->bias, g->ldo};
-    kern<<<grid, kNumThreads, Cfg::SMEM_BYTES, stream>>>(ta, tb, g->M, g->N, g->K, split_k, ep);
+    kern<<<grid, kNumThreads, Cfg::SMEM_BYTES, stream>>>(ta, tb, to, to2, g->M, g->N, g->K, split_k, ep);
     return check_launch("gemm_tc2");
 }
 

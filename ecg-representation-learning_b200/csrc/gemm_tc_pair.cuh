@@ -18,14 +18,72 @@ template <int BN> struct PairCfg {
     static constexpr int B_HALF = BN / 2;
     static constexpr int B_STAGE_BYTES = B_HALF * BK * 2;
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;  // per CTA
-    static constexpr int STAGES = (196608 / STAGE_BYTES) > 8 ? 8 : (196608 / STAGE_BYTES);
+    // epilogue staging: every epilogue warp owns two 32-row x 128-byte (64 bf16) swizzled tiles for TMA stores
+    static constexpr int EPI_TILE_BYTES = 32 * 128;
+    static constexpr int EPI_BYTES = kNumEpilogueWarps * 2 * EPI_TILE_BYTES;  // 64 KB
+    static constexpr int PIPE_BUDGET = 232448 - 1024 - 256 - EPI_BYTES;
+    static constexpr int STAGES = (PIPE_BUDGET / STAGE_BYTES) > 8 ? 8 : (PIPE_BUDGET / STAGE_BYTES);
     static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 + 256;
 };
+
+// Epilogue math for 64 consecutive accumulator columns of one row (thread = row), written as bf16 into the warp's
+// swizzled staging tile(s); the caller then issues one TMA store per tile (TMA clips rows >= M / cols >= N).
+template <int MODE>
+__device__ __forceinline__ void epilogue_chunk64(const EpiParams &ep, int64_t row, bool row_ok, int col_base, int N,
+                                                 const uint32_t r[64], uint8_t *stage0, uint8_t *stage1, int lane) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int col = col_base + 8 * j;
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[8 * j + i]);
+        const bool ok = row_ok && col < N;  // N % 8 == 0, so a group of 8 columns is entirely in or out
+        if (MODE != ECGVIT_EPI_DGELU && ep.bias != nullptr && col < N) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4 *>(ep.bias + col));
+            const float4 b1 = __ldg(reinterpret_cast<const float4 *>(ep.bias + col + 4));
+            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+            v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+        }
+        const uint32_t soff = static_cast<uint32_t>(lane) * 128u + (static_cast<uint32_t>(j ^ (lane & 7)) << 4);
+        if (MODE == ECGVIT_EPI_BIAS_RES) {
+            if (ok) {
+                float a[8];
+                load8(reinterpret_cast<const bf16 *>(ep.aux) + row * ep.ldo + col, a);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] += a[i];
+            }
+        } else if (MODE == ECGVIT_EPI_DGELU) {
+            if (ok) {
+                float u[8];
+                load8(reinterpret_cast<const bf16 *>(ep.aux) + row * ep.ldo + col, u);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] *= gelu_grad<false>(u[i]);
+            }
+        }
+        uint4 packed;
+        packed.x = pack_bf16x2(v[0], v[1]); packed.y = pack_bf16x2(v[2], v[3]);
+        packed.z = pack_bf16x2(v[4], v[5]); packed.w = pack_bf16x2(v[6], v[7]);
+        *reinterpret_cast<uint4 *>(stage0 + soff) = packed;
+        if (MODE == ECGVIT_EPI_BIAS_GELU) {
+            // gelu of the ROUNDED pre-activation: that is the value backward differentiates
+            float lo, hi, h[8];
+            unpack_bf16x2(packed.x, lo, hi); h[0] = gelu_fwd<false>(lo); h[1] = gelu_fwd<false>(hi);
+            unpack_bf16x2(packed.y, lo, hi); h[2] = gelu_fwd<false>(lo); h[3] = gelu_fwd<false>(hi);
+            unpack_bf16x2(packed.z, lo, hi); h[4] = gelu_fwd<false>(lo); h[5] = gelu_fwd<false>(hi);
+            unpack_bf16x2(packed.w, lo, hi); h[6] = gelu_fwd<false>(lo); h[7] = gelu_fwd<false>(hi);
+            uint4 ph;
+            ph.x = pack_bf16x2(h[0], h[1]); ph.y = pack_bf16x2(h[2], h[3]);
+            ph.z = pack_bf16x2(h[4], h[5]); ph.w = pack_bf16x2(h[6], h[7]);
+            *reinterpret_cast<uint4 *>(stage1 + soff) = ph;
+        }
+    }
+}
 
 template <int BN, bool A_MN, bool B_MN, int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
-gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, int M, int N,
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_out2, int M, int N,
                 int K, int split_k, EpiParams ep) {
     using Cfg = PairCfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
@@ -33,7 +91,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint8_t *epi_smem = smem + STAGES * Cfg::STAGE_BYTES;  // 1024-byte aligned (stage sizes are multiples of 8 KB)
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(epi_smem + Cfg::EPI_BYTES);
     uint64_t *empty_bar = full_bar + STAGES;
     uint64_t *tmem_full_bar = empty_bar + STAGES;
     uint64_t *tmem_empty_bar = tmem_full_bar + 2;
@@ -49,6 +108,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&tmap_a);
         ptx::prefetch_tensormap(&tmap_b);
+        if (MODE != ECGVIT_EPI_ATOMIC_F32) ptx::prefetch_tensormap(&tmap_out);
+        if (MODE == ECGVIT_EPI_BIAS_GELU) ptx::prefetch_tensormap(&tmap_out2);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -149,7 +210,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         const int q = warp & 3;
         const int half = (warp - 4) >> 2;
         constexpr int COLS_PER_WARP = BN / 2;
+        uint8_t *stage0 = epi_smem + (warp - 4) * 2 * Cfg::EPI_TILE_BYTES;
+        uint8_t *stage1 = stage0 + Cfg::EPI_TILE_BYTES;
         int it = 0;
+        int buf = 0;
         for (int u = cluster_id; u < num_units; u += num_clusters, ++it) {
             const int tile_n = u % tiles_n;
             const int tile_m = (u / tiles_n) % tiles_m;
@@ -157,23 +221,56 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             const uint32_t acc_phase = (it >> 1) & 1;
             ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
             ptx::tcgen05_fence_after();
-            const int64_t row = static_cast<int64_t>(tile_m) * BM2 + rank * BM + q * 32 + lane;
+            const int row_base = tile_m * BM2 + rank * BM + q * 32;
+            const int64_t row = static_cast<int64_t>(row_base) + lane;
+            if (MODE == ECGVIT_EPI_ATOMIC_F32) {
 #pragma unroll 1
-            for (int c = 0; c < COLS_PER_WARP / 32; ++c) {
-                const int col0 = half * COLS_PER_WARP + c * 32;
-                uint32_t r[32];
-                ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + col0, r);
-                ptx::tmem_ld_wait();
-                if (row < M) {
+                for (int c = 0; c < COLS_PER_WARP / 32; ++c) {
+                    const int col0 = half * COLS_PER_WARP + c * 32;
+                    uint32_t r[32];
+                    ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + col0, r);
+                    ptx::tmem_ld_wait();
+                    if (row < M) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int col = tile_n * BN + col0 + j * 8;
-                        if (col < N) {
-                            float v[8];
+                        for (int j = 0; j < 4; ++j) {
+                            const int col = tile_n * BN + col0 + j * 8;
+                            if (col < N) {
+                                float v[8];
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[j * 8 + i]);
-                            epilogue_store<MODE, bf16, 8, false>(ep, row, col, v);
+                                for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[j * 8 + i]);
+                                epilogue_store<MODE, bf16, 8, false>(ep, row, col, v);
+                            }
                         }
+                    }
+                }
+            } else {
+#pragma unroll 1
+                for (int c = 0; c < COLS_PER_WARP / 64; ++c) {
+                    const int col0 = half * COLS_PER_WARP + c * 64;
+                    const int col_base = tile_n * BN + col0;
+                    if (col_base >= N) break;  // warp-uniform: the whole 64-column chunk is outside the matrix
+                    uint32_t r[64];
+                    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + col0;
+                    ptx::tmem_ld_32x32(taddr, r);
+                    ptx::tmem_ld_32x32(taddr + 32, r + 32);
+                    ptx::tmem_ld_wait();
+                    uint8_t *s0, *s1;
+                    if (MODE == ECGVIT_EPI_BIAS_GELU) {
+                        s0 = stage0; s1 = stage1;
+                        if (lane == 0) ptx::tma_store_wait_read<0>();  // previous chunk's two stores have read smem
+                    } else {
+                        s0 = buf ? stage1 : stage0; s1 = nullptr;
+                        if (lane == 0) ptx::tma_store_wait_read<1>();  // the store that used this buffer two chunks ago
+                        buf ^= 1;
+                    }
+                    __syncwarp();
+                    epilogue_chunk64<MODE>(ep, row, row < M, col_base, N, r, s0, s1, lane);
+                    ptx::fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
+                    __syncwarp();
+                    if (lane == 0) {
+                        ptx::tma_store_2d(&tmap_out, s0, col_base, row_base);
+                        if (MODE == ECGVIT_EPI_BIAS_GELU) ptx::tma_store_2d(&tmap_out2, s1, col_base, row_base);
+                        ptx::tma_store_commit();
                     }
                 }
             }
@@ -181,6 +278,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive_cluster(&tmem_empty_bar[acc], 0);  // the leader's barrier
         }
+        if (MODE != ECGVIT_EPI_ATOMIC_F32 && lane == 0) ptx::tma_store_wait_all<0>();
     }
 
     ptx::tcgen05_fence_before();

@@ -197,3 +197,25 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t *bar, uint16_t cta_mask
 
 }  // namespace ptx
 }  // namespace ecgvit
+
+// =====================================================================================================
+// TMA stores (shared -> global), bulk async-group completion
+namespace ecgvit {
+namespace ptx {
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *m, const void *src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until at most N of this thread's bulk groups still have to READ their shared-memory source
+template <int N> __device__ __forceinline__ void tma_store_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N> __device__ __forceinline__ void tma_store_wait_all() {
+    asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+
+}  // namespace ptx
+}  // namespace ecgvit

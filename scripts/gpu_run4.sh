@@ -1,0 +1,11 @@
+#!/bin/bash
+mkdir -p gpurun_out
+run() { local name=$1 t=$2; shift 2; echo "=== $name" | tee -a gpurun_out/summary.txt; timeout -s KILL $t "$@" > gpurun_out/$name.log 2>&1; echo "exit=$? $(tail -n 1 gpurun_out/$name.log | cut -c1-300)" | tee -a gpurun_out/summary.txt; }
+: > gpurun_out/summary.txt
+PT="python -m pytest -q --tb=short -p no:cacheprovider"
+run k_tc2_layouts 300 $PT tests/test_gpu_kernels.py -m gpu -k "tcgen05_layouts"
+run k_tc2_rest 600 $PT tests/test_gpu_kernels.py -m gpu -k "wgrad or persistent or epilogues"
+run parity_all 900 $PT tests/test_gpu_parity.py -m gpu
+run gemm_bench2 600 python scripts/gemm_bench.py 20
+run bench 900 python bench.py --steps 10 --warmup 3 --profile-json gpurun_out/profile.json
+cat gpurun_out/summary.txt
