@@ -218,7 +218,7 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 
 // 2-D bf16 tensor map over a row-major [outer, inner] matrix with leading dimension ld (elements)
 int make_tmap(CUtensorMap *tm, const void *base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
-              uint32_t box_outer) {
+              uint32_t box_outer, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
     PFN_cuTensorMapEncodeTiled_v12000 enc = get_encode_fn();
     if (enc == nullptr) return fail(-2, "cuTensorMapEncodeTiled not available from the driver");
     cuuint64_t dims[2] = {inner, outer};
@@ -226,7 +226,7 @@ int make_tmap(CUtensorMap *tm, const void *base, uint64_t inner, uint64_t outer,
     cuuint32_t box[2] = {box_inner, box_outer};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(-3, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     return 0;
@@ -280,7 +280,7 @@ template <int BN> int dispatch(const ecgvit_gemm_args *g, int split_k, cudaStrea
 
 template <int BN, bool A_MN, bool B_MN, int MODE>
 int launch_pair(const ecgvit_gemm_args *g, int split_k, cudaStream_t stream) {
-    using Cfg = PairCfg<BN>;
+    using Cfg = PairCfg<BN, B_MN>;
     CUtensorMap ta, tb;
     int rc;
     if (!A_MN) rc = make_tmap(&ta, g->A, g->K, g->M, g->lda, BK, BM);
@@ -289,13 +289,15 @@ int launch_pair(const ecgvit_gemm_args *g, int split_k, cudaStream_t stream) {
     if (!B_MN) rc = make_tmap(&tb, g->B, g->K, g->N, g->ldb, BK, Cfg::B_HALF);
     else rc = make_tmap(&tb, g->B, g->N, g->K, g->ldb, 64, BK);
     if (rc) return rc;
-    // outputs leave through TMA stores of 32-row x 64-column (128-byte) swizzled tiles; TMA clips at M x N
-    CUtensorMap to, to2;
-    to = ta;
-    to2 = ta;
+    // outputs leave (and the residual / pre-activation operand arrives) through TMA on 32-row x 32-column tiles
+    // with 64-byte swizzle; TMA clips at M x N
+    CUtensorMap to = ta, to2 = ta, tx = ta;
     if (MODE != ECGVIT_EPI_ATOMIC_F32) {
-        if ((rc = make_tmap(&to, g->out, g->N, g->M, g->ldo, 64, 32))) return rc;
-        if (MODE == ECGVIT_EPI_BIAS_GELU && (rc = make_tmap(&to2, g->out2, g->N, g->M, g->ldo, 64, 32))) return rc;
+        if ((rc = make_tmap(&to, g->out, g->N, g->M, g->ldo, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+        if (MODE == ECGVIT_EPI_BIAS_GELU &&
+            (rc = make_tmap(&to2, g->out2, g->N, g->M, g->ldo, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+        if ((MODE == ECGVIT_EPI_BIAS_RES || MODE == ECGVIT_EPI_DGELU) &&
+            (rc = make_tmap(&tx, g->aux, g->N, g->M, g->ldo, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
     }
     auto kern = gemm_tc2_kernel<BN, A_MN, B_MN, MODE>;
     static bool attr_set = false;
@@ -309,7 +311,7 @@ int launch_pair(const ecgvit_gemm_args *g, int split_k, cudaStream_t stream) {
     const int clusters = sm_count() / 2;
     const int grid = 2 * (units < clusters ? units : clusters);
     EpiParams ep{g->out, g->out2, g->aux, g->bias, g->ldo};
-    kern<<<grid, kNumThreads, Cfg::SMEM_BYTES, stream>>>(ta, tb, to, to2, g->M, g->N, g->K, split_k, ep);
+    kern<<<grid, kNumThreads, Cfg::SMEM_BYTES, stream>>>(ta, tb, to, to2, tx, g->M, g->N, g->K, split_k, ep);
     return check_launch("gemm_tc2");
 }
 
@@ -330,6 +332,8 @@ template <int BN> int dispatch_pair(const ecgvit_gemm_args *g, int split_k, cuda
     return fail(-1, "gemm(bf16): unsupported combination a_kmajor=%d b_kmajor=%d epilogue=%d", g->a_kmajor,
                 g->b_kmajor, mode);
 }
+
+inline double b_kmajor_eff(int b_kmajor) { return b_kmajor ? 0.88 : 0.82; }  // MN-major B over-fetches at 192
 
 // ECGVIT_GEMM_CTA_GROUP=1 selects the single-CTA kernel (kept for A/B measurements); default is the CTA pair
 int cta_group_setting() {
@@ -379,13 +383,22 @@ int gemm_bf16_tc(const ecgvit_gemm_args *g, cudaStream_t stream) {
     // shared-memory bandwidth for operand reads alone), so they are only chosen when the wide tile would waste a
     // large part of its last wave.
     if (cta_group_setting() == 2) {
+        // Shared memory moves 128 B/clk per SM and every staged byte is written once (TMA) and read once (MMA), so a
+        // 256 x BN pair tile can sustain at most min(1, 128 / (2 * bytes per k block / MMA clocks per k block)) of the
+        // tensor peak: 1.00 at BN = 256, 0.88 at 192, 0.67 at 128.  Pick the width with the best (tile efficiency x
+        // last-wave occupancy).
         const int clusters = sms / 2;
-        auto waves2 = [&](int bn) {
-            const long units = (long)((g->M + 2 * BM - 1) / (2 * BM)) * ((g->N + bn - 1) / bn) * split_k;
-            return (units + clusters - 1) / clusters;
+        const long tiles_m2 = (g->M + 2 * BM - 1) / (2 * BM);
+        auto score = [&](int bn, double eff) {
+            const long units = tiles_m2 * ((g->N + bn - 1) / bn) * split_k;
+            const long waves = (units + clusters - 1) / clusters;
+            // time ~ waves * bn / eff  (per-tile MMA time is proportional to bn)
+            return (double)waves * bn / eff;
         };
-        const bool use128 = (g->N <= 128) || (waves2(128) * 128 * 1.15 < waves2(256) * 256);
-        return use128 ? dispatch_pair<128>(g, split_k, stream) : dispatch_pair<256>(g, split_k, stream);
+        const double s256 = score(256, 1.0), s192 = score(192, b_kmajor_eff(g->b_kmajor)), s128 = score(128, 0.67);
+        if (g->N <= 128 || (s128 < s256 && s128 < s192)) return dispatch_pair<128>(g, split_k, stream);
+        if (s192 < s256) return dispatch_pair<192>(g, split_k, stream);
+        return dispatch_pair<256>(g, split_k, stream);
     }
     auto waves = [&](int bn) {
         const long units = (long)((g->M + BM - 1) / BM) * ((g->N + bn - 1) / bn) * split_k;

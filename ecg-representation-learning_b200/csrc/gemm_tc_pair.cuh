@@ -14,57 +14,67 @@
 //   tmem_empty[a]  on the LEADER : 8 epilogue warps x 2 CTAs arrive (remote arrive from the peer)
 #pragma once
 
-template <int BN> struct PairCfg {
-    static constexpr int B_HALF = BN / 2;
-    static constexpr int B_STAGE_BYTES = B_HALF * BK * 2;
-    static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;  // per CTA
-    // epilogue staging: every epilogue warp owns two 32-row x 128-byte (64 bf16) swizzled tiles for TMA stores
-    static constexpr int EPI_TILE_BYTES = 32 * 128;
-    static constexpr int EPI_BYTES = kNumEpilogueWarps * 2 * EPI_TILE_BYTES;  // 64 KB
-    static constexpr int PIPE_BUDGET = 232448 - 1024 - 256 - EPI_BYTES;
+template <int BN, bool B_MN> struct PairCfg {
+    static constexpr int B_HALF = BN / 2;                                      // B rows (N values) per CTA
+    // MN-major B is staged in 64-wide chunks; at BN = 192 the second chunk is only half used (over-fetch)
+    static constexpr int B_LOAD_ROWS = B_MN ? ((B_HALF + 63) / 64) * 64 : B_HALF;
+    static constexpr int B_STAGE_BYTES = B_LOAD_ROWS * BK * 2;
+    static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;          // per CTA
+    // epilogue staging: every epilogue warp owns four 32-row x 64-byte (32 bf16, SWIZZLE_64B) tiles
+    static constexpr int EPI_TILE_BYTES = 32 * 64;
+    static constexpr int EPI_TILES_PER_WARP = 4;
+    static constexpr int EPI_BYTES = kNumEpilogueWarps * EPI_TILES_PER_WARP * EPI_TILE_BYTES;  // 64 KB
+    static constexpr int NUM_BARRIERS = 2 * 8 + 4 + kNumEpilogueWarps * EPI_TILES_PER_WARP;
+    static constexpr int PIPE_BUDGET = 232448 - 1024 - 1024 - EPI_BYTES;
     static constexpr int STAGES = (PIPE_BUDGET / STAGE_BYTES) > 8 ? 8 : (PIPE_BUDGET / STAGE_BYTES);
     static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 + 256;
+    static constexpr int UNITS_PER_WARP = B_HALF / 32;                         // 32-column units per epilogue warp
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 + 1024;
+    static_assert(NUM_BARRIERS * 8 + 16 <= 1024, "barrier block");
+    static_assert(B_HALF % 32 == 0 && UNITS_PER_WARP <= EPI_TILES_PER_WARP, "tile width");
 };
 
-// Epilogue math for 64 consecutive accumulator columns of one row (thread = row), written as bf16 into the warp's
-// swizzled staging tile(s); the caller then issues one TMA store per tile (TMA clips rows >= M / cols >= N).
+// byte offset of 16-byte chunk j (0..3) of row `lane` inside a 32 x 64-byte SWIZZLE_64B tile
+__device__ __forceinline__ uint32_t sw64_offset(int lane, int j) {
+    return static_cast<uint32_t>(lane) * 64u + (static_cast<uint32_t>(j ^ ((lane >> 1) & 3)) << 4);
+}
+
+// Epilogue math for 32 consecutive accumulator columns of one row (thread = row).  Results are written as bf16 into
+// the warp's swizzled staging tile(s); for BIAS_RES / DGELU the tile already holds the aux operand (residual /
+// pre-activation), fetched by TMA while the mainloop was still running, and is updated in place.
+// The caller then issues one TMA store per tile (TMA clips rows >= M and columns >= N, so there are no guards here
+// except for the bias vector).
 template <int MODE>
-__device__ __forceinline__ void epilogue_chunk64(const EpiParams &ep, int64_t row, bool row_ok, int col_base, int N,
-                                                 const uint32_t r[64], uint8_t *stage0, uint8_t *stage1, int lane) {
+__device__ __forceinline__ void epilogue_unit32(const EpiParams &ep, int col_base, int N, const uint32_t r[32],
+                                                uint8_t *tile0, uint8_t *tile1, int lane) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < 4; ++j) {
         const int col = col_base + 8 * j;
         float v[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[8 * j + i]);
-        const bool ok = row_ok && col < N;  // N % 8 == 0, so a group of 8 columns is entirely in or out
-        if (MODE != ECGVIT_EPI_DGELU && ep.bias != nullptr && col < N) {
+        if (MODE != ECGVIT_EPI_DGELU && ep.bias != nullptr && col < N) {  // N % 8 == 0
             const float4 b0 = __ldg(reinterpret_cast<const float4 *>(ep.bias + col));
             const float4 b1 = __ldg(reinterpret_cast<const float4 *>(ep.bias + col + 4));
             v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
             v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
         }
-        const uint32_t soff = static_cast<uint32_t>(lane) * 128u + (static_cast<uint32_t>(j ^ (lane & 7)) << 4);
-        if (MODE == ECGVIT_EPI_BIAS_RES) {
-            if (ok) {
-                float a[8];
-                load8(reinterpret_cast<const bf16 *>(ep.aux) + row * ep.ldo + col, a);
+        const uint32_t soff = sw64_offset(lane, j);
+        if (MODE == ECGVIT_EPI_BIAS_RES || MODE == ECGVIT_EPI_DGELU) {
+            const uint4 a4 = *reinterpret_cast<const uint4 *>(tile0 + soff);
+            float a[8];
+            unpack_bf16x2(a4.x, a[0], a[1]); unpack_bf16x2(a4.y, a[2], a[3]);
+            unpack_bf16x2(a4.z, a[4], a[5]); unpack_bf16x2(a4.w, a[6], a[7]);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] += a[i];
-            }
-        } else if (MODE == ECGVIT_EPI_DGELU) {
-            if (ok) {
-                float u[8];
-                load8(reinterpret_cast<const bf16 *>(ep.aux) + row * ep.ldo + col, u);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] *= gelu_grad<false>(u[i]);
+            for (int i = 0; i < 8; ++i) {
+                if (MODE == ECGVIT_EPI_BIAS_RES) v[i] += a[i];
+                else v[i] *= gelu_grad<false>(a[i]);
             }
         }
         uint4 packed;
         packed.x = pack_bf16x2(v[0], v[1]); packed.y = pack_bf16x2(v[2], v[3]);
         packed.z = pack_bf16x2(v[4], v[5]); packed.w = pack_bf16x2(v[6], v[7]);
-        *reinterpret_cast<uint4 *>(stage0 + soff) = packed;
+        *reinterpret_cast<uint4 *>(tile0 + soff) = packed;
         if (MODE == ECGVIT_EPI_BIAS_GELU) {
             // gelu of the ROUNDED pre-activation: that is the value backward differentiates
             float lo, hi, h[8];
@@ -75,7 +85,7 @@ __device__ __forceinline__ void epilogue_chunk64(const EpiParams &ep, int64_t ro
             uint4 ph;
             ph.x = pack_bf16x2(h[0], h[1]); ph.y = pack_bf16x2(h[2], h[3]);
             ph.z = pack_bf16x2(h[4], h[5]); ph.w = pack_bf16x2(h[6], h[7]);
-            *reinterpret_cast<uint4 *>(stage1 + soff) = ph;
+            *reinterpret_cast<uint4 *>(tile1 + soff) = ph;
         }
     }
 }
@@ -83,9 +93,10 @@ __device__ __forceinline__ void epilogue_chunk64(const EpiParams &ep, int64_t ro
 template <int BN, bool A_MN, bool B_MN, int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_out2, int M, int N,
-                int K, int split_k, EpiParams ep) {
-    using Cfg = PairCfg<BN>;
+                const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_out2,
+                const __grid_constant__ CUtensorMap tmap_aux, int M, int N, int K, int split_k, EpiParams ep) {
+    using Cfg = PairCfg<BN, B_MN>;
+    constexpr bool kHasAux = (MODE == ECGVIT_EPI_BIAS_RES || MODE == ECGVIT_EPI_DGELU);
     constexpr int STAGES = Cfg::STAGES;
     constexpr int BM2 = 2 * BM;  // rows of the pair tile
 
@@ -96,7 +107,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     uint64_t *empty_bar = full_bar + STAGES;
     uint64_t *tmem_full_bar = empty_bar + STAGES;
     uint64_t *tmem_empty_bar = tmem_full_bar + 2;
-    uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(tmem_empty_bar + 2);
+    uint64_t *aux_bar = tmem_empty_bar + 2;  // [epilogue warp][unit]
+    uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(aux_bar + kNumEpilogueWarps * Cfg::EPI_TILES_PER_WARP);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -110,6 +122,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         ptx::prefetch_tensormap(&tmap_b);
         if (MODE != ECGVIT_EPI_ATOMIC_F32) ptx::prefetch_tensormap(&tmap_out);
         if (MODE == ECGVIT_EPI_BIAS_GELU) ptx::prefetch_tensormap(&tmap_out2);
+        if (kHasAux) ptx::prefetch_tensormap(&tmap_aux);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -120,6 +133,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             ptx::mbar_init(&tmem_full_bar[a], 1);
             ptx::mbar_init(&tmem_empty_bar[a], 2 * kNumEpilogueWarps);
         }
+        for (int i = 0; i < kNumEpilogueWarps * Cfg::EPI_TILES_PER_WARP; ++i) ptx::mbar_init(&aux_bar[i], 1);
         ptx::fence_mbar_init();
     }
     if (warp == 2) ptx::tmem_alloc_2sm(tmem_ptr_smem, Cfg::TMEM_COLS);
@@ -163,7 +177,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                         ptx::tma_load_2d_2sm(sb, &tmap_b, &full_bar[stage], kb * BK, col0);
                     } else {
 #pragma unroll
-                        for (int j = 0; j < Cfg::B_HALF / 64; ++j)
+                        for (int j = 0; j < Cfg::B_LOAD_ROWS / 64; ++j)
                             ptx::tma_load_2d_2sm(sb + j * 8192, &tmap_b, &full_bar[stage], col0 + j * 64, kb * BK);
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -209,35 +223,53 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         // ================================ epilogue (both CTAs, own 128 rows) ======================
         const int q = warp & 3;
         const int half = (warp - 4) >> 2;
-        constexpr int COLS_PER_WARP = BN / 2;
-        uint8_t *stage0 = epi_smem + (warp - 4) * 2 * Cfg::EPI_TILE_BYTES;
-        uint8_t *stage1 = stage0 + Cfg::EPI_TILE_BYTES;
+        constexpr int UNITS = Cfg::UNITS_PER_WARP;
+        uint8_t *tiles = epi_smem + (warp - 4) * Cfg::EPI_TILES_PER_WARP * Cfg::EPI_TILE_BYTES;
+        uint64_t *my_aux_bar = aux_bar + (warp - 4) * Cfg::EPI_TILES_PER_WARP;
         int it = 0;
-        int buf = 0;
         for (int u = cluster_id; u < num_units; u += num_clusters, ++it) {
             const int tile_n = u % tiles_n;
             const int tile_m = (u / tiles_n) % tiles_m;
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
+            const int row_base = tile_m * BM2 + rank * BM + q * 32;
+            const int col_warp = tile_n * BN + half * Cfg::B_HALF;  // first column of this warp's units
+            if (MODE != ECGVIT_EPI_ATOMIC_F32) {
+                // staging tiles are reused every tile: the previous tile's TMA stores must have read them
+                if (lane == 0) {
+                    ptx::tma_store_wait_read<0>();
+                    if (kHasAux) {
+                        // fetch the residual / pre-activation tiles now, while the mainloop of this tile is running
+#pragma unroll
+                        for (int i = 0; i < UNITS; ++i) {
+                            if (col_warp + 32 * i < N) {
+                                ptx::mbar_arrive_expect_tx(&my_aux_bar[i], Cfg::EPI_TILE_BYTES);
+                                ptx::tma_load_2d(tiles + i * Cfg::EPI_TILE_BYTES, &tmap_aux, &my_aux_bar[i],
+                                                 col_warp + 32 * i, row_base);
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+            }
             ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
             ptx::tcgen05_fence_after();
-            const int row_base = tile_m * BM2 + rank * BM + q * 32;
-            const int64_t row = static_cast<int64_t>(row_base) + lane;
+            const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + half * Cfg::B_HALF;
             if (MODE == ECGVIT_EPI_ATOMIC_F32) {
+                const int64_t row = static_cast<int64_t>(row_base) + lane;
 #pragma unroll 1
-                for (int c = 0; c < COLS_PER_WARP / 32; ++c) {
-                    const int col0 = half * COLS_PER_WARP + c * 32;
+                for (int i = 0; i < UNITS; ++i) {
                     uint32_t r[32];
-                    ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + col0, r);
+                    ptx::tmem_ld_32x32(taddr0 + 32 * i, r);
                     ptx::tmem_ld_wait();
                     if (row < M) {
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            const int col = tile_n * BN + col0 + j * 8;
+                            const int col = col_warp + 32 * i + j * 8;
                             if (col < N) {
                                 float v[8];
 #pragma unroll
-                                for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[j * 8 + i]);
+                                for (int k = 0; k < 8; ++k) v[k] = __uint_as_float(r[j * 8 + k]);
                                 epilogue_store<MODE, bf16, 8, false>(ep, row, col, v);
                             }
                         }
@@ -245,31 +277,31 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                 }
             } else {
 #pragma unroll 1
-                for (int c = 0; c < COLS_PER_WARP / 64; ++c) {
-                    const int col0 = half * COLS_PER_WARP + c * 64;
-                    const int col_base = tile_n * BN + col0;
-                    if (col_base >= N) break;  // warp-uniform: the whole 64-column chunk is outside the matrix
-                    uint32_t r[64];
-                    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + col0;
-                    ptx::tmem_ld_32x32(taddr, r);
-                    ptx::tmem_ld_32x32(taddr + 32, r + 32);
-                    ptx::tmem_ld_wait();
-                    uint8_t *s0, *s1;
+                for (int i = 0; i < UNITS; ++i) {
+                    const int col_base = col_warp + 32 * i;
+                    if (col_base >= N) break;  // warp-uniform: the whole unit is outside the matrix
+                    uint32_t r[32];
+                    ptx::tmem_ld_32x32(taddr0 + 32 * i, r);
+                    uint8_t *t0, *t1 = nullptr;
                     if (MODE == ECGVIT_EPI_BIAS_GELU) {
-                        s0 = stage0; s1 = stage1;
-                        if (lane == 0) ptx::tma_store_wait_read<0>();  // previous chunk's two stores have read smem
+                        // two (u, h) tile pairs, alternating: the pair used two units ago must have been read
+                        t0 = tiles + (i & 1) * 2 * Cfg::EPI_TILE_BYTES;
+                        t1 = t0 + Cfg::EPI_TILE_BYTES;
+                        if (i >= 2) {
+                            if (lane == 0) ptx::tma_store_wait_read<1>();
+                            __syncwarp();
+                        }
                     } else {
-                        s0 = buf ? stage1 : stage0; s1 = nullptr;
-                        if (lane == 0) ptx::tma_store_wait_read<1>();  // the store that used this buffer two chunks ago
-                        buf ^= 1;
+                        t0 = tiles + i * Cfg::EPI_TILE_BYTES;
+                        if (kHasAux) ptx::mbar_wait(&my_aux_bar[i], it & 1);
                     }
-                    __syncwarp();
-                    epilogue_chunk64<MODE>(ep, row, row < M, col_base, N, r, s0, s1, lane);
+                    ptx::tmem_ld_wait();
+                    epilogue_unit32<MODE>(ep, col_base, N, r, t0, t1, lane);
                     ptx::fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
                     __syncwarp();
                     if (lane == 0) {
-                        ptx::tma_store_2d(&tmap_out, s0, col_base, row_base);
-                        if (MODE == ECGVIT_EPI_BIAS_GELU) ptx::tma_store_2d(&tmap_out2, s1, col_base, row_base);
+                        ptx::tma_store_2d(&tmap_out, t0, col_base, row_base);
+                        if (MODE == ECGVIT_EPI_BIAS_GELU) ptx::tma_store_2d(&tmap_out2, t1, col_base, row_base);
                         ptx::tma_store_commit();
                     }
                 }
