@@ -58,15 +58,30 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)"""
+    """SM clock / power / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe): NVML from a
+    background thread every 20 ms (nvidia-smi -lms as a fallback)."""
     FIELDS = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
               'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
               'clocks_event_reasons.sw_power_cap')
 
     def __init__(self, index):
         self.index, self.proc, self.lines = index, None, []
+        self.samples, self.stop_flag, self.thread, self.nvml = [], False, None, None
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')  # CUDA ordinal -> NVML index
+            idx = int(vis.split(',')[self.index]) if vis and all(t.strip().isdigit() for t in vis.split(',')) else self.index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.FIELDS}', '--format=csv,noheader,nounits',
                                           '-lms', '100', '-i', str(self.index)], stdout=subprocess.PIPE,
@@ -76,11 +91,39 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        bits = {'hw_slowdown': n.nvmlClocksEventReasonHwSlowdown if hasattr(n, 'nvmlClocksEventReasonHwSlowdown') else 0x8,
+                'hw_thermal_slowdown': 0x40, 'sw_thermal_slowdown': 0x20, 'sw_power_cap': 0x4}
+        while not self.stop_flag:
+            try:
+                sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                pw = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+                try:
+                    rs = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                except Exception:
+                    rs = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.samples.append((sm, pw, [k for k, b in bits.items() if rs & b]))
+            except Exception:
+                pass
+            time.sleep(0.02)
+
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            if not self.samples:
+                return {'sm_mhz': None, 'sm_max_mhz': self.max_sm, 'reasons': ['no samples'], 'samples': 0}
+            power = [p for _, p, _ in self.samples]
+            thr = statistics.median(power)
+            loaded = [s for s, p, _ in self.samples if p >= thr]
+            reasons = sorted({r for _, _, rs in self.samples for r in rs})
+            return {'sm_mhz': statistics.median(loaded), 'sm_max_mhz': self.max_sm, 'reasons': reasons,
+                    'samples': len(self.samples), 'power_w_max': max(power), 'source': 'nvml, 20 ms period'}
         if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
         self.proc.terminate()
@@ -101,12 +144,11 @@ class ClockSampler:
             for name, val in zip(names, f[3:7]):
                 if val.lower().startswith('active'):
                     reasons.add(name)
-        # "under load" = samples at or above the median power draw
         if sm:
             thr = statistics.median(power)
             loaded = [s for s, p in zip(sm, power) if p >= thr] or sm
             return {'sm_mhz': statistics.median(loaded), 'sm_max_mhz': max(mx), 'reasons': sorted(reasons),
-                    'samples': len(sm), 'power_w_max': max(power)}
+                    'samples': len(sm), 'power_w_max': max(power), 'source': 'nvidia-smi -lms 100'}
         return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['no samples'], 'samples': 0}
 
 
@@ -156,7 +198,7 @@ def run_reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=256, help='per-GPU batch')

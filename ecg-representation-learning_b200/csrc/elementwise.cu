@@ -126,50 +126,81 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const T *__restrict_
     }
 }
 
-// LayerNorm backward (+ residual-gradient add, + column sums of the result for the bias gradient upstream)
-template <typename T>
-__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const T *__restrict__ dy, const T *__restrict__ x,
-                                                             const float *__restrict__ gamma,
-                                                             const float *__restrict__ mean_in,
-                                                             const float *__restrict__ rstd_in, const T *dres, T *dx,
-                                                             float *__restrict__ dgamma, float *__restrict__ dbeta,
-                                                             float *__restrict__ dcolsum, int M, int d) {
-    extern __shared__ float red[];  // [3][d]
+// LayerNorm backward (+ residual-gradient add, + column sums of the result for the bias gradient upstream).
+// One warp per row, NV 8-element vectors per lane (d <= 256 * NV).  The three inputs of a row (dy, x, dres) are fetched
+// together and kept PACKED in registers (their fp32 expansions are recomputed in the second pass), gamma is read from
+// shared memory, so that with the 3 x 8 x NV per-lane column accumulators the kernel still fits 2 CTAs (16 warps) per
+// SM: this kernel lives on memory-level parallelism.
+template <typename T> struct Packed8;
+template <> struct Packed8<bf16> { uint4 v; };
+template <> struct Packed8<float> { float4 a, b; };
+__device__ __forceinline__ void ld_packed(Packed8<bf16> &p, const bf16 *src) { p.v = *reinterpret_cast<const uint4 *>(src); }
+__device__ __forceinline__ void ld_packed(Packed8<float> &p, const float *src) {
+    p.a = *reinterpret_cast<const float4 *>(src);
+    p.b = *reinterpret_cast<const float4 *>(src + 4);
+}
+__device__ __forceinline__ void unpack(const Packed8<bf16> &p, float v[8]) {
+    unpack_bf16x2(p.v.x, v[0], v[1]); unpack_bf16x2(p.v.y, v[2], v[3]);
+    unpack_bf16x2(p.v.z, v[4], v[5]); unpack_bf16x2(p.v.w, v[6], v[7]);
+}
+__device__ __forceinline__ void unpack(const Packed8<float> &p, float v[8]) {
+    v[0] = p.a.x; v[1] = p.a.y; v[2] = p.a.z; v[3] = p.a.w; v[4] = p.b.x; v[5] = p.b.y; v[6] = p.b.z; v[7] = p.b.w;
+}
+
+template <typename T, int NV>
+__global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const T *__restrict__ dy, const T *__restrict__ x,
+                                                                const float *__restrict__ gamma,
+                                                                const float *__restrict__ mean_in,
+                                                                const float *__restrict__ rstd_in, const T *dres, T *dx,
+                                                                float *__restrict__ dgamma, float *__restrict__ dbeta,
+                                                                float *__restrict__ dcolsum, int M, int d) {
+    extern __shared__ float red[];  // [3][d] column partials, then [d] gamma
+    float *sgamma = red + 3 * d;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int warps_per_block = blockDim.x >> 5;
     const float inv_d = 1.0f / (float)d;
 
-    float acc_g[LN_MAXV][8], acc_b[LN_MAXV][8], acc_c[LN_MAXV][8], gam[LN_MAXV][8];
+    float acc_g[NV][8], acc_b[NV][8], acc_c[NV][8];
 #pragma unroll
-    for (int i = 0; i < LN_MAXV; ++i) {
-        const int c = (i * 32 + lane) * 8;
+    for (int i = 0; i < NV; ++i)
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { acc_g[i][k] = 0.f; acc_b[i][k] = 0.f; acc_c[i][k] = 0.f; gam[i][k] = 0.f; }
-        if (c < d) load8(gamma + c, gam[i]);
-    }
+        for (int k = 0; k < 8; ++k) { acc_g[i][k] = 0.f; acc_b[i][k] = 0.f; acc_c[i][k] = 0.f; }
     for (int i = threadIdx.x; i < 3 * d; i += blockDim.x) red[i] = 0.f;
+    for (int i = threadIdx.x; i < d; i += blockDim.x) sgamma[i] = gamma[i];
     __syncthreads();
 
     for (int64_t row = (int64_t)blockIdx.x * warps_per_block + warp; row < M;
          row += (int64_t)gridDim.x * warps_per_block) {
+        Packed8<T> pdy[NV], px[NV], pres[NV];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = (i * 32 + lane) * 8;
+            if (c < d) {
+                ld_packed(pdy[i], dy + row * d + c);
+                ld_packed(px[i], x + row * d + c);
+                if (dres != nullptr) ld_packed(pres[i], dres + row * d + c);
+            }
+        }
         const float mean = mean_in[row], rstd = rstd_in[row];
-        float g[LN_MAXV][8], xh[LN_MAXV][8];
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-        for (int i = 0; i < LN_MAXV; ++i) {
+        for (int i = 0; i < NV; ++i) {
             const int c = (i * 32 + lane) * 8;
             if (c < d) {
                 float dyv[8], xv[8];
-                load8(dy + row * d + c, dyv);
-                load8(x + row * d + c, xv);
+                unpack(pdy[i], dyv);
+                unpack(px[i], xv);
+                const float4 g0 = *reinterpret_cast<const float4 *>(sgamma + c);
+                const float4 g1 = *reinterpret_cast<const float4 *>(sgamma + c + 4);
+                const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
-                    xh[i][k] = (xv[k] - mean) * rstd;
-                    g[i][k] = dyv[k] * gam[i][k];
-                    s1 += g[i][k];
-                    s2 = fmaf(g[i][k], xh[i][k], s2);
-                    acc_g[i][k] = fmaf(dyv[k], xh[i][k], acc_g[i][k]);
+                    const float xh = (xv[k] - mean) * rstd;
+                    const float g = dyv[k] * gm[k];
+                    s1 += g;
+                    s2 = fmaf(g, xh, s2);
+                    acc_g[i][k] = fmaf(dyv[k], xh, acc_g[i][k]);
                     acc_b[i][k] += dyv[k];
                 }
             }
@@ -177,15 +208,23 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const T *__restrict_
         s1 = warp_sum(s1) * inv_d;
         s2 = warp_sum(s2) * inv_d;
 #pragma unroll
-        for (int i = 0; i < LN_MAXV; ++i) {
+        for (int i = 0; i < NV; ++i) {
             const int c = (i * 32 + lane) * 8;
             if (c < d) {
-                float o[8];
+                float dyv[8], xv[8], o[8];
+                unpack(pdy[i], dyv);
+                unpack(px[i], xv);
+                const float4 g0 = *reinterpret_cast<const float4 *>(sgamma + c);
+                const float4 g1 = *reinterpret_cast<const float4 *>(sgamma + c + 4);
+                const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
-                for (int k = 0; k < 8; ++k) o[k] = rstd * (g[i][k] - s1 - xh[i][k] * s2);
+                for (int k = 0; k < 8; ++k) {
+                    const float xh = (xv[k] - mean) * rstd;
+                    o[k] = rstd * (dyv[k] * gm[k] - s1 - xh * s2);
+                }
                 if (dres != nullptr) {
                     float r[8];
-                    load8(dres + row * d + c, r);
+                    unpack(pres[i], r);
 #pragma unroll
                     for (int k = 0; k < 8; ++k) o[k] += r[k];
                 }
@@ -200,7 +239,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const T *__restrict_
     }
     // block reduce through shared memory, then one atomic per column per CTA
 #pragma unroll
-    for (int i = 0; i < LN_MAXV; ++i) {
+    for (int i = 0; i < NV; ++i) {
         const int c = (i * 32 + lane) * 8;
         if (c < d) {
 #pragma unroll
@@ -340,12 +379,28 @@ int ecgvit_layernorm_bwd(const void *dy, const void *x, const float *gamma, cons
     ECGVIT_REQUIRE(d % 8 == 0 && d <= 8 * 32 * LN_MAXV, "layernorm_bwd: d=%d must be a multiple of 8 and <= %d", d,
                    8 * 32 * LN_MAXV);
     const int grid = grid_for((int64_t)M * 32, 256, 2);
-    const size_t smem = 3 * (size_t)d * sizeof(float);
-    if (dtype == ECGVIT_BF16)
-        layernorm_bwd_kernel<bf16><<<grid, 256, smem, as_stream(stream)>>>((const bf16 *)dy, (const bf16 *)x, gamma, mean, rstd, (const bf16 *)dres, (bf16 *)dx, dgamma, dbeta, dcolsum, M, d);
-    else if (dtype == ECGVIT_F32)
-        layernorm_bwd_kernel<float><<<grid, 256, smem, as_stream(stream)>>>((const float *)dy, (const float *)x, gamma, mean, rstd, (const float *)dres, (float *)dx, dgamma, dbeta, dcolsum, M, d);
-    else return fail(-1, "layernorm_bwd: unknown dtype %d", dtype);
+    const size_t smem = 4 * (size_t)d * sizeof(float);
+    const int nv = (d + 255) / 256;
+    cudaStream_t st = as_stream(stream);
+#define ECGVIT_LN_BWD(TT, NVV)                                                                                         \
+    layernorm_bwd_kernel<TT, NVV><<<grid, 256, smem, st>>>((const TT *)dy, (const TT *)x, gamma, mean, rstd,          \
+                                                           (const TT *)dres, (TT *)dx, dgamma, dbeta, dcolsum, M, d)
+    if (dtype == ECGVIT_BF16) {
+        switch (nv) {
+            case 1: ECGVIT_LN_BWD(bf16, 1); break;
+            case 2: ECGVIT_LN_BWD(bf16, 2); break;
+            case 3: ECGVIT_LN_BWD(bf16, 3); break;
+            default: ECGVIT_LN_BWD(bf16, 4); break;
+        }
+    } else if (dtype == ECGVIT_F32) {
+        switch (nv) {
+            case 1: ECGVIT_LN_BWD(float, 1); break;
+            case 2: ECGVIT_LN_BWD(float, 2); break;
+            case 3: ECGVIT_LN_BWD(float, 3); break;
+            default: ECGVIT_LN_BWD(float, 4); break;
+        }
+    } else return fail(-1, "layernorm_bwd: unknown dtype %d", dtype);
+#undef ECGVIT_LN_BWD
     return check_launch("layernorm_bwd");
 }
 
