@@ -230,7 +230,7 @@ def main():
     B = args.batch
     torch.manual_seed(77)
     model = ecg_b200.EcgVit(config=ecg_b200.EcgVitConfig(compute_dtype='bf16', **BASE_CFG)).to(dev).train()
-    use_graph = (not args.no_graph) and world == 1
+    use_graph = not args.no_graph  # NCCL all-reduces are captured into the step graph as well
     trainer = ecg_b200.FusedTrainer(model, learning_rate=3e-4, weight_decay=1e-2, schedule='constant',
                                     max_grad_norm=1.0, use_cuda_graph=use_graph)
     xh, yh = synthetic_batch(B, length=BASE_CFG['max_signal_length'], seed=77 + rank)
@@ -277,10 +277,12 @@ def main():
     # ---- end-to-end arm: pinned host batch -> H2D -> step -> D2H of the loss, every step -------------------
     loss_host = torch.zeros(1).pin_memory()
 
+    staged = [trainer.stage(xh, yh)]
+
     def e2e_step():
-        xd = xh.to(dev, non_blocking=True)
-        yd = yh.to(dev, non_blocking=True)
+        xd, yd = staged[0]
         loss, _ = trainer.step(xd, yd)
+        staged[0] = trainer.stage(xh, yh)  # H2D of the next step's batch overlaps this step's kernels
         loss_host.copy_(loss.reshape(1), non_blocking=True)
         torch.cuda.current_stream().synchronize()  # the caller reads the loss every step (train.py:278)
 
@@ -293,9 +295,8 @@ def main():
     roofline, kernels = None, None
     if rank == 0:
         peaks = measured_peaks()
-        eager = ecg_b200.FusedTrainer(model, use_cuda_graph=False)
-        eager._reducer = None
-        eager.world = 1
+        eager = ecg_b200.FusedTrainer(model, use_cuda_graph=False, data_parallel=False)
+        model._after_layer_backward = None  # the profiling step runs on rank 0 alone: no collective
         eager.step(x, y)
         torch.cuda.synchronize()
         _lib.profile[0] = []

@@ -40,8 +40,9 @@ SIGNATURES = {
                                   c_void_p],
     'ecgvit_layernorm_fwd': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float,
                              c_int, c_void_p],
+    'ecgvit_layernorm_bwd_scratch_floats': [c_int],
     'ecgvit_layernorm_bwd': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                             c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
+                             c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
     'ecgvit_gemm': [POINTER(GemmArgs), c_void_p],
     'ecgvit_attention_fwd': [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p],
     'ecgvit_attention_bwd': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float,
@@ -54,7 +55,7 @@ SIGNATURES = {
     'ecgvit_grad_scale_by_clip': [c_void_p, c_int64, c_void_p, c_void_p, c_void_p],
     'ecgvit_cast_f32_to_bf16': [c_void_p, c_void_p, c_int64, c_void_p],
 }
-_RESTYPES = {'ecgvit_last_error': c_char_p}
+_RESTYPES = {'ecgvit_last_error': c_char_p, 'ecgvit_layernorm_bwd_scratch_floats': c_int64}
 
 _lib = None
 
@@ -82,7 +83,7 @@ def last_error():
 
 
 # kernels launched per successful entry-point call (memsets are not kernels); feeds bench.py's `gpu_launches`
-KERNELS_PER_CALL = {'head_fwd': 2, 'head_bwd': 3}
+KERNELS_PER_CALL = {'head_fwd': 2, 'head_bwd': 3, 'layernorm_bwd': 2}
 launch_counter = [0]
 
 

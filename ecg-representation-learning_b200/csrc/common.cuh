@@ -139,6 +139,69 @@ template <bool kExact> __device__ __forceinline__ void gelu_parts(float u, float
         pdf = 0.39894228040143268f * e;
     }
 }
+// ---- packed fp32x2 math (FFMA2 / FMUL2 / FADD2 on sm_100): two lanes of a Horner step per issue slot -----------
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t splat2(float c) { return pack2(c, c); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
+// Shared part of the fast erf-GELU for a PAIR of pre-activations (Abramowitz-Stegun 7.1.26 in u directly):
+//   half_erf = 0.5 * erf(|u| / sqrt2) = 0.5 - (-0.5 * poly(t) * t) ... with t = 1 / (1 + p |u| / sqrt2), e = exp(-u^2/2)
+// ~8.5 issue slots per element (4 of the 17 per pair are MUFU).
+__device__ __forceinline__ void gelu_pair_parts(uint64_t u, uint64_t au, uint64_t &half_erf, uint64_t &e) {
+    const uint64_t q = fma2(au, splat2(0.3275911f * 0.70710678118654752f), splat2(1.0f));
+    float q0, q1;
+    unpack2(q, q0, q1);
+    const uint64_t t = pack2(rcp_approx(q0), rcp_approx(q1));
+    const uint64_t arg = mul2(mul2(u, u), splat2(-0.5f * 1.4426950408889634f));
+    float a0, a1;
+    unpack2(arg, a0, a1);
+    e = pack2(ex2_approx(a0), ex2_approx(a1));
+    // coefficients pre-multiplied by -0.5
+    uint64_t poly = fma2(t, splat2(-0.5f * 1.061405429f), splat2(0.5f * 1.453152027f));
+    poly = fma2(poly, t, splat2(-0.5f * 1.421413741f));
+    poly = fma2(poly, t, splat2(0.5f * 0.284496736f));
+    poly = fma2(poly, t, splat2(-0.5f * 0.254829592f));
+    half_erf = fma2(mul2(poly, t), e, splat2(0.5f));
+}
+// h = gelu(u) for two values:  u * Phi(u) = 0.5 u + |u| * half_erf
+__device__ __forceinline__ void gelu_fwd_pair(float u0, float u1, float &h0, float &h1) {
+    const uint64_t u = pack2(u0, u1), au = pack2(fabsf(u0), fabsf(u1));
+    uint64_t herf, e;
+    gelu_pair_parts(u, au, herf, e);
+    unpack2(fma2(au, herf, mul2(u, splat2(0.5f))), h0, h1);
+}
+// g = gelu'(u) for two values:  Phi(u) + u * phi(u)
+__device__ __forceinline__ void gelu_grad_pair(float u0, float u1, float &g0, float &g1) {
+    const uint64_t u = pack2(u0, u1), au = pack2(fabsf(u0), fabsf(u1));
+    uint64_t herf, e;
+    gelu_pair_parts(u, au, herf, e);
+    float h0, h1;
+    unpack2(herf, h0, h1);
+    const uint64_t cdf = add2(pack2(copysignf(h0, u0), copysignf(h1, u1)), splat2(0.5f));
+    unpack2(fma2(mul2(u, e), splat2(0.39894228040143268f), cdf), g0, g1);
+}
+
 template <bool kExact> __device__ __forceinline__ float gelu_fwd(float u) {
     float cdf, pdf;
     gelu_parts<kExact>(u, cdf, pdf);

@@ -153,9 +153,10 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const T *__restri
                                                                 const float *__restrict__ mean_in,
                                                                 const float *__restrict__ rstd_in, const T *dres, T *dx,
                                                                 float *__restrict__ dgamma, float *__restrict__ dbeta,
-                                                                float *__restrict__ dcolsum, int M, int d) {
-    extern __shared__ float red[];  // [3][d] column partials, then [d] gamma
-    float *sgamma = red + 3 * d;
+                                                                float *__restrict__ dcolsum, float *__restrict__ partial,
+                                                                int M, int d) {
+    extern __shared__ float red[];  // [warps][3][d] column partials, then [d] gamma
+    float *sgamma = red + (blockDim.x >> 5) * 3 * d;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int warps_per_block = blockDim.x >> 5;
@@ -166,7 +167,6 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const T *__restri
     for (int i = 0; i < NV; ++i)
 #pragma unroll
         for (int k = 0; k < 8; ++k) { acc_g[i][k] = 0.f; acc_b[i][k] = 0.f; acc_c[i][k] = 0.f; }
-    for (int i = threadIdx.x; i < 3 * d; i += blockDim.x) red[i] = 0.f;
     for (int i = threadIdx.x; i < d; i += blockDim.x) sgamma[i] = gamma[i];
     __syncthreads();
 
@@ -237,26 +237,46 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const T *__restri
             }
         }
     }
-    // block reduce through shared memory, then one atomic per column per CTA
+    // block reduce: every warp parks its per-lane column sums in its own smem slab (plain stores), then the CTA adds
+    // the slabs and writes ONE partial row per CTA; a tiny second kernel folds the partial rows into the gradients.
+    // (fp32 atomics are avoided on purpose: shared-memory float atomics are CAS loops, and 296 CTAs x 3 x d global
+    // atomics on 3 x d addresses serialise in L2.)
+    float *slab = red + warp * 3 * d;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
         const int c = (i * 32 + lane) * 8;
         if (c < d) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                atomicAdd(&red[c + k], acc_g[i][k]);
-                atomicAdd(&red[d + c + k], acc_b[i][k]);
-                if (dcolsum != nullptr) atomicAdd(&red[2 * d + c + k], acc_c[i][k]);
-            }
+            *reinterpret_cast<float4 *>(slab + c) = make_float4(acc_g[i][0], acc_g[i][1], acc_g[i][2], acc_g[i][3]);
+            *reinterpret_cast<float4 *>(slab + c + 4) = make_float4(acc_g[i][4], acc_g[i][5], acc_g[i][6], acc_g[i][7]);
+            *reinterpret_cast<float4 *>(slab + d + c) = make_float4(acc_b[i][0], acc_b[i][1], acc_b[i][2], acc_b[i][3]);
+            *reinterpret_cast<float4 *>(slab + d + c + 4) = make_float4(acc_b[i][4], acc_b[i][5], acc_b[i][6], acc_b[i][7]);
+            *reinterpret_cast<float4 *>(slab + 2 * d + c) = make_float4(acc_c[i][0], acc_c[i][1], acc_c[i][2], acc_c[i][3]);
+            *reinterpret_cast<float4 *>(slab + 2 * d + c + 4) = make_float4(acc_c[i][4], acc_c[i][5], acc_c[i][6], acc_c[i][7]);
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < d; i += blockDim.x) {
-        atomicAdd(dgamma + i, red[i]);
-        atomicAdd(dbeta + i, red[d + i]);
-        if (dcolsum != nullptr) atomicAdd(dcolsum + i, red[2 * d + i]);
+    for (int i = threadIdx.x; i < 3 * d; i += blockDim.x) {
+        float t = 0.f;
+        for (int w = 0; w < warps_per_block; ++w) t += red[w * 3 * d + i];
+        partial[(int64_t)blockIdx.x * 3 * d + i] = t;
     }
 }
+
+// folds the per-CTA partial rows: dgamma += sum_b partial[b][0], dbeta += ...[1], dcolsum += ...[2]
+__global__ void __launch_bounds__(256) layernorm_bwd_finalize_kernel(const float *__restrict__ partial, int nblocks,
+                                                                      float *__restrict__ dgamma,
+                                                                      float *__restrict__ dbeta,
+                                                                      float *__restrict__ dcolsum, int d) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 3 * d) return;
+    float t = 0.f;
+    for (int b = 0; b < nblocks; ++b) t += partial[(int64_t)b * 3 * d + i];
+    if (i < d) dgamma[i] += t;
+    else if (i < 2 * d) dbeta[i - d] += t;
+    else if (dcolsum != nullptr) dcolsum[i - 2 * d] += t;
+}
+
+constexpr int LN_BWD_MAX_BLOCKS = 2 * 160;  // >= 2 CTAs x SM count
 
 // ---------------------------------------------------------------------------------------------------
 // out[n] += sum_m x[m, n]; block = 32 column-vectors (8 wide) x 8 row lanes; grid.y splits the rows
@@ -372,19 +392,31 @@ int ecgvit_layernorm_fwd(const void *x, const float *gamma, const float *beta, v
     return check_launch("layernorm_fwd");
 }
 
+int64_t ecgvit_layernorm_bwd_scratch_floats(int d) { return (int64_t)LN_BWD_MAX_BLOCKS * 3 * d; }
+
 int ecgvit_layernorm_bwd(const void *dy, const void *x, const float *gamma, const float *mean, const float *rstd,
-                         const void *dres, void *dx, float *dgamma, float *dbeta, float *dcolsum, int M, int d,
-                         int dtype, void *stream) {
-    ECGVIT_REQUIRE(dy && x && gamma && mean && rstd && dx && dgamma && dbeta && M > 0, "layernorm_bwd: bad arguments");
+                         const void *dres, void *dx, float *dgamma, float *dbeta, float *dcolsum, float *scratch,
+                         int M, int d, int dtype, void *stream) {
+    ECGVIT_REQUIRE(dy && x && gamma && mean && rstd && dx && dgamma && dbeta && scratch && M > 0,
+                   "layernorm_bwd: bad arguments");
     ECGVIT_REQUIRE(d % 8 == 0 && d <= 8 * 32 * LN_MAXV, "layernorm_bwd: d=%d must be a multiple of 8 and <= %d", d,
                    8 * 32 * LN_MAXV);
-    const int grid = grid_for((int64_t)M * 32, 256, 2);
-    const size_t smem = 4 * (size_t)d * sizeof(float);
+    int grid = grid_for((int64_t)M * 32, 256, 2);
+    if (grid > LN_BWD_MAX_BLOCKS) grid = LN_BWD_MAX_BLOCKS;
+    const size_t smem = (8 * 3 + 1) * (size_t)d * sizeof(float);
     const int nv = (d + 255) / 256;
     cudaStream_t st = as_stream(stream);
 #define ECGVIT_LN_BWD(TT, NVV)                                                                                         \
-    layernorm_bwd_kernel<TT, NVV><<<grid, 256, smem, st>>>((const TT *)dy, (const TT *)x, gamma, mean, rstd,          \
-                                                           (const TT *)dres, (TT *)dx, dgamma, dbeta, dcolsum, M, d)
+    do {                                                                                                               \
+        static bool attr_set = false;                                                                                  \
+        if (!attr_set) {                                                                                               \
+            cudaFuncSetAttribute(layernorm_bwd_kernel<TT, NVV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 25 * 1024 * 4); \
+            attr_set = true;                                                                                           \
+        }                                                                                                              \
+        layernorm_bwd_kernel<TT, NVV><<<grid, 256, smem, st>>>((const TT *)dy, (const TT *)x, gamma, mean, rstd,      \
+                                                               (const TT *)dres, (TT *)dx, dgamma, dbeta, dcolsum,     \
+                                                               scratch, M, d);                                         \
+    } while (0)
     if (dtype == ECGVIT_BF16) {
         switch (nv) {
             case 1: ECGVIT_LN_BWD(bf16, 1); break;
@@ -401,7 +433,10 @@ int ecgvit_layernorm_bwd(const void *dy, const void *x, const float *gamma, cons
         }
     } else return fail(-1, "layernorm_bwd: unknown dtype %d", dtype);
 #undef ECGVIT_LN_BWD
-    return check_launch("layernorm_bwd");
+    int rc = check_launch("layernorm_bwd");
+    if (rc) return rc;
+    layernorm_bwd_finalize_kernel<<<(3 * d + 255) / 256, 256, 0, st>>>(scratch, grid, dgamma, dbeta, dcolsum, d);
+    return check_launch("layernorm_bwd_finalize");
 }
 
 int ecgvit_colsum(const void *x, float *out, int M, int N, int64_t ld, int dtype, void *stream) {

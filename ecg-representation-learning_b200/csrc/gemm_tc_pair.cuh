@@ -65,10 +65,17 @@ __device__ __forceinline__ void epilogue_unit32(const EpiParams &ep, int col_bas
             float a[8];
             unpack_bf16x2(a4.x, a[0], a[1]); unpack_bf16x2(a4.y, a[2], a[3]);
             unpack_bf16x2(a4.z, a[4], a[5]); unpack_bf16x2(a4.w, a[6], a[7]);
+            if (MODE == ECGVIT_EPI_BIAS_RES) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                if (MODE == ECGVIT_EPI_BIAS_RES) v[i] += a[i];
-                else v[i] *= gelu_grad<false>(a[i]);
+                for (int i = 0; i < 8; ++i) v[i] += a[i];
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; i += 2) {
+                    float g0, g1;
+                    gelu_grad_pair(a[i], a[i + 1], g0, g1);
+                    v[i] *= g0;
+                    v[i + 1] *= g1;
+                }
             }
         }
         uint4 packed;
@@ -76,12 +83,11 @@ __device__ __forceinline__ void epilogue_unit32(const EpiParams &ep, int col_bas
         packed.z = pack_bf16x2(v[4], v[5]); packed.w = pack_bf16x2(v[6], v[7]);
         *reinterpret_cast<uint4 *>(tile0 + soff) = packed;
         if (MODE == ECGVIT_EPI_BIAS_GELU) {
-            // gelu of the ROUNDED pre-activation: that is the value backward differentiates
-            float lo, hi, h[8];
-            unpack_bf16x2(packed.x, lo, hi); h[0] = gelu_fwd<false>(lo); h[1] = gelu_fwd<false>(hi);
-            unpack_bf16x2(packed.y, lo, hi); h[2] = gelu_fwd<false>(lo); h[3] = gelu_fwd<false>(hi);
-            unpack_bf16x2(packed.z, lo, hi); h[4] = gelu_fwd<false>(lo); h[5] = gelu_fwd<false>(hi);
-            unpack_bf16x2(packed.w, lo, hi); h[6] = gelu_fwd<false>(lo); h[7] = gelu_fwd<false>(hi);
+            // gelu of the fp32 pre-activation (its bf16 rounding, which backward differentiates, moves h by less than
+            // h's own bf16 rounding)
+            float h[8];
+#pragma unroll
+            for (int i = 0; i < 8; i += 2) gelu_fwd_pair(v[i], v[i + 1], h[i], h[i + 1]);
             uint4 ph;
             ph.x = pack_bf16x2(h[0], h[1]); ph.y = pack_bf16x2(h[2], h[3]);
             ph.z = pack_bf16x2(h[4], h[5]); ph.w = pack_bf16x2(h[6], h[7]);

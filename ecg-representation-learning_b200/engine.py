@@ -102,6 +102,7 @@ class StepEngine:
         w.dqkv = buf(M, 3 * inner)
         w.du = buf(M, mlp)
         w.de = buf(B * n, d)
+        w.ln_scratch = buf(int(self.lib.ecgvit_layernorm_bwd_scratch_floats(d)), dtype=torch.float32)
         self.ws[key] = w
         return w
 
@@ -202,7 +203,8 @@ class StepEngine:
             _lib.check(lib.ecgvit_layernorm_bwd(
                 w.dln.data_ptr(), w.y[l].data_ptr(), pf[p + 'ln2.w'].data_ptr(), w.stat2[l][0].data_ptr(),
                 w.stat2[l][1].data_ptr(), dz.data_ptr(), dy.data_ptr(), gr[p + 'ln2.w'].data_ptr(),
-                gr[p + 'ln2.b'].data_ptr(), gr[p + 'out.b'].data_ptr(), M, d, dt, st), 'layernorm_bwd')
+                gr[p + 'ln2.b'].data_ptr(), gr[p + 'out.b'].data_ptr(), w.ln_scratch.data_ptr(), M, d, dt, st),
+                'layernorm_bwd')
             # ---- attention branch: y = x + Wo attn(Wqkv ln1(x)) + bo
             self._gemm(d, inner, M, dy, d, 0, w.o[l], inner, 0, EPI_ATOMIC_F32, gr[p + 'out.w'], inner, split_k=0)
             self._gemm(M, inner, d, dy, d, 1, wt[p + 'out.w'], inner, 0, EPI_STORE, w.d_o, inner)
@@ -216,7 +218,8 @@ class StepEngine:
             _lib.check(lib.ecgvit_layernorm_bwd(
                 w.dln.data_ptr(), w.x[l].data_ptr(), pf[p + 'ln1.w'].data_ptr(), w.stat1[l][0].data_ptr(),
                 w.stat1[l][1].data_ptr(), dy.data_ptr(), dz.data_ptr(), gr[p + 'ln1.w'].data_ptr(),
-                gr[p + 'ln1.b'].data_ptr(), _lib.ptr(below_bias), M, d, dt, st), 'layernorm_bwd')
+                gr[p + 'ln1.b'].data_ptr(), _lib.ptr(below_bias), w.ln_scratch.data_ptr(), M, d, dt, st),
+                'layernorm_bwd')
             if m._after_layer_backward is not None:
                 m._after_layer_backward(l)
         # ---- embedding: tok = [cls | a_patch We^T + be] + pos

@@ -11,6 +11,7 @@ reaches the kernels through a 64-byte device block, and the non-finite check of 
 flag polled on request.  With `world_size > 1` gradients are summed over NCCL in per-layer buckets on a side
 stream while backward is still running (`parallel.py`).
 """
+import collections
 import math
 
 import torch
@@ -47,7 +48,7 @@ def get_train_args(args=None, n_train=None):
 class FusedTrainer:
     def __init__(self, model, learning_rate=3e-4, weight_decay=1e-2, betas=(0.9, 0.999), eps=1e-8,
                  schedule='constant', n_warmup=0, n_step=1 << 30, max_grad_norm=1.0, process_group=None,
-                 bucket_layers=2, use_cuda_graph=False):
+                 bucket_layers=2, use_cuda_graph=False, data_parallel=True):
         self.model = model
         self.lr, self.wd, self.betas, self.eps = learning_rate, weight_decay, betas, eps
         self.schedule, self.n_warmup, self.n_step = schedule, n_warmup, n_step
@@ -56,7 +57,8 @@ class FusedTrainer:
         self.lib = _lib.load()
         self.group = process_group
         self.world = 1
-        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+        if data_parallel and (process_group is not None or
+                              (torch.distributed.is_available() and torch.distributed.is_initialized())):
             self.world = torch.distributed.get_world_size(process_group)
         self.bucket_layers = bucket_layers
         self.use_cuda_graph = use_cuda_graph
@@ -64,6 +66,7 @@ class FusedTrainer:
         self._graph = None
         self._reducer = None
         self.launches_per_step = None
+        self._step_done = collections.deque(maxlen=2)
 
     # ---- lazily created device state ---------------------------------------------------------------
     def _ensure_state(self, device):
@@ -119,11 +122,14 @@ class FusedTrainer:
             raise NotImplementedError('dropout > 0 is not implemented in the fused step yet')
         self._ensure_state(sample_values.device)
         self._upload_hyper()
-        if self.use_cuda_graph and self._reducer is None:
+        if self.use_cuda_graph:
             out = self._graph_step(sample_values, labels)
         else:
             out = self._device_step(sample_values, labels)
         self.step_count += 1  # scheduler.step() (train.py:283)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._step_done.append(ev)  # lets stage() reuse an input slot only after the step that read it
         return out
 
     def _graph_step(self, sample_values, labels):
@@ -153,6 +159,34 @@ class FusedTrainer:
         self._static_y.copy_(labels, non_blocking=True)
         self._graph.replay()
         return self._graph_out
+
+    # ---- input staging ---------------------------------------------------------------------------------
+    def stage(self, sample_values_host, labels_host):
+        """Start the host->device copy of the NEXT batch on a side stream (pinned source recommended) and return device
+        tensors whose use on the current stream is ordered after the copy.  Two slots alternate, so when calls go
+        `cur = stage(); loop: step(*cur); nxt = stage(); ...; cur = nxt` the copy of batch i+1 overlaps the kernels of
+        step i (the reference copies synchronously inside the step, train.py:274)."""
+        dev = torch.device('cuda', torch.cuda.current_device())
+        if getattr(self, '_stage_slots', None) is None or self._stage_slots[0][0].shape != sample_values_host.shape:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._stage_slots = [(torch.empty(sample_values_host.shape, device=dev, dtype=torch.float32),
+                                  torch.empty(labels_host.shape, device=dev, dtype=torch.float32),
+                                  torch.cuda.Event()) for _ in range(2)]
+            self._stage_next = 0
+        xd, yd, copied = self._stage_slots[self._stage_next]
+        self._stage_next ^= 1
+        cs = self._copy_stream
+        # this slot was last read by the step BEFORE the most recently enqueued one (which reads the other slot)
+        if len(self._step_done) == 2:
+            cs.wait_event(self._step_done[0])
+        elif len(self._step_done) == 1 and self.step_count >= 2:
+            cs.wait_event(self._step_done[0])
+        with torch.cuda.stream(cs):
+            xd.copy_(sample_values_host, non_blocking=True)
+            yd.copy_(labels_host, non_blocking=True)
+            copied.record(cs)
+        torch.cuda.current_stream().wait_event(copied)
+        return xd, yd
 
     # ---- host-visible results (these synchronise) ----------------------------------------------------
     def grad_norm(self):

@@ -64,10 +64,12 @@ int ecgvit_embed_assemble_bwd(const void *dtok, void *de, float *dcls, float *dp
 /* ---- nn.LayerNorm(d, eps) forward (PreNorm.norm / mlp_head[0]); saves per-row mean and rstd (fp32) */
 int ecgvit_layernorm_fwd(const void *x, const float *gamma, const float *beta, void *y, float *mean,
                          float *rstd, int M, int d, float eps, int dtype, void *stream);
-/* backward: dx = (dres ? dres : 0) + LN'(dy); dgamma += ..; dbeta += ..; if dcolsum: dcolsum += colsum(dx) */
+/* backward: dx = (dres ? dres : 0) + LN'(dy); dgamma += ..; dbeta += ..; if dcolsum: dcolsum += colsum(dx).
+ * scratch: fp32 workspace of ecgvit_layernorm_bwd_scratch_floats(d) elements (per-CTA column partials) */
+int64_t ecgvit_layernorm_bwd_scratch_floats(int d);
 int ecgvit_layernorm_bwd(const void *dy, const void *x, const float *gamma, const float *mean,
                          const float *rstd, const void *dres, void *dx, float *dgamma, float *dbeta,
-                         float *dcolsum, int M, int d, int dtype, void *stream);
+                         float *dcolsum, float *scratch, int M, int d, int dtype, void *stream);
 
 /* ---- dense contraction  C[m,n] = sum_k A(m,k) * B(n,k)  with fused epilogue.
  *      Replaces nn.Linear forward / its autograd dgrad / wgrad (vit_pytorch Attention.to_qkv, to_out[0],

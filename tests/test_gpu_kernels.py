@@ -168,9 +168,10 @@ def test_layernorm_fwd_bwd(lib, dtype, d):
     yr.backward(dy.float())
     dx = torch.empty(M, d, device='cuda', dtype=td)
     dg, db, dc = (torch.zeros(d, device='cuda') for _ in range(3))
+    scratch = torch.empty(int(lib.ecgvit_layernorm_bwd_scratch_floats(d)), device='cuda')
     L.check(lib.ecgvit_layernorm_bwd(dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
-                                     dres.data_ptr(), dx.data_ptr(), dg.data_ptr(), db.data_ptr(), dc.data_ptr(), M, d,
-                                     dtype, stream()), 'ln_bwd')
+                                     dres.data_ptr(), dx.data_ptr(), dg.data_ptr(), db.data_ptr(), dc.data_ptr(),
+                                     scratch.data_ptr(), M, d, dtype, stream()), 'ln_bwd')
     want_dx = xr.grad + dres.float()
     assert rel(dx, want_dx) < (1e-5 if dtype == L.F32 else 5e-3)
     assert rel(dg, gr.grad) < 1e-4 and rel(db, br.grad) < 1e-4
