@@ -378,8 +378,11 @@ def main():
             'roofline': roofline, 'cpu_baseline': cpu_baseline, 'kernels': kernels,
         }
         print(json.dumps(line), flush=True)
+    sys.stdout.flush()
     if world > 1:
-        dist.destroy_process_group()
+        # NCCL communicators captured in live CUDA graphs do not tear down cleanly: leave without the destructor dance
+        torch.cuda.synchronize()
+        os._exit(0)
 
 
 if __name__ == '__main__':

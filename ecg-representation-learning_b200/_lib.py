@@ -12,6 +12,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, 'libecgvit_b200.so')
 
 F32, BF16 = 0, 1
+STATS_FLOATS = 2052  # ECGVIT_STATS_FLOATS
 EPI_STORE, EPI_BIAS_RES, EPI_BIAS_GELU, EPI_DGELU, EPI_ATOMIC_F32 = 0, 1, 2, 3, 4
 REDUCTION = {'mean': 0, 'sum': 1, 'none': 2}
 
@@ -83,7 +84,7 @@ def last_error():
 
 
 # kernels launched per successful entry-point call (memsets are not kernels); feeds bench.py's `gpu_launches`
-KERNELS_PER_CALL = {'head_fwd': 2, 'head_bwd': 3, 'layernorm_bwd': 2}
+KERNELS_PER_CALL = {'head_fwd': 2, 'head_bwd': 3, 'layernorm_bwd': 2, 'grad_sumsq': 2}
 launch_counter = [0]
 
 

@@ -44,15 +44,24 @@ __device__ __forceinline__ float quad_max(float v) {
     return v;
 }
 
-// copy an [N x DH] head tile (row stride `ld` elements) into smem [NMAX][DH + 8], zero-filling rows >= N
+__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(dst))),
+                 "l"(src)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+// copy an [N x DH] head tile (row stride `ld` elements) into smem [NMAX][DH + 8] with cp.async (no register staging),
+// zero-filling rows >= N; the caller waits with cp_async_wait_all() + __syncthreads()
 template <int DH>
-__device__ __forceinline__ void load_tile(bf16 (*dst)[DH + 8], const bf16 *src, int64_t ld, int N) {
+__device__ __forceinline__ void load_tile(bf16 (*dst)[DH + 8], const bf16 *src, int ld, int N) {
     constexpr int VPR = DH / 8;
     for (int i = threadIdx.x; i < NMAX * VPR; i += blockDim.x) {
         const int r = i / VPR, c = (i % VPR) * 8;
-        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (r < N) v = *reinterpret_cast<const uint4 *>(src + (int64_t)r * ld + c);
-        *reinterpret_cast<uint4 *>(&dst[r][c]) = v;
+        if (r < N) cp_async16(&dst[r][c], src + r * ld + c);
+        else *reinterpret_cast<uint4 *>(&dst[r][c]) = make_uint4(0u, 0u, 0u, 0u);
     }
 }
 
@@ -120,13 +129,13 @@ __device__ __forceinline__ void transposed_times_rows(float acc[DH / 8][4], bf16
 }
 
 template <int DH>
-__device__ __forceinline__ void store_rows(bf16 *dst, int64_t ld, float acc[DH / 8][4], int r0, int r1, int N, int t,
+__device__ __forceinline__ void store_rows(bf16 *dst, int ld, float acc[DH / 8][4], int r0, int r1, int N, int t,
                                            float mul0, float mul1) {
+    bf16 *p0 = dst + r0 * ld + 2 * t, *p1 = dst + r1 * ld + 2 * t;
 #pragma unroll
     for (int j = 0; j < DH / 8; ++j) {
-        const int c = 8 * j + 2 * t;
-        if (r0 < N) *reinterpret_cast<uint32_t *>(dst + (int64_t)r0 * ld + c) = pack_bf16x2(acc[j][0] * mul0, acc[j][1] * mul0);
-        if (r1 < N) *reinterpret_cast<uint32_t *>(dst + (int64_t)r1 * ld + c) = pack_bf16x2(acc[j][2] * mul1, acc[j][3] * mul1);
+        if (r0 < N) *reinterpret_cast<uint32_t *>(p0 + 8 * j) = pack_bf16x2(acc[j][0] * mul0, acc[j][1] * mul0);
+        if (r1 < N) *reinterpret_cast<uint32_t *>(p1 + 8 * j) = pack_bf16x2(acc[j][2] * mul1, acc[j][3] * mul1);
     }
 }
 
@@ -138,11 +147,12 @@ __global__ void __launch_bounds__(128) attention_fwd_mma_kernel(const bf16 *__re
     __shared__ __align__(16) bf16 sV[NMAX][DH + 8];
     const int h = blockIdx.x % H, b = blockIdx.x / H;
     const int inner = H * DH;
-    const int64_t ld = 3 * (int64_t)inner;
-    const bf16 *base = qkv + (int64_t)b * N * ld + (int64_t)h * DH;
+    const int ld = 3 * inner;
+    const bf16 *base = qkv + (int64_t)b * N * ld + h * DH;
     load_tile<DH>(sQ, base, ld, N);
     load_tile<DH>(sK, base + inner, ld, N);
     load_tile<DH>(sV, base + 2 * inner, ld, N);
+    cp_async_wait_all();
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = warp * 16;
@@ -167,8 +177,8 @@ __global__ void __launch_bounds__(128) attention_fwd_mma_kernel(const bf16 *__re
     float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        s[j][0] = exp2f((s[j][0] - mx0) * sl2); s[j][1] = exp2f((s[j][1] - mx0) * sl2);
-        s[j][2] = exp2f((s[j][2] - mx1) * sl2); s[j][3] = exp2f((s[j][3] - mx1) * sl2);
+        s[j][0] = ex2_approx((s[j][0] - mx0) * sl2); s[j][1] = ex2_approx((s[j][1] - mx0) * sl2);
+        s[j][2] = ex2_approx((s[j][2] - mx1) * sl2); s[j][3] = ex2_approx((s[j][3] - mx1) * sl2);
         sum0 += s[j][0] + s[j][1];
         sum1 += s[j][2] + s[j][3];
     }
@@ -189,7 +199,7 @@ __global__ void __launch_bounds__(128) attention_fwd_mma_kernel(const bf16 *__re
         for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
     frag_times_rows<DH>(acc, pa, sV, n_tiles16, lane);
     const int r0 = m0 + g, r1 = r0 + 8;
-    bf16 *ob = o + (int64_t)b * N * inner + (int64_t)h * DH;
+    bf16 *ob = o + (int64_t)b * N * inner + h * DH;
     store_rows<DH>(ob, inner, acc, r0, r1, N, t, 1.0f / sum0, 1.0f / sum1);
     if (t == 0) {
         float *l = lse + ((int64_t)b * H + h) * N;
@@ -211,39 +221,60 @@ __global__ void __launch_bounds__(128) attention_bwd_mma_kernel(const bf16 *__re
     TileN sP = reinterpret_cast<TileN>(sdO + NMAX);
     TileN sdS = sP + NMAX;
 
+    float *sD = reinterpret_cast<float *>(sdS + NMAX);  // [NMAX] rowsum(dO * O)
+
     const int h = blockIdx.x % H, b = blockIdx.x / H;
     const int inner = H * DH;
-    const int64_t ld = 3 * (int64_t)inner;
-    const bf16 *base = qkv + (int64_t)b * N * ld + (int64_t)h * DH;
-    const bf16 *ob = o + (int64_t)b * N * inner + (int64_t)h * DH;
+    const int ld = 3 * inner;
+    const bf16 *base = qkv + (int64_t)b * N * ld + h * DH;
+    const bf16 *ob = o + (int64_t)b * N * inner + h * DH;
+    const bf16 *dob = d_o + (int64_t)b * N * inner + h * DH;
     load_tile<DH>(sQ, base, ld, N);
     load_tile<DH>(sK, base + inner, ld, N);
     load_tile<DH>(sV, base + 2 * inner, ld, N);
-    load_tile<DH>(sdO, d_o + (int64_t)b * N * inner + (int64_t)h * DH, inner, N);
+    load_tile<DH>(sdO, dob, inner, N);
+    // the O tile never goes to shared memory: its chunks stay in registers until dO has landed, then
+    // D[r] = sum_d dO[r,d] * O[r,d] is reduced over the DH/8 consecutive threads that hold row r
+    constexpr int VPR = DH / 8;
+    constexpr int CHUNKS = (NMAX * VPR) / 128;
+    uint4 oreg[CHUNKS];
+#pragma unroll
+    for (int k = 0; k < CHUNKS; ++k) {
+        const int i = threadIdx.x + k * 128;
+        const int r = i / VPR, c = (i % VPR) * 8;
+        oreg[k] = make_uint4(0u, 0u, 0u, 0u);
+        if (r < N) oreg[k] = *reinterpret_cast<const uint4 *>(ob + r * inner + c);
+    }
+    cp_async_wait_all();
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < CHUNKS; ++k) {
+        const int i = threadIdx.x + k * 128;
+        const int r = i / VPR, c = (i % VPR) * 8;
+        float ov[8], dv[8];
+        const uint4 d4 = *reinterpret_cast<const uint4 *>(&sdO[r][c]);
+        unpack_bf16x2(oreg[k].x, ov[0], ov[1]); unpack_bf16x2(oreg[k].y, ov[2], ov[3]);
+        unpack_bf16x2(oreg[k].z, ov[4], ov[5]); unpack_bf16x2(oreg[k].w, ov[6], ov[7]);
+        unpack_bf16x2(d4.x, dv[0], dv[1]); unpack_bf16x2(d4.y, dv[2], dv[3]);
+        unpack_bf16x2(d4.z, dv[4], dv[5]); unpack_bf16x2(d4.w, dv[6], dv[7]);
+        float part = 0.f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) part = fmaf(ov[e], dv[e], part);
+#pragma unroll
+        for (int off = VPR / 2; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+        if ((i % VPR) == 0) sD[r] = part;
+    }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = warp * 16;
     const int g = lane >> 2, t = lane & 3;
     const int n_tiles16 = (N + 15) / 16;
-    bf16 *dq = dqkv + (int64_t)b * N * ld + (int64_t)h * DH;
+    bf16 *dq = dqkv + (int64_t)b * N * ld + h * DH;
     const bool active = m0 < N;  // this warp owns query rows (and, later, key rows) m0 .. m0+15
 
     if (active) {
         const int r0 = m0 + g, r1 = r0 + 8;
-        // D[r] = sum_d dO[r,d] * O[r,d]   (each quad splits the head dim)
-        float D0 = 0.f, D1 = 0.f;
-        for (int d = t * 2; d < DH; d += 8) {
-            if (r0 < N) {
-                const __nv_bfloat162 ov = *reinterpret_cast<const __nv_bfloat162 *>(ob + (int64_t)r0 * inner + d);
-                D0 += __bfloat162float(sdO[r0][d]) * __low2float(ov) + __bfloat162float(sdO[r0][d + 1]) * __high2float(ov);
-            }
-            if (r1 < N) {
-                const __nv_bfloat162 ov = *reinterpret_cast<const __nv_bfloat162 *>(ob + (int64_t)r1 * inner + d);
-                D1 += __bfloat162float(sdO[r1][d]) * __low2float(ov) + __bfloat162float(sdO[r1][d + 1]) * __high2float(ov);
-            }
-        }
-        D0 = quad_sum(D0);
-        D1 = quad_sum(D1);
+        const float D0 = sD[r0], D1 = sD[r1];
         const float *l = lse + ((int64_t)b * H + h) * N;
         const float l0 = r0 < N ? l[r0] * LOG2E : 0.f, l1 = r1 < N ? l[r1] * LOG2E : 0.f;
 
@@ -259,7 +290,7 @@ __global__ void __launch_bounds__(128) attention_bwd_mma_kernel(const bf16 *__re
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const bool valid = (c + (i & 1) < N) && ((i < 2 ? r0 : r1) < N);
-                p[i] = valid ? exp2f(s[j][i] * sl2 - (i < 2 ? l0 : l1)) : 0.f;
+                p[i] = valid ? ex2_approx(s[j][i] * sl2 - (i < 2 ? l0 : l1)) : 0.f;
                 ds[i] = p[i] * (dp[j][i] - (i < 2 ? D0 : D1)) * scale;
             }
             const uint32_t p01 = pack_bf16x2(p[0], p[1]), p23 = pack_bf16x2(p[2], p[3]);
@@ -300,7 +331,7 @@ __global__ void __launch_bounds__(128) attention_bwd_mma_kernel(const bf16 *__re
 }
 
 template <int DH> constexpr size_t bwd_smem_bytes() {
-    return sizeof(bf16) * (4 * NMAX * (DH + 8) + 2 * NMAX * (NMAX + 8));
+    return sizeof(bf16) * (4 * NMAX * (DH + 8) + 2 * NMAX * (NMAX + 8)) + sizeof(float) * NMAX;
 }
 
 template <int DH>

@@ -13,6 +13,12 @@ enum { H_LR = 0, H_BETA1, H_BETA2, H_EPS, H_WD, H_BC1, H_BC2, H_MAXNORM, H_GSCAL
        H_ONE_MINUS_B1, H_ONE_MINUS_B2, H_DECAY, H_STEP_SIZE, H_BC2_SQRT };
 enum { S_SUMSQ = 0, S_NONFINITE, S_NORM };
 
+// Stage 1: one partial sum of squares per CTA (fixed grid-stride order inside the CTA).
+// Stage 2: a single CTA adds the partials in index order.  No atomics: the total norm must be BIT-IDENTICAL on every
+// data-parallel replica (it scales the update through the clip coefficient), and run-to-run reproducible.
+constexpr int SUMSQ_MAX_BLOCKS = 2048;
+constexpr int S_PARTIALS = 4;  // stats[4 .. 4 + SUMSQ_MAX_BLOCKS) is scratch for the per-CTA partials
+
 __global__ void __launch_bounds__(256) grad_sumsq_kernel(const float *__restrict__ g, int64_t n,
                                                           const float *__restrict__ hyper, float *__restrict__ stats) {
     __shared__ float red[8];
@@ -32,9 +38,23 @@ __global__ void __launch_bounds__(256) grad_sumsq_kernel(const float *__restrict
     if (threadIdx.x < 32) {
         float t = threadIdx.x < 8 ? red[threadIdx.x] : 0.f;
         t = warp_sum(t);
+        if (threadIdx.x == 0) stats[S_PARTIALS + blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(256) grad_sumsq_finalize_kernel(float *__restrict__ stats, int nblocks) {
+    __shared__ float red[8];
+    float s = 0.f;
+    for (int i = threadIdx.x; i < nblocks; i += blockDim.x) s += stats[S_PARTIALS + i];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float t = threadIdx.x < 8 ? red[threadIdx.x] : 0.f;
+        t = warp_sum(t);
         if (threadIdx.x == 0) {
-            atomicAdd(&stats[S_SUMSQ], t);
-            if (!isfinite(t)) stats[S_NONFINITE] = 1.0f;
+            stats[S_SUMSQ] = t;
+            stats[S_NONFINITE] = isfinite(t) ? 0.0f : 1.0f;
         }
     }
 }
@@ -122,10 +142,13 @@ extern "C" {
 int ecgvit_grad_sumsq(const float *g, int64_t n, const float *hyper, float *stats, void *stream) {
     ECGVIT_REQUIRE(g && hyper && stats && n > 0, "grad_sumsq: bad arguments");
     ECGVIT_REQUIRE((reinterpret_cast<uintptr_t>(g) & 15) == 0, "grad_sumsq: g must be 16-byte aligned");
-    cudaError_t e = cudaMemsetAsync(stats, 0, 4 * sizeof(float), as_stream(stream));
-    if (e != cudaSuccess) return fail((int)e, "grad_sumsq: memset: %s", cudaGetErrorString(e));
-    grad_sumsq_kernel<<<flat_grid(n), 256, 0, as_stream(stream)>>>(g, n, hyper, stats);
-    return check_launch("grad_sumsq");
+    int grid = flat_grid(n);
+    if (grid > SUMSQ_MAX_BLOCKS) grid = SUMSQ_MAX_BLOCKS;
+    grad_sumsq_kernel<<<grid, 256, 0, as_stream(stream)>>>(g, n, hyper, stats);
+    int rc = check_launch("grad_sumsq");
+    if (rc) return rc;
+    grad_sumsq_finalize_kernel<<<1, 256, 0, as_stream(stream)>>>(stats, grid);
+    return check_launch("grad_sumsq_finalize");
 }
 
 int ecgvit_adamw_step(float *p, float *m, float *v, const float *g, void *shadow_bf16, int64_t n,

@@ -38,7 +38,7 @@ def _flat_grads(model):
 def _scratch(model):
     if getattr(model, '_opt_scratch', None) is None or model._opt_scratch[0].device != model._flat_p.device:
         dev = model._flat_p.device
-        model._opt_scratch = (torch.zeros(16, device=dev), torch.zeros(4, device=dev))
+        model._opt_scratch = (torch.zeros(16, device=dev), torch.zeros(_lib.STATS_FLOATS, device=dev))
     return model._opt_scratch
 
 

@@ -78,7 +78,7 @@ class FusedTrainer:
         self.exp_avg = torch.zeros(n, device=device, dtype=torch.float32)
         self.exp_avg_sq = torch.zeros(n, device=device, dtype=torch.float32)
         self.hyper = torch.zeros(16, device=device, dtype=torch.float32)
-        self.stats = torch.zeros(4, device=device, dtype=torch.float32)
+        self.stats = torch.zeros(_lib.STATS_FLOATS, device=device, dtype=torch.float32)
         if self.world > 1:
             from .parallel import BucketedGradReducer
             self._reducer = BucketedGradReducer(m, self.group, self.bucket_layers)

@@ -128,7 +128,10 @@ int ecgvit_colsum(const void *x, float *out, int M, int N, int64_t ld, int dtype
  *        [7] max_grad_norm (<=0: no clipping)  [8] grad_scale (1/world for DDP sum-allreduce)
  *        [9] 1-beta1  [10] 1-beta2  [11] 1-lr*weight_decay  [12] lr/(1-beta1^t)  [13] sqrt(1-beta2^t)
  *        ([9..13] are derived by the host in double precision, as torch.optim.AdamW derives them)
- *      stats (device, fp32[4]): [0] sum of squares of (grad_scale*g)  [1] non-finite flag  [2] total_norm (written by adamw) */
+ *      stats (device, fp32[ECGVIT_STATS_FLOATS]): [0] sum of squares of (grad_scale*g)  [1] non-finite flag
+ *        [2] total_norm (written by adamw / grad_scale_by_clip)  [4..] per-CTA partials (scratch).
+ *      The norm is reduced without atomics, so it is bit-identical on every replica and from run to run. */
+#define ECGVIT_STATS_FLOATS 2052
 int ecgvit_grad_sumsq(const float *g, int64_t n, const float *hyper, float *stats, void *stream);
 int ecgvit_adamw_step(float *p, float *m, float *v, const float *g, void *shadow_bf16, int64_t n,
                       const float *hyper, float *stats, void *stream);

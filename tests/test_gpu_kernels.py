@@ -175,7 +175,7 @@ def test_layernorm_fwd_bwd(lib, dtype, d):
     want_dx = xr.grad + dres.float()
     assert rel(dx, want_dx) < (1e-5 if dtype == L.F32 else 5e-3)
     assert rel(dg, gr.grad) < 1e-4 and rel(db, br.grad) < 1e-4
-    assert rel(dc, dx.float().sum(0)) < 1e-4
+    assert rel(dc, want_dx.sum(0)) < (1e-4 if dtype == L.F32 else 1e-3)  # column sums of the unrounded result
 
 
 @pytest.mark.parametrize('dtype', [L.F32, L.BF16])
@@ -282,7 +282,7 @@ def test_clip_and_adamw_match_torch(lib, max_norm):
     opt = torch.optim.AdamW([ref], lr=3e-4, weight_decay=1e-2)
     p, m, v = p0.clone(), torch.zeros(n, device='cuda'), torch.zeros(n, device='cuda')
     shadow = torch.empty(n, device='cuda', dtype=torch.bfloat16)
-    hyper, stats = torch.zeros(16, device='cuda'), torch.zeros(4, device='cuda')
+    hyper, stats = torch.zeros(16, device='cuda'), torch.zeros(L.STATS_FLOATS, device='cuda')
     for t in range(1, 4):
         g = g0 * t
         ref.grad = g.clone()
@@ -308,7 +308,7 @@ def test_adamw_skips_update_on_nonfinite_gradients(lib):
     p, m, v = p0.clone(), torch.zeros(n, device='cuda'), torch.zeros(n, device='cuda')
     g = torch.randn(n, device='cuda')
     g[17] = float('inf')
-    hyper, stats = torch.zeros(16, device='cuda'), torch.zeros(4, device='cuda')
+    hyper, stats = torch.zeros(16, device='cuda'), torch.zeros(L.STATS_FLOATS, device='cuda')
     hyper.copy_(torch.tensor(L.adamw_hyper(3e-4, 0.9, 0.999, 1e-8, 1e-2, 1, 1.0, 1.0)))
     L.check(lib.ecgvit_grad_sumsq(g.data_ptr(), n, hyper.data_ptr(), stats.data_ptr(), stream()), 'sumsq')
     L.check(lib.ecgvit_adamw_step(p.data_ptr(), m.data_ptr(), v.data_ptr(), g.data_ptr(), None, n, hyper.data_ptr(),
