@@ -66,11 +66,11 @@ __device__ __forceinline__ void load_tile(bf16 (*dst)[DH + 8], const bf16 *src, 
 }
 
 // s[j][:] (16 rows x 64 keys, C-fragment layout) = X[m0:m0+16, :DH] * Y[:, :DH]^T, both row-major in smem
-template <int DH>
-__device__ __forceinline__ void rows_times_transposed(float s[8][4], bf16 (*X)[DH + 8], bf16 (*Y)[DH + 8], int m0,
-                                                      int n_tiles16, int lane) {
+template <int DH, int NT>
+__device__ __forceinline__ void rows_times_transposed(float s[2 * NT][4], bf16 (*X)[DH + 8], bf16 (*Y)[DH + 8], int m0,
+                                                      int lane) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
+    for (int j = 0; j < 2 * NT; ++j)
 #pragma unroll
         for (int i = 0; i < 4; ++i) s[j][i] = 0.f;
 #pragma unroll
@@ -78,52 +78,46 @@ __device__ __forceinline__ void rows_times_transposed(float s[8][4], bf16 (*X)[D
         uint32_t a[4];
         ldsm_x4(a, &X[m0 + (lane & 7) + ((lane >> 3) & 1) * 8][kk * 16 + (lane >> 4) * 8]);
 #pragma unroll
-        for (int np = 0; np < 4; ++np) {
-            if (np < n_tiles16) {
-                uint32_t b[4];
-                ldsm_x4(b, &Y[np * 16 + (lane & 7) + (lane >> 4) * 8][kk * 16 + ((lane >> 3) & 1) * 8]);
-                mma16816(s[2 * np], a, b[0], b[1]);
-                mma16816(s[2 * np + 1], a, b[2], b[3]);
-            }
+        for (int np = 0; np < NT; ++np) {
+            uint32_t b[4];
+            ldsm_x4(b, &Y[np * 16 + (lane & 7) + (lane >> 4) * 8][kk * 16 + ((lane >> 3) & 1) * 8]);
+            mma16816(s[2 * np], a, b[0], b[1]);
+            mma16816(s[2 * np + 1], a, b[2], b[3]);
         }
     }
 }
 
 // acc[DH/8][4] (16 rows x DH) += P(16 x 64, given as A fragments per 16-key tile) * Z[:, :DH], Z row-major [key][d]
-template <int DH>
-__device__ __forceinline__ void frag_times_rows(float acc[DH / 8][4], const uint32_t pa[4][4], bf16 (*Z)[DH + 8],
-                                                int n_tiles16, int lane) {
+template <int DH, int NT>
+__device__ __forceinline__ void frag_times_rows(float acc[DH / 8][4], const uint32_t pa[NT][4], bf16 (*Z)[DH + 8],
+                                                int lane) {
 #pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-        if (kk < n_tiles16) {
+    for (int kk = 0; kk < NT; ++kk) {
 #pragma unroll
-            for (int dp = 0; dp < DH / 16; ++dp) {
-                uint32_t b[4];
-                ldsm_x4_t(b, &Z[kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8][dp * 16 + (lane >> 4) * 8]);
-                mma16816(acc[2 * dp], pa[kk], b[0], b[1]);
-                mma16816(acc[2 * dp + 1], pa[kk], b[2], b[3]);
-            }
+        for (int dp = 0; dp < DH / 16; ++dp) {
+            uint32_t b[4];
+            ldsm_x4_t(b, &Z[kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8][dp * 16 + (lane >> 4) * 8]);
+            mma16816(acc[2 * dp], pa[kk], b[0], b[1]);
+            mma16816(acc[2 * dp + 1], pa[kk], b[2], b[3]);
         }
     }
 }
 
 // acc (16 rows j0.. x DH) += W^T[j0:j0+16, :] * Z, with W stored [q][key] (pitch 72) and Z stored [q][d]
-template <int DH>
+template <int DH, int NT>
 __device__ __forceinline__ void transposed_times_rows(float acc[DH / 8][4], bf16 (*W)[NMAX + 8], bf16 (*Z)[DH + 8],
-                                                      int j0, int n_tiles16, int lane) {
+                                                      int j0, int lane) {
 #pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-        if (kk < n_tiles16) {
-            uint32_t a[4];
-            const int mi = lane >> 3;
-            ldsm_x4_t(a, &W[kk * 16 + (lane & 7) + (mi >> 1) * 8][j0 + (mi & 1) * 8]);
+    for (int kk = 0; kk < NT; ++kk) {
+        uint32_t a[4];
+        const int mi = lane >> 3;
+        ldsm_x4_t(a, &W[kk * 16 + (lane & 7) + (mi >> 1) * 8][j0 + (mi & 1) * 8]);
 #pragma unroll
-            for (int dp = 0; dp < DH / 16; ++dp) {
-                uint32_t b[4];
-                ldsm_x4_t(b, &Z[kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8][dp * 16 + (lane >> 4) * 8]);
-                mma16816(acc[2 * dp], a, b[0], b[1]);
-                mma16816(acc[2 * dp + 1], a, b[2], b[3]);
-            }
+        for (int dp = 0; dp < DH / 16; ++dp) {
+            uint32_t b[4];
+            ldsm_x4_t(b, &Z[kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8][dp * 16 + (lane >> 4) * 8]);
+            mma16816(acc[2 * dp], a, b[0], b[1]);
+            mma16816(acc[2 * dp + 1], a, b[2], b[3]);
         }
     }
 }
@@ -139,7 +133,7 @@ __device__ __forceinline__ void store_rows(bf16 *dst, int ld, float acc[DH / 8][
     }
 }
 
-template <int DH>
+template <int DH, int NT>
 __global__ void __launch_bounds__(128) attention_fwd_mma_kernel(const bf16 *__restrict__ qkv, bf16 *__restrict__ o,
                                                                  float *__restrict__ lse, int N, int H, float scale) {
     __shared__ __align__(16) bf16 sQ[NMAX][DH + 8];
@@ -158,14 +152,13 @@ __global__ void __launch_bounds__(128) attention_fwd_mma_kernel(const bf16 *__re
     const int m0 = warp * 16;
     if (m0 >= N) return;
     const int g = lane >> 2, t = lane & 3;
-    const int n_tiles16 = (N + 15) / 16;
 
-    float s[8][4];
-    rows_times_transposed<DH>(s, sQ, sK, m0, n_tiles16, lane);
+    float s[2 * NT][4];
+    rows_times_transposed<DH, NT>(s, sQ, sK, m0, lane);
     const float sl2 = scale * LOG2E;
     float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < 2 * NT; ++j) {
         const int c = 8 * j + 2 * t;
         if (c >= N) { s[j][0] = -INFINITY; s[j][2] = -INFINITY; }
         if (c + 1 >= N) { s[j][1] = -INFINITY; s[j][3] = -INFINITY; }
@@ -176,7 +169,7 @@ __global__ void __launch_bounds__(128) attention_fwd_mma_kernel(const bf16 *__re
     mx1 = quad_max(mx1);
     float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < 2 * NT; ++j) {
         s[j][0] = ex2_approx((s[j][0] - mx0) * sl2); s[j][1] = ex2_approx((s[j][1] - mx0) * sl2);
         s[j][2] = ex2_approx((s[j][2] - mx1) * sl2); s[j][3] = ex2_approx((s[j][3] - mx1) * sl2);
         sum0 += s[j][0] + s[j][1];
@@ -184,9 +177,9 @@ __global__ void __launch_bounds__(128) attention_fwd_mma_kernel(const bf16 *__re
     }
     sum0 = quad_sum(sum0);
     sum1 = quad_sum(sum1);
-    uint32_t pa[4][4];
+    uint32_t pa[NT][4];
 #pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
+    for (int kk = 0; kk < NT; ++kk) {
         pa[kk][0] = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
         pa[kk][1] = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
         pa[kk][2] = pack_bf16x2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
@@ -197,7 +190,7 @@ __global__ void __launch_bounds__(128) attention_fwd_mma_kernel(const bf16 *__re
     for (int j = 0; j < DH / 8; ++j)
 #pragma unroll
         for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
-    frag_times_rows<DH>(acc, pa, sV, n_tiles16, lane);
+    frag_times_rows<DH, NT>(acc, pa, sV, lane);
     const int r0 = m0 + g, r1 = r0 + 8;
     bf16 *ob = o + (int64_t)b * N * inner + h * DH;
     store_rows<DH>(ob, inner, acc, r0, r1, N, t, 1.0f / sum0, 1.0f / sum1);
@@ -208,7 +201,7 @@ __global__ void __launch_bounds__(128) attention_fwd_mma_kernel(const bf16 *__re
     }
 }
 
-template <int DH>
+template <int DH, int NT>
 __global__ void __launch_bounds__(128) attention_bwd_mma_kernel(const bf16 *__restrict__ qkv, const bf16 *__restrict__ o,
                                                                  const bf16 *__restrict__ d_o,
                                                                  const float *__restrict__ lse, bf16 *__restrict__ dqkv,
@@ -268,7 +261,6 @@ __global__ void __launch_bounds__(128) attention_bwd_mma_kernel(const bf16 *__re
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = warp * 16;
     const int g = lane >> 2, t = lane & 3;
-    const int n_tiles16 = (N + 15) / 16;
     bf16 *dq = dqkv + (int64_t)b * N * ld + h * DH;
     const bool active = m0 < N;  // this warp owns query rows (and, later, key rows) m0 .. m0+15
 
@@ -278,13 +270,13 @@ __global__ void __launch_bounds__(128) attention_bwd_mma_kernel(const bf16 *__re
         const float *l = lse + ((int64_t)b * H + h) * N;
         const float l0 = r0 < N ? l[r0] * LOG2E : 0.f, l1 = r1 < N ? l[r1] * LOG2E : 0.f;
 
-        float s[8][4], dp[8][4];
-        rows_times_transposed<DH>(s, sQ, sK, m0, n_tiles16, lane);    // S = Q K^T
-        rows_times_transposed<DH>(dp, sdO, sV, m0, n_tiles16, lane);  // dP = dO V^T
+        float s[2 * NT][4], dp[2 * NT][4];
+        rows_times_transposed<DH, NT>(s, sQ, sK, m0, lane);    // S = Q K^T
+        rows_times_transposed<DH, NT>(dp, sdO, sV, m0, lane);  // dP = dO V^T
         const float sl2 = scale * LOG2E;
-        uint32_t dsa[4][4];
+        uint32_t dsa[NT][4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < 2 * NT; ++j) {
             const int c = 8 * j + 2 * t;
             float p[4], ds[4];
 #pragma unroll
@@ -308,7 +300,7 @@ __global__ void __launch_bounds__(128) attention_bwd_mma_kernel(const bf16 *__re
         for (int j = 0; j < DH / 8; ++j)
 #pragma unroll
             for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
-        frag_times_rows<DH>(acc, dsa, sK, n_tiles16, lane);
+        frag_times_rows<DH, NT>(acc, dsa, sK, lane);
         store_rows<DH>(dq, ld, acc, r0, r1, N, t, 1.f, 1.f);
     }
     __syncthreads();
@@ -319,13 +311,13 @@ __global__ void __launch_bounds__(128) attention_bwd_mma_kernel(const bf16 *__re
         for (int j = 0; j < DH / 8; ++j)
 #pragma unroll
             for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
-        transposed_times_rows<DH>(acc, sdS, sQ, m0, n_tiles16, lane);  // dK = dS^T Q
+        transposed_times_rows<DH, NT>(acc, sdS, sQ, m0, lane);  // dK = dS^T Q
         store_rows<DH>(dq + inner, ld, acc, r0, r1, N, t, 1.f, 1.f);
 #pragma unroll
         for (int j = 0; j < DH / 8; ++j)
 #pragma unroll
             for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
-        transposed_times_rows<DH>(acc, sP, sdO, m0, n_tiles16, lane);  // dV = P^T dO
+        transposed_times_rows<DH, NT>(acc, sP, sdO, m0, lane);  // dV = P^T dO
         store_rows<DH>(dq + 2 * inner, ld, acc, r0, r1, N, t, 1.f, 1.f);
     }
 }
@@ -334,46 +326,60 @@ template <int DH> constexpr size_t bwd_smem_bytes() {
     return sizeof(bf16) * (4 * NMAX * (DH + 8) + 2 * NMAX * (NMAX + 8)) + sizeof(float) * NMAX;
 }
 
-template <int DH>
+template <int DH, int NT>
 int launch_bwd(const void *qkv, const void *o, const void *d_o, const float *lse, void *dqkv, int B, int N, int H,
                float scale, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(attention_bwd_mma_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(attention_bwd_mma_kernel<DH, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)bwd_smem_bytes<DH>());
         if (e != cudaSuccess) return fail((int)e, "attention_bwd_mma: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         attr_set = true;
     }
-    attention_bwd_mma_kernel<DH><<<B * H, 128, bwd_smem_bytes<DH>(), stream>>>(
+    attention_bwd_mma_kernel<DH, NT><<<B * H, 128, bwd_smem_bytes<DH>(), stream>>>(
         (const bf16 *)qkv, (const bf16 *)o, (const bf16 *)d_o, lse, (bf16 *)dqkv, N, H, scale);
     return check_launch("attention_bwd_mma");
+}
+
+template <int DH, int NT>
+int launch_fwd(const void *qkv, void *o, float *lse, int B, int N, int H, float scale, cudaStream_t stream) {
+    attention_fwd_mma_kernel<DH, NT><<<B * H, 128, 0, stream>>>((const bf16 *)qkv, (bf16 *)o, lse, N, H, scale);
+    return check_launch("attention_fwd_mma");
 }
 
 }  // namespace
 
 bool attention_mma_supported(int N, int dh) { return N <= NMAX && (dh == 16 || dh == 32 || dh == 64); }
 
+// the number of 16-key tiles is a template parameter so the inner loops carry no runtime predicates
+#define ECGVIT_ATTN_DISPATCH(FN, ...)                                                     \
+    do {                                                                                  \
+        const int nt = (N + 15) / 16;                                                     \
+        switch (dh * 8 + nt) {                                                            \
+            case 16 * 8 + 1: return FN<16, 1>(__VA_ARGS__);                               \
+            case 16 * 8 + 2: return FN<16, 2>(__VA_ARGS__);                               \
+            case 16 * 8 + 3: return FN<16, 3>(__VA_ARGS__);                               \
+            case 16 * 8 + 4: return FN<16, 4>(__VA_ARGS__);                               \
+            case 32 * 8 + 1: return FN<32, 1>(__VA_ARGS__);                               \
+            case 32 * 8 + 2: return FN<32, 2>(__VA_ARGS__);                               \
+            case 32 * 8 + 3: return FN<32, 3>(__VA_ARGS__);                               \
+            case 32 * 8 + 4: return FN<32, 4>(__VA_ARGS__);                               \
+            case 64 * 8 + 1: return FN<64, 1>(__VA_ARGS__);                               \
+            case 64 * 8 + 2: return FN<64, 2>(__VA_ARGS__);                               \
+            case 64 * 8 + 3: return FN<64, 3>(__VA_ARGS__);                               \
+            case 64 * 8 + 4: return FN<64, 4>(__VA_ARGS__);                               \
+            default: return fail(-1, "attention_mma: unsupported head dim %d / length %d", dh, N); \
+        }                                                                                 \
+    } while (0)
+
 int attention_fwd_mma(const void *qkv, void *o, float *lse, int B, int N, int H, int dh, float scale,
                       cudaStream_t stream) {
-    const bf16 *q = (const bf16 *)qkv;
-    bf16 *op = (bf16 *)o;
-    switch (dh) {
-        case 16: attention_fwd_mma_kernel<16><<<B * H, 128, 0, stream>>>(q, op, lse, N, H, scale); break;
-        case 32: attention_fwd_mma_kernel<32><<<B * H, 128, 0, stream>>>(q, op, lse, N, H, scale); break;
-        case 64: attention_fwd_mma_kernel<64><<<B * H, 128, 0, stream>>>(q, op, lse, N, H, scale); break;
-        default: return fail(-1, "attention_fwd_mma: unsupported head dim %d", dh);
-    }
-    return check_launch("attention_fwd_mma");
+    ECGVIT_ATTN_DISPATCH(launch_fwd, qkv, o, lse, B, N, H, scale, stream);
 }
 
 int attention_bwd_mma(const void *qkv, const void *o, const void *d_o, const float *lse, void *dqkv, int B, int N,
                       int H, int dh, float scale, cudaStream_t stream) {
-    switch (dh) {
-        case 16: return launch_bwd<16>(qkv, o, d_o, lse, dqkv, B, N, H, scale, stream);
-        case 32: return launch_bwd<32>(qkv, o, d_o, lse, dqkv, B, N, H, scale, stream);
-        case 64: return launch_bwd<64>(qkv, o, d_o, lse, dqkv, B, N, H, scale, stream);
-        default: return fail(-1, "attention_bwd_mma: unsupported head dim %d", dh);
-    }
+    ECGVIT_ATTN_DISPATCH(launch_bwd, qkv, o, d_o, lse, dqkv, B, N, H, scale, stream);
 }
 
 }  // namespace ecgvit
