@@ -26,7 +26,8 @@ class GemmArgs(Structure):
         ('epilogue', c_int),
         ('out', c_void_p), ('ldo', c_int64),
         ('out2', c_void_p), ('aux', c_void_p), ('bias', c_void_p),
-        ('dtype', c_int), ('split_k', c_int), ('reserved', c_int),
+        ('dtype', c_int), ('split_k', c_int),
+        ('dropout_stream', c_int), ('dropout_p', c_float), ('dropout_seed', c_void_p),
     ]
 
 
@@ -36,18 +37,22 @@ SIGNATURES = {
     'ecgvit_last_error': [],
     'ecgvit_device_ok': [],
     'ecgvit_patchify': [c_void_p, c_void_p, c_int, c_int, c_int64, c_int, c_int, c_int, c_void_p],
-    'ecgvit_embed_assemble': [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
-    'ecgvit_embed_assemble_bwd': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
-                                  c_void_p],
+    'ecgvit_embed_assemble': [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int, c_void_p,
+                              c_int, c_void_p],
+    'ecgvit_embed_assemble_bwd': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int,
+                                  c_void_p, c_int, c_void_p],
+    'ecgvit_dropout_bwd_copy': [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_float, c_int, c_void_p, c_int,
+                                c_void_p],
     'ecgvit_layernorm_fwd': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float,
                              c_int, c_void_p],
     'ecgvit_layernorm_bwd_scratch_floats': [c_int],
     'ecgvit_layernorm_bwd': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                              c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
     'ecgvit_gemm': [POINTER(GemmArgs), c_void_p],
-    'ecgvit_attention_fwd': [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p],
+    'ecgvit_attention_fwd': [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float, c_int,
+                             c_void_p, c_int, c_void_p],
     'ecgvit_attention_bwd': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float,
-                             c_int, c_void_p],
+                             c_float, c_int, c_void_p, c_int, c_void_p],
     'ecgvit_head_fwd': [c_void_p] * 11 + [c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p],
     'ecgvit_head_bwd': [c_void_p] * 15 + [c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p],
     'ecgvit_colsum': [c_void_p, c_void_p, c_int, c_int, c_int64, c_int, c_void_p],
@@ -108,6 +113,26 @@ profile_meta = [None]  # optional description of the next call (GEMM shape / epi
 def ptr(t):
     """device pointer of a torch tensor (or None)"""
     return None if t is None else t.data_ptr()
+
+
+def dropout_keep_mask(seed, stream, p, index):
+    """host replica of the kernels' counter-based dropout (csrc/common.cuh `dropout_hash`): multiplier (0 or
+    1/(1-p_q)) for every element index in the int64 tensor `index`; used by the tests to inject the SAME masks into the
+    CPU oracle"""
+    import torch
+    thr = min(int(p * 65536.0 + 0.5), 65535)
+    if thr == 0:
+        return torch.ones(index.shape, dtype=torch.float32)
+    m32 = 0xFFFFFFFF
+    idx = index.to(torch.int64)
+    pair = idx >> 1
+    h = (pair * 0x9E3779B1 + ((seed ^ ((stream * 0x85EBCA77 + 0xC2B2AE3D) & m32)) & m32)) & m32
+    h = h ^ (h >> 16); h = (h * 0x7feb352d) & m32
+    h = h ^ (h >> 15); h = (h * 0x846ca68b) & m32
+    h = h ^ (h >> 16)
+    bits = torch.where((idx & 1) == 1, h >> 16, h & 0xFFFF)
+    scale = 1.0 / (1.0 - thr / 65536.0)
+    return torch.where(bits >= thr, torch.tensor(scale, dtype=torch.float32), torch.tensor(0.0, dtype=torch.float32))
 
 
 def adamw_hyper(lr, beta1, beta2, eps, weight_decay, step, max_norm, grad_scale):

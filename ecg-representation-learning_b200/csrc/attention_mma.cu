@@ -135,7 +135,8 @@ __device__ __forceinline__ void store_rows(bf16 *dst, int ld, float acc[DH / 8][
 
 template <int DH, int NT>
 __global__ void __launch_bounds__(128) attention_fwd_mma_kernel(const bf16 *__restrict__ qkv, bf16 *__restrict__ o,
-                                                                 float *__restrict__ lse, int N, int H, float scale) {
+                                                                 float *__restrict__ lse, int N, int H, float scale,
+                                                                 DropoutParams drop) {
     __shared__ __align__(16) bf16 sQ[NMAX][DH + 8];
     __shared__ __align__(16) bf16 sK[NMAX][DH + 8];
     __shared__ __align__(16) bf16 sV[NMAX][DH + 8];
@@ -177,6 +178,20 @@ __global__ void __launch_bounds__(128) attention_fwd_mma_kernel(const bf16 *__re
     }
     sum0 = quad_sum(sum0);
     sum1 = quad_sum(sum1);
+    if (drop.threshold != 0) {
+        // attention-probability dropout: mask the (still unnormalised) probabilities that feed P V; the row sums
+        // keep normalising with the undropped values.  element index = ((b*H + h) * 64 + query) * 64 + key
+        const uint32_t seed = __ldg(drop.seed);
+        const uint32_t base0 = (static_cast<uint32_t>(blockIdx.x) * NMAX + (m0 + g)) * NMAX + 2 * t;
+#pragma unroll
+        for (int j = 0; j < 2 * NT; ++j) {
+            float a0, a1;
+            dropout_pair(drop, seed, base0 + 8 * j, a0, a1);
+            s[j][0] *= a0; s[j][1] *= a1;
+            dropout_pair(drop, seed, base0 + 8 * NMAX + 8 * j, a0, a1);
+            s[j][2] *= a0; s[j][3] *= a1;
+        }
+    }
     uint32_t pa[NT][4];
 #pragma unroll
     for (int kk = 0; kk < NT; ++kk) {
@@ -205,7 +220,7 @@ template <int DH, int NT>
 __global__ void __launch_bounds__(128) attention_bwd_mma_kernel(const bf16 *__restrict__ qkv, const bf16 *__restrict__ o,
                                                                  const bf16 *__restrict__ d_o,
                                                                  const float *__restrict__ lse, bf16 *__restrict__ dqkv,
-                                                                 int N, int H, float scale) {
+                                                                 int N, int H, float scale, DropoutParams drop) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     typedef bf16(*TileD)[DH + 8];
     typedef bf16(*TileN)[NMAX + 8];
@@ -274,16 +289,24 @@ __global__ void __launch_bounds__(128) attention_bwd_mma_kernel(const bf16 *__re
         rows_times_transposed<DH, NT>(s, sQ, sK, m0, lane);    // S = Q K^T
         rows_times_transposed<DH, NT>(dp, sdO, sV, m0, lane);  // dP = dO V^T
         const float sl2 = scale * LOG2E;
+        const bool dropping = drop.threshold != 0;
+        const uint32_t seed = dropping ? __ldg(drop.seed) : 0u;
+        const uint32_t base0 = (static_cast<uint32_t>(blockIdx.x) * NMAX + r0) * NMAX + 2 * t;
         uint32_t dsa[NT][4];
 #pragma unroll
         for (int j = 0; j < 2 * NT; ++j) {
             const int c = 8 * j + 2 * t;
-            float p[4], ds[4];
+            float p[4], ds[4], mk[4] = {1.f, 1.f, 1.f, 1.f};
+            if (dropping) {
+                dropout_pair(drop, seed, base0 + 8 * j, mk[0], mk[1]);
+                dropout_pair(drop, seed, base0 + 8 * NMAX + 8 * j, mk[2], mk[3]);
+            }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const bool valid = (c + (i & 1) < N) && ((i < 2 ? r0 : r1) < N);
-                p[i] = valid ? ex2_approx(s[j][i] * sl2 - (i < 2 ? l0 : l1)) : 0.f;
-                ds[i] = p[i] * (dp[j][i] - (i < 2 ? D0 : D1)) * scale;
+                const float pu = valid ? ex2_approx(s[j][i] * sl2 - (i < 2 ? l0 : l1)) : 0.f;  // softmax probability
+                ds[i] = pu * (dp[j][i] * mk[i] - (i < 2 ? D0 : D1)) * scale;                  // dS uses the undropped P
+                p[i] = pu * mk[i];                                                            // dV uses the dropped P
             }
             const uint32_t p01 = pack_bf16x2(p[0], p[1]), p23 = pack_bf16x2(p[2], p[3]);
             const uint32_t d01 = pack_bf16x2(ds[0], ds[1]), d23 = pack_bf16x2(ds[2], ds[3]);
@@ -328,7 +351,7 @@ template <int DH> constexpr size_t bwd_smem_bytes() {
 
 template <int DH, int NT>
 int launch_bwd(const void *qkv, const void *o, const void *d_o, const float *lse, void *dqkv, int B, int N, int H,
-               float scale, cudaStream_t stream) {
+               float scale, DropoutParams drop, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(attention_bwd_mma_kernel<DH, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -337,13 +360,14 @@ int launch_bwd(const void *qkv, const void *o, const void *d_o, const float *lse
         attr_set = true;
     }
     attention_bwd_mma_kernel<DH, NT><<<B * H, 128, bwd_smem_bytes<DH>(), stream>>>(
-        (const bf16 *)qkv, (const bf16 *)o, (const bf16 *)d_o, lse, (bf16 *)dqkv, N, H, scale);
+        (const bf16 *)qkv, (const bf16 *)o, (const bf16 *)d_o, lse, (bf16 *)dqkv, N, H, scale, drop);
     return check_launch("attention_bwd_mma");
 }
 
 template <int DH, int NT>
-int launch_fwd(const void *qkv, void *o, float *lse, int B, int N, int H, float scale, cudaStream_t stream) {
-    attention_fwd_mma_kernel<DH, NT><<<B * H, 128, 0, stream>>>((const bf16 *)qkv, (bf16 *)o, lse, N, H, scale);
+int launch_fwd(const void *qkv, void *o, float *lse, int B, int N, int H, float scale, DropoutParams drop,
+               cudaStream_t stream) {
+    attention_fwd_mma_kernel<DH, NT><<<B * H, 128, 0, stream>>>((const bf16 *)qkv, (bf16 *)o, lse, N, H, scale, drop);
     return check_launch("attention_fwd_mma");
 }
 
@@ -373,13 +397,13 @@ bool attention_mma_supported(int N, int dh) { return N <= NMAX && (dh == 16 || d
     } while (0)
 
 int attention_fwd_mma(const void *qkv, void *o, float *lse, int B, int N, int H, int dh, float scale,
-                      cudaStream_t stream) {
-    ECGVIT_ATTN_DISPATCH(launch_fwd, qkv, o, lse, B, N, H, scale, stream);
+                      DropoutParams drop, cudaStream_t stream) {
+    ECGVIT_ATTN_DISPATCH(launch_fwd, qkv, o, lse, B, N, H, scale, drop, stream);
 }
 
 int attention_bwd_mma(const void *qkv, const void *o, const void *d_o, const float *lse, void *dqkv, int B, int N,
-                      int H, int dh, float scale, cudaStream_t stream) {
-    ECGVIT_ATTN_DISPATCH(launch_bwd, qkv, o, d_o, lse, dqkv, B, N, H, scale, stream);
+                      int H, int dh, float scale, DropoutParams drop, cudaStream_t stream) {
+    ECGVIT_ATTN_DISPATCH(launch_bwd, qkv, o, d_o, lse, dqkv, B, N, H, scale, drop, stream);
 }
 
 }  // namespace ecgvit

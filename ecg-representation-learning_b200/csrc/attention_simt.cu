@@ -25,7 +25,7 @@ __device__ __forceinline__ void load_head_tile(float *dst, const T *src, int64_t
 template <typename T>
 __global__ void __launch_bounds__(128) attention_fwd_simt_kernel(const T *__restrict__ qkv, T *__restrict__ o,
                                                                   float *__restrict__ lse, int N, int H, int dh,
-                                                                  float scale) {
+                                                                  float scale, DropoutParams drop) {
     extern __shared__ float sm[];
     const int pitch = dh + 1, spitch = N + 1;
     float *Qs = sm, *Ks = Qs + N * pitch, *Vs = Ks + N * pitch, *S = Vs + N * pitch;
@@ -57,7 +57,14 @@ __global__ void __launch_bounds__(128) attention_fwd_simt_kernel(const T *__rest
         }
         sum = warp_sum(sum);
         const float inv = 1.0f / sum;
-        for (int j = lane; j < N; j += 32) S[i * spitch + j] *= inv;
+        if (drop.threshold != 0) {
+            // element index = ((b*H + h) * pitch + query) * pitch + key, pitch = N rounded up to 64
+            const uint32_t seed = __ldg(drop.seed), np = (N + 63) / 64 * 64;
+            for (int j = lane; j < N; j += 32)
+                S[i * spitch + j] *= inv * dropout_one(drop, seed, (blockIdx.x * np + i) * np + j);
+        } else {
+            for (int j = lane; j < N; j += 32) S[i * spitch + j] *= inv;
+        }
         if (lane == 0) lse[((int64_t)b * H + h) * N + i] = m + logf(sum);
     }
     __syncthreads();
@@ -74,7 +81,8 @@ template <typename T>
 __global__ void __launch_bounds__(128) attention_bwd_simt_kernel(const T *__restrict__ qkv, const T *__restrict__ o,
                                                                   const T *__restrict__ d_o,
                                                                   const float *__restrict__ lse, T *__restrict__ dqkv,
-                                                                  int N, int H, int dh, float scale) {
+                                                                  int N, int H, int dh, float scale,
+                                                                  DropoutParams drop) {
     extern __shared__ float sm[];
     const int pitch = dh + 1, spitch = N + 1;
     float *Qs = sm, *Ks = Qs + N * pitch, *Vs = Ks + N * pitch, *dOs = Vs + N * pitch;
@@ -109,20 +117,26 @@ __global__ void __launch_bounds__(128) attention_bwd_simt_kernel(const T *__rest
     __syncthreads();
     T *dq = dqkv + (int64_t)b * N * ld + (int64_t)h * dh;
     T *dk = dq + inner, *dv = dq + 2 * inner;
-    // dV[j,d] = sum_i P[i,j] dO[i,d]
+    const bool dropping = drop.threshold != 0;
+    const uint32_t seed = dropping ? __ldg(drop.seed) : 0u, np = (N + 63) / 64 * 64;
+    // dV[j,d] = sum_i Pdrop[i,j] dO[i,d]
     for (int idx = threadIdx.x; idx < N * dh; idx += blockDim.x) {
         const int j = idx / dh, d = idx - j * dh;
         float acc = 0.f;
-        for (int i = 0; i < N; ++i) acc = fmaf(P[i * spitch + j], dOs[i * pitch + d], acc);
+        for (int i = 0; i < N; ++i) {
+            const float mk = dropping ? dropout_one(drop, seed, (blockIdx.x * np + i) * np + j) : 1.f;
+            acc = fmaf(P[i * spitch + j] * mk, dOs[i * pitch + d], acc);
+        }
         dv[(int64_t)j * ld + d] = from_f32<T>(acc);
     }
     __syncthreads();
-    // dS = P * (dO V^T - D), in place over P
+    // dS = P * (mask * dO V^T - D), in place over P
     for (int idx = threadIdx.x; idx < N * N; idx += blockDim.x) {
         const int i = idx / N, j = idx - i * N;
         float dp = 0.f;
         for (int d = 0; d < dh; ++d) dp = fmaf(dOs[i * pitch + d], Vs[j * pitch + d], dp);
-        P[i * spitch + j] *= (dp - Dv[i]);
+        const float mk = dropping ? dropout_one(drop, seed, (blockIdx.x * np + i) * np + j) : 1.f;
+        P[i * spitch + j] *= (dp * mk - Dv[i]);
     }
     __syncthreads();
     for (int idx = threadIdx.x; idx < N * dh; idx += blockDim.x) {
@@ -150,29 +164,29 @@ template <typename K> int set_smem(K kern, size_t bytes, const char *what) {
 }  // namespace
 
 int attention_fwd_simt(const void *qkv, void *o, float *lse, int B, int N, int H, int dh, float scale, int dtype,
-                       cudaStream_t stream) {
+                       DropoutParams drop, cudaStream_t stream) {
     const size_t smem = fwd_smem(N, dh);
     int rc;
     if (dtype == ECGVIT_BF16) {
         if ((rc = set_smem(attention_fwd_simt_kernel<bf16>, smem, "attention_fwd"))) return rc;
-        attention_fwd_simt_kernel<bf16><<<B * H, 128, smem, stream>>>((const bf16 *)qkv, (bf16 *)o, lse, N, H, dh, scale);
+        attention_fwd_simt_kernel<bf16><<<B * H, 128, smem, stream>>>((const bf16 *)qkv, (bf16 *)o, lse, N, H, dh, scale, drop);
     } else {
         if ((rc = set_smem(attention_fwd_simt_kernel<float>, smem, "attention_fwd"))) return rc;
-        attention_fwd_simt_kernel<float><<<B * H, 128, smem, stream>>>((const float *)qkv, (float *)o, lse, N, H, dh, scale);
+        attention_fwd_simt_kernel<float><<<B * H, 128, smem, stream>>>((const float *)qkv, (float *)o, lse, N, H, dh, scale, drop);
     }
     return check_launch("attention_fwd_simt");
 }
 
 int attention_bwd_simt(const void *qkv, const void *o, const void *d_o, const float *lse, void *dqkv, int B, int N,
-                       int H, int dh, float scale, int dtype, cudaStream_t stream) {
+                       int H, int dh, float scale, int dtype, DropoutParams drop, cudaStream_t stream) {
     const size_t smem = bwd_smem(N, dh);
     int rc;
     if (dtype == ECGVIT_BF16) {
         if ((rc = set_smem(attention_bwd_simt_kernel<bf16>, smem, "attention_bwd"))) return rc;
-        attention_bwd_simt_kernel<bf16><<<B * H, 128, smem, stream>>>((const bf16 *)qkv, (const bf16 *)o, (const bf16 *)d_o, lse, (bf16 *)dqkv, N, H, dh, scale);
+        attention_bwd_simt_kernel<bf16><<<B * H, 128, smem, stream>>>((const bf16 *)qkv, (const bf16 *)o, (const bf16 *)d_o, lse, (bf16 *)dqkv, N, H, dh, scale, drop);
     } else {
         if ((rc = set_smem(attention_bwd_simt_kernel<float>, smem, "attention_bwd"))) return rc;
-        attention_bwd_simt_kernel<float><<<B * H, 128, smem, stream>>>((const float *)qkv, (const float *)o, (const float *)d_o, lse, (float *)dqkv, N, H, dh, scale);
+        attention_bwd_simt_kernel<float><<<B * H, 128, smem, stream>>>((const float *)qkv, (const float *)o, (const float *)d_o, lse, (float *)dqkv, N, H, dh, scale, drop);
     }
     return check_launch("attention_bwd_simt");
 }

@@ -213,6 +213,60 @@ template <bool kExact> __device__ __forceinline__ float gelu_grad(float u) {
     return fmaf(u, pdf, cdf);
 }
 
+// ---- dropout ----------------------------------------------------------------------------------------
+// Counter-based: the keep decision of element `idx` of dropout site `stream` is a pure function of
+// (seed, stream, idx), so backward regenerates the mask instead of reading one from HBM.  One 32-bit hash
+// (lowbias32) decides an aligned PAIR of elements with 16 bits each: drop if bits < threshold = round(p * 65536).
+// nn.Dropout semantics: y = x * keep / (1 - p).  (torch's Philox stream cannot be reproduced bit-for-bit by any other
+// implementation; tests inject this mask into the oracle instead.)
+struct DropoutParams {
+    const uint32_t *seed;  // device scalar, refreshed by the host every step; nullptr / threshold 0 = no dropout
+    uint32_t stream;       // which dropout site
+    uint32_t threshold;    // round(p * 65536)
+    float scale;           // 1 / (1 - threshold / 65536)
+};
+__device__ __forceinline__ uint32_t dropout_hash(uint32_t seed, uint32_t stream, uint32_t pair) {
+    uint32_t h = pair * 0x9E3779B1u + (seed ^ (stream * 0x85EBCA77u + 0xC2B2AE3Du));
+    h ^= h >> 16; h *= 0x7feb352du;
+    h ^= h >> 15; h *= 0x846ca68bu;
+    h ^= h >> 16;
+    return h;
+}
+// multipliers (0 or scale) for elements idx (even) and idx + 1
+__device__ __forceinline__ void dropout_pair(const DropoutParams &d, uint32_t seed, uint32_t idx_even, float &m0,
+                                             float &m1) {
+    const uint32_t h = dropout_hash(seed, d.stream, idx_even >> 1);
+    m0 = (h & 0xffffu) >= d.threshold ? d.scale : 0.f;
+    m1 = (h >> 16) >= d.threshold ? d.scale : 0.f;
+}
+// multiplier of a single element (any parity)
+__device__ __forceinline__ float dropout_one(const DropoutParams &d, uint32_t seed, uint32_t idx) {
+    const uint32_t h = dropout_hash(seed, d.stream, idx >> 1);
+    const uint32_t bits = (idx & 1u) ? (h >> 16) : (h & 0xffffu);
+    return bits >= d.threshold ? d.scale : 0.f;
+}
+// scale NV (even) consecutive values starting at even element index idx0
+template <int NV>
+__device__ __forceinline__ void dropout_apply(const DropoutParams &d, uint32_t seed, uint32_t idx0, float v[NV]) {
+#pragma unroll
+    for (int i = 0; i < NV; i += 2) {
+        float m0, m1;
+        dropout_pair(d, seed, idx0 + i, m0, m1);
+        v[i] *= m0;
+        v[i + 1] *= m1;
+    }
+}
+
+inline DropoutParams make_dropout(float p, int stream, const uint32_t *seed) {
+    DropoutParams d{nullptr, 0u, 0u, 1.0f};
+    if (seed != nullptr && p > 0.f) {
+        uint32_t thr = static_cast<uint32_t>(p * 65536.0f + 0.5f);
+        if (thr > 65535u) thr = 65535u;
+        if (thr > 0u) d = DropoutParams{seed, static_cast<uint32_t>(stream), thr, 1.0f / (1.0f - thr / 65536.0f)};
+    }
+    return d;
+}
+
 // ---- GEMM epilogue parameters shared by the tcgen05 and FFMA kernels -----------------------------
 struct EpiParams {
     void *out;
@@ -220,6 +274,7 @@ struct EpiParams {
     const void *aux;
     const float *bias;
     int64_t ldo;
+    DropoutParams drop;  // BIAS_RES: on (acc + bias); BIAS_GELU: on gelu(out); DGELU: on acc
 };
 
 // Applies epilogue MODE to NV (4 or 8) consecutive accumulator columns of one row and stores them.
@@ -244,6 +299,10 @@ __device__ __forceinline__ void epilogue_store(const EpiParams &p, int64_t row, 
         }
     }
     T *o = reinterpret_cast<T *>(p.out) + off;
+    const bool drop = p.drop.threshold != 0;
+    const uint32_t seed = drop ? __ldg(p.drop.seed) : 0u;
+    if (drop && (MODE == ECGVIT_EPI_BIAS_RES || MODE == ECGVIT_EPI_DGELU))
+        dropout_apply<NV>(p.drop, seed, static_cast<uint32_t>(off), acc);
     if (MODE == ECGVIT_EPI_BIAS_RES) {
         float r[NV];
         if (NV == 8) load8(reinterpret_cast<const T *>(p.aux) + off, r);
@@ -261,6 +320,7 @@ __device__ __forceinline__ void epilogue_store(const EpiParams &p, int64_t row, 
         // the saved pre-activation is what backward differentiates, so round it first (bf16 mode)
 #pragma unroll
         for (int i = 0; i < NV; ++i) h[i] = gelu_fwd<kExactGelu>(to_f32(from_f32<T>(acc[i])));
+        if (drop) dropout_apply<NV>(p.drop, seed, static_cast<uint32_t>(off), h);
         T *o2 = reinterpret_cast<T *>(p.out2) + off;
         if (NV == 8) store8(o2, h); else store4(o2, h);
     }

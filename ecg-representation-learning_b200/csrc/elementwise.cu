@@ -30,7 +30,10 @@ __global__ void patchify_kernel(const float *__restrict__ x, T *__restrict__ a, 
 // tok[b,0,:] = cls + pos[0];  tok[b,1+w,:] = e[b*n+w,:] + pos[1+w,:]
 template <typename T>
 __global__ void embed_assemble_kernel(const T *__restrict__ e, const float *__restrict__ cls,
-                                      const float *__restrict__ pos, T *__restrict__ tok, int B, int n_patch, int d) {
+                                      const float *__restrict__ pos, T *__restrict__ tok, int B, int n_patch, int d,
+                                      DropoutParams drop) {
+    const bool dropping = drop.threshold != 0;
+    const uint32_t seed = dropping ? __ldg(drop.seed) : 0u;
     const int N = n_patch + 1;
     const int vec_per_row = d / 8;
     const int64_t total = (int64_t)B * N * vec_per_row;
@@ -45,6 +48,7 @@ __global__ void embed_assemble_kernel(const T *__restrict__ e, const float *__re
         else load8(e + (b * n_patch + (j - 1)) * d + c, v);
 #pragma unroll
         for (int k = 0; k < 8; ++k) v[k] += p[k];
+        if (dropping) dropout_apply<8>(drop, seed, static_cast<uint32_t>(r * d + c), v);
         store8(tok + r * d + c, v);
     }
 }
@@ -53,14 +57,19 @@ __global__ void embed_assemble_kernel(const T *__restrict__ e, const float *__re
 template <typename T>
 __global__ void embed_assemble_bwd_kernel(const T *__restrict__ dtok, T *__restrict__ de, float *__restrict__ dcls,
                                           float *__restrict__ dpos, float *__restrict__ dbias, int B, int n_patch,
-                                          int d) {
+                                          int d, DropoutParams drop) {
     const int N = n_patch + 1;
     const int j = blockIdx.x;
     const int col = blockIdx.y * blockDim.x + threadIdx.x;
     if (col >= d) return;
+    const bool dropping = drop.threshold != 0;
+    const uint32_t seed = dropping ? __ldg(drop.seed) : 0u;
     float s = 0.f;
     for (int b = 0; b < B; ++b) {
-        const T g = dtok[((int64_t)b * N + j) * d + col];
+        const int64_t idx = ((int64_t)b * N + j) * d + col;
+        float gf = to_f32(dtok[idx]);
+        if (dropping) gf *= dropout_one(drop, seed, static_cast<uint32_t>(idx));
+        const T g = from_f32<T>(gf);
         s += to_f32(g);
         if (j > 0) de[((int64_t)b * n_patch + (j - 1)) * d + col] = g;
     }
@@ -298,21 +307,68 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const T *__restri
     }
 }
 
-// folds the per-CTA partial rows: dgamma += sum_b partial[b][0], dbeta += ...[1], dcolsum += ...[2]
+// folds the per-CTA partial rows: dgamma += sum_b partial[b][0], dbeta += ...[1], dcolsum += ...[2].
+// block = 32 columns x 8 row groups (coalesced 128-byte reads, 8 independent chains per column), smem tree at the end
 __global__ void __launch_bounds__(256) layernorm_bwd_finalize_kernel(const float *__restrict__ partial, int nblocks,
                                                                       float *__restrict__ dgamma,
                                                                       float *__restrict__ dbeta,
                                                                       float *__restrict__ dcolsum, int d) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= 3 * d) return;
+    __shared__ float red[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + tx;
     float t = 0.f;
-    for (int b = 0; b < nblocks; ++b) t += partial[(int64_t)b * 3 * d + i];
-    if (i < d) dgamma[i] += t;
-    else if (i < 2 * d) dbeta[i - d] += t;
-    else if (dcolsum != nullptr) dcolsum[i - 2 * d] += t;
+    if (i < 3 * d)
+        for (int b = ty; b < nblocks; b += 8) t += partial[(int64_t)b * 3 * d + i];
+    red[ty][tx] = t;
+    __syncthreads();
+    if (ty == 0 && i < 3 * d) {
+        float s = 0.f;
+#pragma unroll
+        for (int y = 0; y < 8; ++y) s += red[y][tx];
+        if (i < d) dgamma[i] += s;
+        else if (i < 2 * d) dbeta[i - d] += s;
+        else if (dcolsum != nullptr) dcolsum[i - 2 * d] += s;
+    }
 }
 
 constexpr int LN_BWD_MAX_BLOCKS = 2 * 160;  // >= 2 CTAs x SM count
+
+// ---------------------------------------------------------------------------------------------------
+// dym = mask * dy / (1 - p);  dcolsum[n] += sum_m dym[m, n].  Same block shape as colsum_kernel.
+template <typename T>
+__global__ void __launch_bounds__(256) dropout_bwd_copy_kernel(const T *__restrict__ dy, T *__restrict__ dym,
+                                                                float *__restrict__ dcolsum, int M, int N, int64_t ld,
+                                                                int rows_per_block, DropoutParams drop) {
+    __shared__ float red[8][32 * 8 + 1];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = (blockIdx.x * 32 + tx) * 8;
+    const int r0 = blockIdx.y * rows_per_block;
+    const int r1 = min(r0 + rows_per_block, M);
+    const uint32_t seed = __ldg(drop.seed);
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    if (c < N) {
+        for (int r = r0 + ty; r < r1; r += 8) {
+            float v[8];
+            load8(dy + (int64_t)r * ld + c, v);
+            dropout_apply<8>(drop, seed, static_cast<uint32_t>((int64_t)r * ld + c), v);
+            store8(dym + (int64_t)r * ld + c, v);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] += to_f32(from_f32<T>(v[k]));
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) red[ty][tx * 8 + k] = acc[k];
+    __syncthreads();
+    if (dcolsum != nullptr) {
+        float s = 0.f;
+#pragma unroll
+        for (int y = 0; y < 8; ++y) s += red[y][threadIdx.x];
+        const int col = blockIdx.x * 256 + threadIdx.x;
+        if (col < N) atomicAdd(dcolsum + col, s);
+    }
+}
 
 // ---------------------------------------------------------------------------------------------------
 // out[n] += sum_m x[m, n]; block = 32 column-vectors (8 wide) x 8 row lanes; grid.y splits the rows
@@ -389,27 +445,30 @@ int ecgvit_patchify(const float *x, void *a, int B, int C, int64_t x_ld, int n_p
 }
 
 int ecgvit_embed_assemble(const void *e, const float *cls, const float *pos, void *tok, int B, int n_patch, int d,
-                          int dtype, void *stream) {
+                          float dropout_p, int dropout_stream, const uint32_t *dropout_seed, int dtype, void *stream) {
+    const DropoutParams drop = make_dropout(dropout_p, dropout_stream, dropout_seed);
     ECGVIT_REQUIRE(e && cls && pos && tok && B > 0 && n_patch > 0, "embed_assemble: bad arguments");
     ECGVIT_REQUIRE(d % 8 == 0, "embed_assemble: d=%d must be a multiple of 8", d);
     const int64_t total = (int64_t)B * (n_patch + 1) * (d / 8);
     const int grid = grid_for(total, 256);
     if (dtype == ECGVIT_BF16)
-        embed_assemble_kernel<bf16><<<grid, 256, 0, as_stream(stream)>>>((const bf16 *)e, cls, pos, (bf16 *)tok, B, n_patch, d);
+        embed_assemble_kernel<bf16><<<grid, 256, 0, as_stream(stream)>>>((const bf16 *)e, cls, pos, (bf16 *)tok, B, n_patch, d, drop);
     else if (dtype == ECGVIT_F32)
-        embed_assemble_kernel<float><<<grid, 256, 0, as_stream(stream)>>>((const float *)e, cls, pos, (float *)tok, B, n_patch, d);
+        embed_assemble_kernel<float><<<grid, 256, 0, as_stream(stream)>>>((const float *)e, cls, pos, (float *)tok, B, n_patch, d, drop);
     else return fail(-1, "embed_assemble: unknown dtype %d", dtype);
     return check_launch("embed_assemble");
 }
 
 int ecgvit_embed_assemble_bwd(const void *dtok, void *de, float *dcls, float *dpos, float *dbias, int B,
-                              int n_patch, int d, int dtype, void *stream) {
+                              int n_patch, int d, float dropout_p, int dropout_stream, const uint32_t *dropout_seed,
+                              int dtype, void *stream) {
+    const DropoutParams drop = make_dropout(dropout_p, dropout_stream, dropout_seed);
     ECGVIT_REQUIRE(dtok && de && dcls && dpos && dbias && B > 0 && n_patch > 0 && d > 0, "embed_assemble_bwd: bad arguments");
     dim3 grid(n_patch + 1, (d + 127) / 128);
     if (dtype == ECGVIT_BF16)
-        embed_assemble_bwd_kernel<bf16><<<grid, 128, 0, as_stream(stream)>>>((const bf16 *)dtok, (bf16 *)de, dcls, dpos, dbias, B, n_patch, d);
+        embed_assemble_bwd_kernel<bf16><<<grid, 128, 0, as_stream(stream)>>>((const bf16 *)dtok, (bf16 *)de, dcls, dpos, dbias, B, n_patch, d, drop);
     else if (dtype == ECGVIT_F32)
-        embed_assemble_bwd_kernel<float><<<grid, 128, 0, as_stream(stream)>>>((const float *)dtok, (float *)de, dcls, dpos, dbias, B, n_patch, d);
+        embed_assemble_bwd_kernel<float><<<grid, 128, 0, as_stream(stream)>>>((const float *)dtok, (float *)de, dcls, dpos, dbias, B, n_patch, d, drop);
     else return fail(-1, "embed_assemble_bwd: unknown dtype %d", dtype);
     return check_launch("embed_assemble_bwd");
 }
@@ -486,7 +545,7 @@ int ecgvit_layernorm_bwd(const void *dy, const void *x, const float *gamma, cons
 #undef ECGVIT_LN_BWD
     int rc = check_launch("layernorm_bwd");
     if (rc) return rc;
-    layernorm_bwd_finalize_kernel<<<(3 * d + 255) / 256, 256, 0, st>>>(scratch, grid, dgamma, dbeta, dcolsum, d);
+    layernorm_bwd_finalize_kernel<<<(3 * d + 31) / 32, 256, 0, st>>>(scratch, grid, dgamma, dbeta, dcolsum, d);
     return check_launch("layernorm_bwd_finalize");
 }
 
@@ -505,6 +564,26 @@ int ecgvit_colsum(const void *x, float *out, int M, int N, int64_t ld, int dtype
         colsum_kernel<float><<<grid, 256, 0, as_stream(stream)>>>((const float *)x, out, M, N, ld, rows_per_block);
     else return fail(-1, "colsum: unknown dtype %d", dtype);
     return check_launch("colsum");
+}
+
+int ecgvit_dropout_bwd_copy(const void *dy, void *dym, float *dcolsum, int M, int N, int64_t ld, float dropout_p,
+                            int dropout_stream, const uint32_t *dropout_seed, int dtype, void *stream) {
+    ECGVIT_REQUIRE(dy && dym && M > 0 && N > 0, "dropout_bwd_copy: bad arguments");
+    ECGVIT_REQUIRE(N % 8 == 0 && ld % 8 == 0, "dropout_bwd_copy: N=%d and ld=%lld must be multiples of 8", N, (long long)ld);
+    const DropoutParams drop = make_dropout(dropout_p, dropout_stream, dropout_seed);
+    ECGVIT_REQUIRE(drop.threshold != 0, "dropout_bwd_copy: needs p > 0 and a seed");
+    const int col_blocks = (N + 255) / 256;
+    int row_blocks = (sm_count() * 4 + col_blocks - 1) / col_blocks;
+    if (row_blocks > (M + 63) / 64) row_blocks = (M + 63) / 64;
+    if (row_blocks < 1) row_blocks = 1;
+    const int rows_per_block = (M + row_blocks - 1) / row_blocks;
+    dim3 grid(col_blocks, (M + rows_per_block - 1) / rows_per_block);
+    if (dtype == ECGVIT_BF16)
+        dropout_bwd_copy_kernel<bf16><<<grid, 256, 0, as_stream(stream)>>>((const bf16 *)dy, (bf16 *)dym, dcolsum, M, N, ld, rows_per_block, drop);
+    else if (dtype == ECGVIT_F32)
+        dropout_bwd_copy_kernel<float><<<grid, 256, 0, as_stream(stream)>>>((const float *)dy, (float *)dym, dcolsum, M, N, ld, rows_per_block, drop);
+    else return fail(-1, "dropout_bwd_copy: unknown dtype %d", dtype);
+    return check_launch("dropout_bwd_copy");
 }
 
 int ecgvit_cast_f32_to_bf16(const float *src, void *dst, int64_t n, void *stream) {

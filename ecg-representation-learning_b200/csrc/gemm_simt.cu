@@ -75,7 +75,7 @@ int gemm_f32_ffma(const ecgvit_gemm_args *g, cudaStream_t stream) {
     const float *A = reinterpret_cast<const float *>(g->A), *B = reinterpret_cast<const float *>(g->B);
     const int64_t sAm = g->a_kmajor ? g->lda : 1, sAk = g->a_kmajor ? 1 : g->lda;
     const int64_t sBn = g->b_kmajor ? g->ldb : 1, sBk = g->b_kmajor ? 1 : g->ldb;
-    EpiParams ep{g->out, g->out2, g->aux, g->bias, g->ldo};
+    EpiParams ep{g->out, g->out2, g->aux, g->bias, g->ldo, make_dropout(g->dropout_p, g->dropout_stream, g->dropout_seed)};
     dim3 grid((g->N + TN - 1) / TN, (g->M + TM - 1) / TM);
     switch (g->epilogue) {
 #define ECGVIT_CASE(MODE) \

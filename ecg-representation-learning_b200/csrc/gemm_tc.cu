@@ -254,7 +254,7 @@ int launch(const ecgvit_gemm_args *g, int split_k, cudaStream_t stream) {
     const int tiles_m = (g->M + BM - 1) / BM, tiles_n = (g->N + BN - 1) / BN;
     const int units = tiles_m * tiles_n * split_k;
     const int grid = units < sm_count() ? units : sm_count();
-    EpiParams ep{g->out, g->out2, g->aux, g->bias, g->ldo};
+    EpiParams ep{g->out, g->out2, g->aux, g->bias, g->ldo, make_dropout(g->dropout_p, g->dropout_stream, g->dropout_seed)};
     kern<<<grid, kNumThreads, Cfg::SMEM_BYTES, stream>>>(ta, tb, g->M, g->N, g->K, split_k, ep);
     return check_launch("gemm_tc");
 }
@@ -310,7 +310,7 @@ int launch_pair(const ecgvit_gemm_args *g, int split_k, cudaStream_t stream) {
     const int units = tiles_m * tiles_n * split_k;
     const int clusters = sm_count() / 2;
     const int grid = 2 * (units < clusters ? units : clusters);
-    EpiParams ep{g->out, g->out2, g->aux, g->bias, g->ldo};
+    EpiParams ep{g->out, g->out2, g->aux, g->bias, g->ldo, make_dropout(g->dropout_p, g->dropout_stream, g->dropout_seed)};
     kern<<<grid, kNumThreads, Cfg::SMEM_BYTES, stream>>>(ta, tb, to, to2, tx, g->M, g->N, g->K, split_k, ep);
     return check_launch("gemm_tc2");
 }

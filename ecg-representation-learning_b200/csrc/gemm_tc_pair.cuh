@@ -45,8 +45,10 @@ __device__ __forceinline__ uint32_t sw64_offset(int lane, int j) {
 // The caller then issues one TMA store per tile (TMA clips rows >= M and columns >= N, so there are no guards here
 // except for the bias vector).
 template <int MODE>
-__device__ __forceinline__ void epilogue_unit32(const EpiParams &ep, int col_base, int N, const uint32_t r[32],
-                                                uint8_t *tile0, uint8_t *tile1, int lane) {
+__device__ __forceinline__ void epilogue_unit32(const EpiParams &ep, int64_t row, int col_base, int N,
+                                                const uint32_t r[32], uint8_t *tile0, uint8_t *tile1, int lane) {
+    const bool drop = ep.drop.threshold != 0;  // kernel-uniform
+    const uint32_t seed = drop ? __ldg(ep.drop.seed) : 0u;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const int col = col_base + 8 * j;
@@ -60,6 +62,8 @@ __device__ __forceinline__ void epilogue_unit32(const EpiParams &ep, int col_bas
             v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
         }
         const uint32_t soff = sw64_offset(lane, j);
+        const uint32_t eidx = static_cast<uint32_t>(row * ep.ldo + col);  // element index of v[0] (even)
+        if (drop && (MODE == ECGVIT_EPI_BIAS_RES || MODE == ECGVIT_EPI_DGELU)) dropout_apply<8>(ep.drop, seed, eidx, v);
         if (MODE == ECGVIT_EPI_BIAS_RES || MODE == ECGVIT_EPI_DGELU) {
             const uint4 a4 = *reinterpret_cast<const uint4 *>(tile0 + soff);
             float a[8];
@@ -88,6 +92,7 @@ __device__ __forceinline__ void epilogue_unit32(const EpiParams &ep, int col_bas
             float h[8];
 #pragma unroll
             for (int i = 0; i < 8; i += 2) gelu_fwd_pair(v[i], v[i + 1], h[i], h[i + 1]);
+            if (drop) dropout_apply<8>(ep.drop, seed, eidx, h);
             uint4 ph;
             ph.x = pack_bf16x2(h[0], h[1]); ph.y = pack_bf16x2(h[2], h[3]);
             ph.z = pack_bf16x2(h[4], h[5]); ph.w = pack_bf16x2(h[6], h[7]);
@@ -302,7 +307,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                         if (kHasAux) ptx::mbar_wait(&my_aux_bar[i], it & 1);
                     }
                     ptx::tmem_ld_wait();
-                    epilogue_unit32<MODE>(ep, col_base, N, r, t0, t1, lane);
+                    epilogue_unit32<MODE>(ep, static_cast<int64_t>(row_base) + lane, col_base, N, r, t0, t1, lane);
                     ptx::fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
                     __syncwarp();
                     if (lane == 0) {

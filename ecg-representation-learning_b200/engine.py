@@ -35,15 +35,37 @@ class StepEngine:
         self.lib = _lib.load()
         self.ws = {}
         self._cur = None
+        # device scalar holding this step's dropout seed (refreshed by the host before every training forward)
+        self.rng = torch.zeros(2, device=model._flat_p.device, dtype=torch.int32)
+        self._seed_counter = 0
+        self.base_seed = 0x5EED
+
+    def new_dropout_seed(self, seed=None):
+        """draw the seed of the next training forward (its backward regenerates the same masks from it)"""
+        self._seed_counter += 1
+        if seed is None:
+            seed = (self.base_seed * 0x9E3779B1 + self._seed_counter * 0x85EBCA6B) & 0x7FFFFFFF
+        self.rng.copy_(torch.tensor([seed, self._seed_counter & 0x7FFFFFFF], dtype=torch.int32))
+        return seed
+
+    def _dropout_probs(self):
+        """(p_embedding, p_block) as the reference wires them (ecg_vit.py:113-114); zero in eval mode"""
+        m = self.model
+        if not m.training:
+            return 0.0, 0.0
+        return float(m.config.attention_probs_dropout_prob), float(m.config.hidden_dropout_prob)
 
     # ---- helpers ---------------------------------------------------------------------------------
     @property
     def _stream(self):
         return torch.cuda.current_stream().cuda_stream
 
-    def _gemm(self, M, N, K, A, lda, a_k, B, ldb, b_k, epi, out, ldo, out2=None, aux=None, bias=None, split_k=1):
+    def _gemm(self, M, N, K, A, lda, a_k, B, ldb, b_k, epi, out, ldo, out2=None, aux=None, bias=None, split_k=1,
+              drop=None):
+        p, stream = drop if drop is not None else (0.0, 0)
         g = GemmArgs(M, N, K, A.data_ptr(), lda, a_k, B.data_ptr(), ldb, b_k, epi, out.data_ptr(), ldo,
-                     _lib.ptr(out2), _lib.ptr(aux), _lib.ptr(bias), self.model._dtype_code, split_k, 0)
+                     _lib.ptr(out2), _lib.ptr(aux), _lib.ptr(bias), self.model._dtype_code, split_k,
+                     stream, p, self.rng.data_ptr() if p > 0 else None)
         if _lib.profile[0] is not None:
             _lib.profile_meta[0] = (M, N, K, epi)
         _lib.check(self.lib.ecgvit_gemm(ctypes.byref(g), self._stream), 'gemm')
@@ -102,6 +124,7 @@ class StepEngine:
         w.dqkv = buf(M, 3 * inner)
         w.du = buf(M, mlp)
         w.de = buf(B * n, d)
+        w.dzm = buf(M, d)  # dropout-masked copy of a residual-stream gradient (only used when p > 0)
         w.ln_scratch = buf(int(self.lib.ecgvit_layernorm_bwd_scratch_floats(d)), dtype=torch.float32)
         self.ws[key] = w
         return w
@@ -130,26 +153,33 @@ class StepEngine:
         # e = a_patch @ We^T + be
         self._gemm(B * n, d, P * C, w.a_patch, P * C, 1, wt['embed.w'], P * C, 1, EPI_STORE, w.e, d,
                    bias=pf['embed.b'])
+        p_emb, p_blk = self._dropout_probs()
+        w.p_emb, w.p_blk = p_emb, p_blk
+        seed_ptr = self.rng.data_ptr()
         _lib.check(lib.ecgvit_embed_assemble(w.e.data_ptr(), pf['cls'].data_ptr(), pf['pos'].data_ptr(),
-                                             w.x[0].data_ptr(), B, n, d, dt, st), 'embed_assemble')
+                                             w.x[0].data_ptr(), B, n, d, p_emb, 0, seed_ptr if p_emb > 0 else None,
+                                             dt, st), 'embed_assemble')
         scale = float(dh) ** -0.5
+        blk_seed = seed_ptr if p_blk > 0 else None
         for l in range(c.num_hidden_layers):
             p = f'l{l}.'
+            # dropout sites of block l: 1+4l attention probabilities, 2+4l after to_out, 3+4l after GELU, 4+4l after net[3]
+            s_att, s_out, s_act, s_ff2 = 1 + 4 * l, 2 + 4 * l, 3 + 4 * l, 4 + 4 * l
             _lib.check(lib.ecgvit_layernorm_fwd(w.x[l].data_ptr(), pf[p + 'ln1.w'].data_ptr(), pf[p + 'ln1.b'].data_ptr(),
                                                 w.ln1[l].data_ptr(), w.stat1[l][0].data_ptr(), w.stat1[l][1].data_ptr(),
                                                 M, d, LN_EPS, dt, st), 'layernorm_fwd')
             self._gemm(M, 3 * inner, d, w.ln1[l], d, 1, wt[p + 'qkv.w'], d, 1, EPI_STORE, w.qkv[l], 3 * inner)
             _lib.check(lib.ecgvit_attention_fwd(w.qkv[l].data_ptr(), w.o[l].data_ptr(), w.lse[l].data_ptr(), B, N, H, dh,
-                                                scale, dt, st), 'attention_fwd')
+                                                scale, p_blk, s_att, blk_seed, dt, st), 'attention_fwd')
             self._gemm(M, d, inner, w.o[l], inner, 1, wt[p + 'out.w'], inner, 1, EPI_BIAS_RES, w.y[l], d,
-                       aux=w.x[l], bias=pf[p + 'out.b'])
+                       aux=w.x[l], bias=pf[p + 'out.b'], drop=(p_blk, s_out))
             _lib.check(lib.ecgvit_layernorm_fwd(w.y[l].data_ptr(), pf[p + 'ln2.w'].data_ptr(), pf[p + 'ln2.b'].data_ptr(),
                                                 w.ln2[l].data_ptr(), w.stat2[l][0].data_ptr(), w.stat2[l][1].data_ptr(),
                                                 M, d, LN_EPS, dt, st), 'layernorm_fwd')
             self._gemm(M, mlp, d, w.ln2[l], d, 1, wt[p + 'ff1.w'], d, 1, EPI_BIAS_GELU, w.u[l], mlp,
-                       out2=w.h[l], bias=pf[p + 'ff1.b'])
+                       out2=w.h[l], bias=pf[p + 'ff1.b'], drop=(p_blk, s_act))
             self._gemm(M, d, mlp, w.h[l], mlp, 1, wt[p + 'ff2.w'], mlp, 1, EPI_BIAS_RES, w.x[l + 1], d,
-                       aux=w.y[l], bias=pf[p + 'ff2.b'])
+                       aux=w.y[l], bias=pf[p + 'ff2.b'], drop=(p_blk, s_ff2))
         red = _lib.REDUCTION[reduction]
         loss_buf = None
         if labels is not None:
@@ -184,37 +214,55 @@ class StepEngine:
         if zero_grads:
             m._flat_g.zero_()
         dz, dy = w.dres[0], w.dres[1]
+        p_emb, p_blk = w.p_emb, w.p_blk
+        seed_ptr = self.rng.data_ptr()
+        blk_seed = seed_ptr if p_blk > 0 else None
         last = f'l{depth - 1}.'
+        # with dropout between net[3] / to_out[0] and the residual add, the Linear sees mask * dz / (1 - p): its operand
+        # and its bias gradient come from the masked copy, so the producers must not pre-sum the unmasked gradient
         _lib.check(lib.ecgvit_head_bwd(
             w.x[depth].data_ptr(), pf['head.ln.w'].data_ptr(), pf['head.w'].data_ptr(), w.labels.data_ptr(),
             w.xn.data_ptr(), w.hstat[0].data_ptr(), w.hstat[1].data_ptr(), w.logits.data_ptr(), dz.data_ptr(),
             gr['head.w'].data_ptr(), gr['head.b'].data_ptr(), gr['head.ln.w'].data_ptr(), gr['head.ln.b'].data_ptr(),
-            gr[last + 'ff2.b'].data_ptr(), w.head_scratch.data_ptr(), B, N, d, m.num_class,
+            gr[last + 'ff2.b'].data_ptr() if p_blk == 0 else None, w.head_scratch.data_ptr(), B, N, d, m.num_class,
             _lib.REDUCTION[w.reduction], float(grad_scale), dt, st), 'head_bwd')
         scale = float(dh) ** -0.5
+
+        def masked(g, bias_grad, site):
+            """gradient w.r.t. the output of a Linear that is followed by dropout (identity when p = 0)"""
+            if p_blk == 0:
+                return g
+            _lib.check(lib.ecgvit_dropout_bwd_copy(g.data_ptr(), w.dzm.data_ptr(), bias_grad.data_ptr(), M, d, d, p_blk,
+                                                   site, seed_ptr, dt, st), 'dropout_bwd_copy')
+            return w.dzm
+
         for l in range(depth - 1, -1, -1):
             p = f'l{l}.'
-            # ---- feed-forward branch: x[l+1] = y + W2 gelu(W1 ln2(y) + b1) + b2
-            self._gemm(d, mlp, M, dz, d, 0, w.h[l], mlp, 0, EPI_ATOMIC_F32, gr[p + 'ff2.w'], mlp, split_k=0)
-            self._gemm(M, mlp, d, dz, d, 1, wt[p + 'ff2.w'], mlp, 0, EPI_DGELU, w.du, mlp, aux=w.u[l])
+            s_att, s_out, s_act, s_ff2 = 1 + 4 * l, 2 + 4 * l, 3 + 4 * l, 4 + 4 * l
+            # ---- feed-forward branch: x[l+1] = y + drop(W2 drop(gelu(W1 ln2(y) + b1)) + b2)
+            dzl = masked(dz, gr[p + 'ff2.b'], s_ff2)
+            self._gemm(d, mlp, M, dzl, d, 0, w.h[l], mlp, 0, EPI_ATOMIC_F32, gr[p + 'ff2.w'], mlp, split_k=0)
+            self._gemm(M, mlp, d, dzl, d, 1, wt[p + 'ff2.w'], mlp, 0, EPI_DGELU, w.du, mlp, aux=w.u[l],
+                       drop=(p_blk, s_act))
             _lib.check(lib.ecgvit_colsum(w.du.data_ptr(), gr[p + 'ff1.b'].data_ptr(), M, mlp, mlp, dt, st), 'colsum')
             self._gemm(mlp, d, M, w.du, mlp, 0, w.ln2[l], d, 0, EPI_ATOMIC_F32, gr[p + 'ff1.w'], d, split_k=0)
             self._gemm(M, d, mlp, w.du, mlp, 1, wt[p + 'ff1.w'], d, 0, EPI_STORE, w.dln, d)
             _lib.check(lib.ecgvit_layernorm_bwd(
                 w.dln.data_ptr(), w.y[l].data_ptr(), pf[p + 'ln2.w'].data_ptr(), w.stat2[l][0].data_ptr(),
                 w.stat2[l][1].data_ptr(), dz.data_ptr(), dy.data_ptr(), gr[p + 'ln2.w'].data_ptr(),
-                gr[p + 'ln2.b'].data_ptr(), gr[p + 'out.b'].data_ptr(), w.ln_scratch.data_ptr(), M, d, dt, st),
-                'layernorm_bwd')
-            # ---- attention branch: y = x + Wo attn(Wqkv ln1(x)) + bo
-            self._gemm(d, inner, M, dy, d, 0, w.o[l], inner, 0, EPI_ATOMIC_F32, gr[p + 'out.w'], inner, split_k=0)
-            self._gemm(M, inner, d, dy, d, 1, wt[p + 'out.w'], inner, 0, EPI_STORE, w.d_o, inner)
+                gr[p + 'ln2.b'].data_ptr(), gr[p + 'out.b'].data_ptr() if p_blk == 0 else None,
+                w.ln_scratch.data_ptr(), M, d, dt, st), 'layernorm_bwd')
+            # ---- attention branch: y = x + drop(Wo attn(Wqkv ln1(x)) + bo)
+            dyl = masked(dy, gr[p + 'out.b'], s_out)
+            self._gemm(d, inner, M, dyl, d, 0, w.o[l], inner, 0, EPI_ATOMIC_F32, gr[p + 'out.w'], inner, split_k=0)
+            self._gemm(M, inner, d, dyl, d, 1, wt[p + 'out.w'], inner, 0, EPI_STORE, w.d_o, inner)
             _lib.check(lib.ecgvit_attention_bwd(w.qkv[l].data_ptr(), w.o[l].data_ptr(), w.d_o.data_ptr(),
-                                                w.lse[l].data_ptr(), w.dqkv.data_ptr(), B, N, H, dh, scale, dt, st),
-                       'attention_bwd')
+                                                w.lse[l].data_ptr(), w.dqkv.data_ptr(), B, N, H, dh, scale, p_blk, s_att,
+                                                blk_seed, dt, st), 'attention_bwd')
             self._gemm(3 * inner, d, M, w.dqkv, 3 * inner, 0, w.ln1[l], d, 0, EPI_ATOMIC_F32, gr[p + 'qkv.w'], d,
                        split_k=0)
             self._gemm(M, d, 3 * inner, w.dqkv, 3 * inner, 1, wt[p + 'qkv.w'], d, 0, EPI_STORE, w.dln, d)
-            below_bias = gr[f'l{l - 1}.ff2.b'] if l > 0 else None
+            below_bias = gr[f'l{l - 1}.ff2.b'] if (l > 0 and p_blk == 0) else None
             _lib.check(lib.ecgvit_layernorm_bwd(
                 w.dln.data_ptr(), w.x[l].data_ptr(), pf[p + 'ln1.w'].data_ptr(), w.stat1[l][0].data_ptr(),
                 w.stat1[l][1].data_ptr(), dy.data_ptr(), dz.data_ptr(), gr[p + 'ln1.w'].data_ptr(),
@@ -224,8 +272,8 @@ class StepEngine:
                 m._after_layer_backward(l)
         # ---- embedding: tok = [cls | a_patch We^T + be] + pos
         _lib.check(lib.ecgvit_embed_assemble_bwd(dz.data_ptr(), w.de.data_ptr(), gr['cls'].data_ptr(),
-                                                 gr['pos'].data_ptr(), gr['embed.b'].data_ptr(), B, n, d, dt, st),
-                   'embed_assemble_bwd')
+                                                 gr['pos'].data_ptr(), gr['embed.b'].data_ptr(), B, n, d, p_emb, 0,
+                                                 seed_ptr if p_emb > 0 else None, dt, st), 'embed_assemble_bwd')
         self._gemm(d, P * C, B * n, w.de, d, 0, w.a_patch, P * C, 0, EPI_ATOMIC_F32, gr['embed.w'], P * C, split_k=0)
         if m._after_layer_backward is not None:
             m._after_layer_backward(-1)

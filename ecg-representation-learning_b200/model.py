@@ -178,12 +178,10 @@ class EcgVit(nn.Module):
     def forward(self, sample_values: torch.FloatTensor, labels: torch.LongTensor = None):
         if self.loss_weight:
             raise NotImplementedError('per-label loss_weight (ecg_vit.py:144-147) is not implemented in the fused head')
-        if self.training and (self.config.hidden_dropout_prob > 0 or self.config.attention_probs_dropout_prob > 0):
-            raise NotImplementedError(
-                'dropout > 0 in training mode is not implemented yet: construct the config with '
-                'hidden_dropout_prob=0, attention_probs_dropout_prob=0 or call .eval()')
         self._prepare(sample_values.device)
         need_grad = torch.is_grad_enabled() and labels is not None and any(p.requires_grad for p in self.parameters())
+        if self.training and (self.config.hidden_dropout_prob > 0 or self.config.attention_probs_dropout_prob > 0):
+            self._engine.new_dropout_seed()  # masks of this forward; its backward regenerates them from the same seed
         if need_grad:
             loss, logits = _EcgVitFunction.apply(self, sample_values, labels, *self._param_list())
         else:

@@ -82,6 +82,7 @@ class FusedTrainer:
         if self.world > 1:
             from .parallel import BucketedGradReducer
             self._reducer = BucketedGradReducer(m, self.group, self.bucket_layers)
+            m._engine.base_seed += 7919 * torch.distributed.get_rank(self.group)  # independent masks per replica
         self._state_ready = True
 
     def current_lr(self):
@@ -117,11 +118,11 @@ class FusedTrainer:
         """One optimisation step on device-resident fp32 inputs; returns (loss, logits) device tensors (no sync).
 
         The returned tensors are views of workspace buffers: valid until the next step."""
-        if self.model.training and (self.model.config.hidden_dropout_prob > 0 or
-                                    self.model.config.attention_probs_dropout_prob > 0):
-            raise NotImplementedError('dropout > 0 is not implemented in the fused step yet')
         self._ensure_state(sample_values.device)
         self._upload_hyper()
+        cfg = self.model.config
+        if self.model.training and (cfg.hidden_dropout_prob > 0 or cfg.attention_probs_dropout_prob > 0):
+            self.model._engine.new_dropout_seed()  # a device scalar: the captured graph reads the fresh value
         if self.use_cuda_graph:
             out = self._graph_step(sample_values, labels)
         else:

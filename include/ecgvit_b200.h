@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define ECGVIT_ABI_VERSION 1
+#define ECGVIT_ABI_VERSION 2
 
 enum { ECGVIT_F32 = 0, ECGVIT_BF16 = 1 };
 
@@ -56,10 +56,13 @@ int ecgvit_patchify(const float *x, void *a, int B, int C, int64_t x_ld, int n_p
 /* ---- CLS concat + positional add: replaces torch.cat(cls, x); x += pos_embedding[:, :n+1]
  *      tok[b,0,:] = cls + pos[0];  tok[b,1+w,:] = e[b*n_patch+w,:] + pos[1+w]  (e already holds the bias) */
 int ecgvit_embed_assemble(const void *e, const float *cls, const float *pos, void *tok, int B, int n_patch,
-                          int d, int dtype, void *stream);
-/* backward of the above: de = dtok[:,1:,:]; dpos += sum_b dtok; dcls += sum_b dtok[:,0]; dbias += sum_{b,w} dtok[:,1:] */
+                          int d, float dropout_p, int dropout_stream, const uint32_t *dropout_seed, int dtype,
+                          void *stream);
+/* backward of the above (g = dropout mask applied to dtok): de = g[:,1:,:]; dpos += sum_b g; dcls += sum_b g[:,0];
+ * dbias += sum_{b,w} g[:,1:] */
 int ecgvit_embed_assemble_bwd(const void *dtok, void *de, float *dcls, float *dpos, float *dbias, int B,
-                              int n_patch, int d, int dtype, void *stream);
+                              int n_patch, int d, float dropout_p, int dropout_stream,
+                              const uint32_t *dropout_seed, int dtype, void *stream);
 
 /* ---- nn.LayerNorm(d, eps) forward (PreNorm.norm / mlp_head[0]); saves per-row mean and rstd (fp32) */
 int ecgvit_layernorm_fwd(const void *x, const float *gamma, const float *beta, void *y, float *mean,
@@ -92,8 +95,12 @@ typedef struct ecgvit_gemm_args {
     const void *aux;    /* BIAS_RES: residual; DGELU: pre-activation (same ld as out) */
     const float *bias;  /* fp32 [N] or NULL */
     int dtype;
-    int split_k;        /* >1 only with ECGVIT_EPI_ATOMIC_F32 */
-    int reserved;
+    int split_k;        /* >1 only with ECGVIT_EPI_ATOMIC_F32; 0 = choose */
+    /* nn.Dropout fused into the epilogue (p = 0 or seed = NULL: off).  BIAS_RES: out = drop(acc + bias) + aux;
+     * BIAS_GELU: out2 = drop(gelu(out)); DGELU: out = drop(acc) * gelu'(aux).  See "dropout" below. */
+    int dropout_stream;
+    float dropout_p;
+    const uint32_t *dropout_seed;
 } ecgvit_gemm_args;
 int ecgvit_gemm(const ecgvit_gemm_args *g, void *stream);
 
@@ -101,9 +108,11 @@ int ecgvit_gemm(const ecgvit_gemm_args *g, void *stream);
  *      Softmax + attn v + rearrange back (vit_pytorch Attention.forward).
  *      qkv [B*N, 3*H*dh] (q | k | v, each head-major), o [B*N, H*dh], lse [B, H, N] fp32. */
 int ecgvit_attention_fwd(const void *qkv, void *o, float *lse, int B, int N, int H, int dh, float scale,
-                         int dtype, void *stream);
+                         float dropout_p, int dropout_stream, const uint32_t *dropout_seed, int dtype,
+                         void *stream);
 int ecgvit_attention_bwd(const void *qkv, const void *o, const void *d_o, const float *lse, void *dqkv,
-                         int B, int N, int H, int dh, float scale, int dtype, void *stream);
+                         int B, int N, int H, int dh, float scale, float dropout_p, int dropout_stream,
+                         const uint32_t *dropout_seed, int dtype, void *stream);
 
 /* ---- CLS pool + mlp_head (LayerNorm + Linear(d -> n_class)) + nn.BCEWithLogitsLoss (ecg_vit.py:118,148).
  *      tok [B*N, d]; logits fp32 [B, n_class]; loss: scalar (mean / sum) or [B, n_class] (none).
@@ -118,6 +127,17 @@ int ecgvit_head_bwd(const void *tok, const float *gamma, const float *w, const f
                     const float *mean, const float *rstd, const float *logits, void *dtok, float *dw,
                     float *db, float *dgamma, float *dbeta, float *dcolsum, float *scratch, int B, int N, int d,
                     int n_class, int reduction, float grad_scale, int dtype, void *stream);
+
+/* ---- dropout (nn.Dropout at the 5 sites per block + embedding of vit_pytorch; p wiring in ecg_vit.py:113-114).
+ *      Counter-based: element `idx` of site `dropout_stream` is kept iff the 16 bits that lowbias32(seed, stream,
+ *      idx >> 1) assigns to it are >= round(p * 65536); kept values are scaled by 1 / (1 - p).  `dropout_seed` points to
+ *      a DEVICE uint32 the host refreshes every step, so forward and backward regenerate the same mask and no mask is
+ *      stored.  Element indices: row * ld + col for [M, ld] tensors; ((b*H + h) * Np + query) * Np + key with
+ *      Np = N rounded up to 64 for attention probabilities.
+ *      Backward of a dropout that sits between a Linear and the residual add (to_out[1], net[4]):
+ *      dym = mask * dy / (1 - p) (operand of the Linear's dgrad / wgrad), dcolsum += colsum(dym) (its bias gradient). */
+int ecgvit_dropout_bwd_copy(const void *dy, void *dym, float *dcolsum, int M, int N, int64_t ld, float dropout_p,
+                            int dropout_stream, const uint32_t *dropout_seed, int dtype, void *stream);
 
 /* ---- column sum  out[n] += sum_m x[m, n]   (bias gradients) */
 int ecgvit_colsum(const void *x, float *out, int M, int N, int64_t ld, int dtype, void *stream);

@@ -43,7 +43,7 @@ for name, (m, n, k), ak, bk, epi in SHAPES:
         j = i % nbuf
         g = L.GemmArgs(m, n, k, A[j].data_ptr(), A[j].stride(0), ak, B[j].data_ptr(), B[j].stride(0), bk, epi,
                        out[j].data_ptr(), n, out2[j].data_ptr(), aux[j].data_ptr(),
-                       bias.data_ptr() if epi != L.EPI_ATOMIC_F32 else None, L.BF16, 0, 0)
+                       bias.data_ptr() if epi != L.EPI_ATOMIC_F32 else None, L.BF16, 0, 0, 0.0, None)
         L.check(lib.ecgvit_gemm(ctypes.byref(g), st), 'gemm')
 
     for i in range(3):

@@ -30,7 +30,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     for s in _declared_symbols():
         assert hasattr(raw, s), f'{s} declared in the header but not exported'
     assert set(_declared_symbols()) == set(ecg_b200._lib.SIGNATURES), 'ctypes table and header disagree'
-    assert lib.ecgvit_abi_version() == 1
+    assert lib.ecgvit_abi_version() == 2
 
 
 def test_gemm_args_struct_layout_matches_header():
@@ -38,7 +38,8 @@ def test_gemm_args_struct_layout_matches_header():
     g = ecg_b200._lib.GemmArgs
     # int M,N,K | ptr A | i64 lda | int a_kmajor | ptr B | i64 ldb | int b_kmajor, epilogue | ptr out | i64 ldo | 3 ptr | 3 int
     assert g.A.offset == 16 and g.lda.offset == 24 and g.B.offset == 40 and g.out.offset == 64
-    assert g.bias.offset == 96 and g.dtype.offset == 104 and ctypes.sizeof(g) == 120
+    assert g.bias.offset == 96 and g.dtype.offset == 104 and g.dropout_p.offset == 116
+    assert g.dropout_seed.offset == 120 and ctypes.sizeof(g) == 128
 
 
 def test_argument_validation_returns_error_without_touching_the_gpu():

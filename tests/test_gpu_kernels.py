@@ -33,7 +33,7 @@ def rel(a, b):
 
 def gemm(lib, A, B, M, N, K, a_k, b_k, epi, out, dtype, out2=None, aux=None, bias=None, split_k=1):
     g = L.GemmArgs(M, N, K, A.data_ptr(), A.stride(0), a_k, B.data_ptr(), B.stride(0), b_k, epi, out.data_ptr(),
-                   out.stride(0), L.ptr(out2), L.ptr(aux), L.ptr(bias), dtype, split_k, 0)
+                   out.stride(0), L.ptr(out2), L.ptr(aux), L.ptr(bias), dtype, split_k, 0, 0.0, None)
     L.check(lib.ecgvit_gemm(ctypes.byref(g), stream()), 'gemm')
 
 
@@ -189,8 +189,8 @@ def test_attention_fwd_bwd(lib, dtype, cfg):
     scale = dh ** -0.5
     o = torch.empty(B * N, inner, device='cuda', dtype=td)
     lse = torch.empty(B, H, N, device='cuda')
-    L.check(lib.ecgvit_attention_fwd(qkv.data_ptr(), o.data_ptr(), lse.data_ptr(), B, N, H, dh, scale, dtype, stream()),
-            'attn')
+    L.check(lib.ecgvit_attention_fwd(qkv.data_ptr(), o.data_ptr(), lse.data_ptr(), B, N, H, dh, scale, 0.0, 0, None, dtype,
+                                     stream()), 'attn')
     ref_in = qkv.float().requires_grad_(True)
     q, k, v = (t.reshape(B, N, H, dh).permute(0, 2, 1, 3) for t in ref_in.chunk(3, dim=-1))
     s = (q @ k.transpose(-1, -2)) * scale
@@ -201,7 +201,7 @@ def test_attention_fwd_bwd(lib, dtype, cfg):
     want.backward(d_o.float())
     dqkv = torch.empty_like(qkv)
     L.check(lib.ecgvit_attention_bwd(qkv.data_ptr(), o.data_ptr(), d_o.data_ptr(), lse.data_ptr(), dqkv.data_ptr(), B, N,
-                                     H, dh, scale, dtype, stream()), 'attn_bwd')
+                                     H, dh, scale, 0.0, 0, None, dtype, stream()), 'attn_bwd')
     assert rel(dqkv, ref_in.grad) < (1e-5 if dtype == L.F32 else 1.5e-2)
 
 
@@ -255,15 +255,15 @@ def test_embed_assemble_and_colsum(lib, dtype):
     e = torch.randn(B * n, d, device='cuda').to(td)
     cls, pos = torch.randn(d, device='cuda'), torch.randn(n + 1, d, device='cuda')
     tok = torch.empty(B * (n + 1), d, device='cuda', dtype=td)
-    L.check(lib.ecgvit_embed_assemble(e.data_ptr(), cls.data_ptr(), pos.data_ptr(), tok.data_ptr(), B, n, d, dtype,
-                                      stream()), 'assemble')
+    L.check(lib.ecgvit_embed_assemble(e.data_ptr(), cls.data_ptr(), pos.data_ptr(), tok.data_ptr(), B, n, d, 0.0, 0, None,
+                                      dtype, stream()), 'assemble')
     want = torch.cat([cls.expand(B, 1, d), e.float().reshape(B, n, d)], 1) + pos
     assert rel(tok, want.reshape(-1, d)) < (1e-7 if dtype == L.F32 else 4e-3)
     dtok = torch.randn(B * (n + 1), d, device='cuda').to(td)
     de = torch.empty(B * n, d, device='cuda', dtype=td)
     dcls, dpos, dbias = torch.zeros(d, device='cuda'), torch.zeros(n + 1, d, device='cuda'), torch.zeros(d, device='cuda')
     L.check(lib.ecgvit_embed_assemble_bwd(dtok.data_ptr(), de.data_ptr(), dcls.data_ptr(), dpos.data_ptr(),
-                                          dbias.data_ptr(), B, n, d, dtype, stream()), 'assemble_bwd')
+                                          dbias.data_ptr(), B, n, d, 0.0, 0, None, dtype, stream()), 'assemble_bwd')
     g = dtok.float().reshape(B, n + 1, d)
     assert torch.equal(de.reshape(B, n, d), dtok.reshape(B, n + 1, d)[:, 1:])
     assert rel(dpos, g.sum(0)) < 1e-6 and rel(dcls, g[:, 0].sum(0)) < 1e-6 and rel(dbias, g[:, 1:].sum((0, 1))) < 1e-5

@@ -69,12 +69,24 @@ def test_cpu_forward_fails_loudly():
         m.vit(torch.zeros(1, 12, 1, 500))  # the parameter containers have no eager forward
 
 
-def test_loss_reduction_property_and_dropout_guard():
+def test_loss_reduction_property():
     m = EcgVit(config=EcgVitConfig(**dict(GOLDEN_CFG, hidden_dropout_prob=0.1)))
     m.loss_reduction = 'none'
     assert m.loss_reduction == 'none'
-    with pytest.raises(NotImplementedError):
-        m.train()(torch.zeros(1, 12, 500))
+
+
+def test_dropout_mask_replica_statistics():
+    """host replica of the kernels' counter-based dropout: keep rate, scale, determinism, stream independence"""
+    idx = torch.arange(0, 200000)
+    a = ecg_b200._lib.dropout_keep_mask(1234, 7, 0.1, idx)
+    b = ecg_b200._lib.dropout_keep_mask(1234, 7, 0.1, idx)
+    c = ecg_b200._lib.dropout_keep_mask(1234, 8, 0.1, idx)
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    keep = float((a > 0).float().mean())
+    assert abs(keep - 0.9) < 5e-3
+    assert abs(float(a.max()) - 1.0 / (1.0 - 6554 / 65536)) < 1e-6
+    assert abs(float(a.mean()) - 1.0) < 1e-2  # unbiased
+    assert torch.equal(ecg_b200._lib.dropout_keep_mask(1, 0, 0.0, idx[:10]), torch.ones(10))
 
 
 def test_lr_multiplier_matches_oracle_schedule():
