@@ -30,8 +30,8 @@ sys.path.insert(0, ROOT)
 METRIC = 'ecg_vit_base_bf16_train_samples_per_s'
 UNIT = 'samples/s'
 BASE_CFG = dict(max_signal_length=2500, patch_size=50, num_channels=12, hidden_size=768, num_hidden_layers=12,
-                num_attention_heads=12, intermediate_size=3072, hidden_dropout_prob=0.0,
-                attention_probs_dropout_prob=0.0)
+                num_attention_heads=12, intermediate_size=3072, hidden_dropout_prob=0.1,
+                attention_probs_dropout_prob=0.1)  # dropout 0.1 = the reference's default (ecg_vit.py:38-39)
 NUM_CLASS = 71
 
 
@@ -187,7 +187,7 @@ def run_reference_arm(args):
         'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': 'ECG-ViT base (d=768, 12 layers, 12 heads, patch 50) pre-training step, 12x2500',
-                   'batch_per_step': batch, 'device': 'cpu'},
+                   'batch_per_step': batch, 'device': 'cpu', 'dropout': args.dropout},
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
@@ -205,8 +205,10 @@ def main():
     ap.add_argument('--ref-batch', type=int, default=16, help='bounded CPU batch of the reference arm')
     ap.add_argument('--no-graph', action='store_true', help='launch kernels from Python instead of one CUDA graph')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--dropout', type=float, default=0.1, help='hidden / attention-probs dropout (reference default 0.1)')
     ap.add_argument('--profile-json', default=None, help='write the per-kernel event breakdown here')
     args = ap.parse_args()
+    BASE_CFG['hidden_dropout_prob'] = BASE_CFG['attention_probs_dropout_prob'] = args.dropout
     if args.impl == 'reference':
         return run_reference_arm(args)
     args.warmup = max(args.warmup, 3)
@@ -367,7 +369,8 @@ def main():
             'dtype': 'bf16', 'data': 'synthetic',
             'config': {'workload': 'ECG-ViT base (d=768, 12 layers, 12 heads, patch 50) bf16 pre-training step, '
                                    'batch 256 per GPU, 12x2500 signals (BASELINE.json configs[1]; configs[2] at N=8)',
-                       'global_batch': world * B, 'per_gpu_batch': B, 'dropout': 0.0, 'parallelism': f'dp{world}',
+                       'global_batch': world * B, 'per_gpu_batch': B, 'dropout': args.dropout,
+                       'parallelism': f'dp{world}',
                        'l2': 'per-step working set (~4 GB of activations + 1.9 GB of optimizer traffic) exceeds the '
                              '126 MB L2, no explicit flush',
                        'cuda_graph': use_graph, 'optimizer': 'AdamW lr 3e-4 wd 1e-2, clip_grad_norm 1.0'},
