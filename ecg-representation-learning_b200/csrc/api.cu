@@ -1,6 +1,8 @@
 // C-ABI plumbing: error string, device query, GEMM front door.
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace ecgvit {
 
 char *last_error_buffer() {
@@ -17,6 +19,15 @@ int sm_count() {
         if (n <= 0) n = 148;
     }
     return n;
+}
+
+bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("ECGVIT_PDL");
+        v = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
 }
 
 int gemm_bf16_tc(const ecgvit_gemm_args *g, cudaStream_t stream);   // gemm_tc.cu

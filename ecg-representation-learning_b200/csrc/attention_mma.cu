@@ -140,6 +140,8 @@ __global__ void __launch_bounds__(128) attention_fwd_mma_kernel(const bf16 *__re
     __shared__ __align__(16) bf16 sQ[NMAX][DH + 8];
     __shared__ __align__(16) bf16 sK[NMAX][DH + 8];
     __shared__ __align__(16) bf16 sV[NMAX][DH + 8];
+    pdl_launch_dependents();
+    pdl_wait();
     const int h = blockIdx.x % H, b = blockIdx.x / H;
     const int inner = H * DH;
     const int ld = 3 * inner;
@@ -230,6 +232,8 @@ __global__ void __launch_bounds__(128) attention_bwd_mma_kernel(const bf16 *__re
     TileN sdS = sP + NMAX;
 
     float *sD = reinterpret_cast<float *>(sdS + NMAX);  // [NMAX] rowsum(dO * O)
+    pdl_launch_dependents();
+    pdl_wait();
 
     const int h = blockIdx.x % H, b = blockIdx.x / H;
     const int inner = H * DH;
@@ -359,15 +363,16 @@ int launch_bwd(const void *qkv, const void *o, const void *d_o, const float *lse
         if (e != cudaSuccess) return fail((int)e, "attention_bwd_mma: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         attr_set = true;
     }
-    attention_bwd_mma_kernel<DH, NT><<<B * H, 128, bwd_smem_bytes<DH>(), stream>>>(
-        (const bf16 *)qkv, (const bf16 *)o, (const bf16 *)d_o, lse, (bf16 *)dqkv, N, H, scale, drop);
+    launch_pdl(attention_bwd_mma_kernel<DH, NT>, dim3(B * H), dim3(128), bwd_smem_bytes<DH>(), stream,
+               (const bf16 *)qkv, (const bf16 *)o, (const bf16 *)d_o, lse, (bf16 *)dqkv, N, H, scale, drop);
     return check_launch("attention_bwd_mma");
 }
 
 template <int DH, int NT>
 int launch_fwd(const void *qkv, void *o, float *lse, int B, int N, int H, float scale, DropoutParams drop,
                cudaStream_t stream) {
-    attention_fwd_mma_kernel<DH, NT><<<B * H, 128, 0, stream>>>((const bf16 *)qkv, (bf16 *)o, lse, N, H, scale, drop);
+    launch_pdl(attention_fwd_mma_kernel<DH, NT>, dim3(B * H), dim3(128), 0, stream, (const bf16 *)qkv, (bf16 *)o, lse, N,
+               H, scale, drop);
     return check_launch("attention_fwd_mma");
 }
 

@@ -34,6 +34,34 @@ inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s
 
 int sm_count();  // cached multiprocessor count of the current device (api.cu)
 
+// ---- programmatic dependent launch --------------------------------------------------------------------
+// The per-layer kernels are launched with programmaticStreamSerialization: kernel N+1 may be scheduled while kernel
+// N drains its last wave, runs its prologue (barrier init, TMEM alloc, tensormap prefetch, smem setup) and then
+// blocks in pdl_wait() until kernel N has completed and flushed.  Every such kernel calls pdl_launch_dependents()
+// first thing (the dependent launch fires once ALL CTAs of the grid have done so, i.e. when the last wave is
+// resident) and pdl_wait() before its first access to global memory.  ECGVIT_PDL=0 disables the attribute.
+bool pdl_enabled();  // api.cu
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 // ---- element type helpers -------------------------------------------------------------------------
 typedef __nv_bfloat16 bf16;
 

@@ -140,6 +140,8 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const T *__restrict_
                                                              const float *__restrict__ beta, T *__restrict__ y,
                                                              float *__restrict__ mean_out, float *__restrict__ rstd_out,
                                                              int M, int d, float eps) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;
     const float inv_d = 1.0f / (float)d;
@@ -207,6 +209,8 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const T *__restri
                                                                 float *__restrict__ dcolsum, float *__restrict__ partial,
                                                                 int M, int d) {
     extern __shared__ float red[];  // [warps][3][d] column partials, then [d] gamma
+    pdl_launch_dependents();
+    pdl_wait();
     float *sgamma = red + (blockDim.x >> 5) * 3 * d;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -314,6 +318,8 @@ __global__ void __launch_bounds__(256) layernorm_bwd_finalize_kernel(const float
                                                                       float *__restrict__ dbeta,
                                                                       float *__restrict__ dcolsum, int d) {
     __shared__ float red[8][33];
+    pdl_launch_dependents();
+    pdl_wait();
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int i = blockIdx.x * 32 + tx;
     float t = 0.f;
@@ -340,6 +346,8 @@ __global__ void __launch_bounds__(256) dropout_bwd_copy_kernel(const T *__restri
                                                                 float *__restrict__ dcolsum, int M, int N, int64_t ld,
                                                                 int rows_per_block, DropoutParams drop) {
     __shared__ float red[8][32 * 8 + 1];
+    pdl_launch_dependents();
+    pdl_wait();
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int c = (blockIdx.x * 32 + tx) * 8;
     const int r0 = blockIdx.y * rows_per_block;
@@ -376,6 +384,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(const T *__restrict__ x, float *__restrict__ out, int M, int N,
                                                       int64_t ld, int rows_per_block) {
     __shared__ float red[8][32 * 8 + 1];
+    pdl_launch_dependents();
+    pdl_wait();
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int c = (blockIdx.x * 32 + tx) * 8;
     const int r0 = blockIdx.y * rows_per_block;
@@ -482,7 +492,8 @@ int ecgvit_layernorm_fwd(const void *x, const float *gamma, const float *beta, v
     const int nv = (d + 255) / 256;
     cudaStream_t st = as_stream(stream);
 #define ECGVIT_LN_FWD(TT, NVV)                                                                                     \
-    layernorm_fwd_kernel<TT, NVV><<<grid, 256, 0, st>>>((const TT *)x, gamma, beta, (TT *)y, mean, rstd, M, d, eps)
+    launch_pdl(layernorm_fwd_kernel<TT, NVV>, dim3(grid), dim3(256), 0, st, (const TT *)x, gamma, beta, (TT *)y, mean,  \
+               rstd, M, d, eps)
     if (dtype == ECGVIT_BF16) {
         switch (nv) {
             case 1: ECGVIT_LN_FWD(bf16, 1); break;
@@ -523,9 +534,8 @@ int ecgvit_layernorm_bwd(const void *dy, const void *x, const float *gamma, cons
             cudaFuncSetAttribute(layernorm_bwd_kernel<TT, NVV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 25 * 1024 * 4); \
             attr_set = true;                                                                                           \
         }                                                                                                              \
-        layernorm_bwd_kernel<TT, NVV><<<grid, 256, smem, st>>>((const TT *)dy, (const TT *)x, gamma, mean, rstd,      \
-                                                               (const TT *)dres, (TT *)dx, dgamma, dbeta, dcolsum,     \
-                                                               scratch, M, d);                                         \
+        launch_pdl(layernorm_bwd_kernel<TT, NVV>, dim3(grid), dim3(256), smem, st, (const TT *)dy, (const TT *)x,     \
+                   gamma, mean, rstd, (const TT *)dres, (TT *)dx, dgamma, dbeta, dcolsum, scratch, M, d);              \
     } while (0)
     if (dtype == ECGVIT_BF16) {
         switch (nv) {
@@ -545,7 +555,8 @@ int ecgvit_layernorm_bwd(const void *dy, const void *x, const float *gamma, cons
 #undef ECGVIT_LN_BWD
     int rc = check_launch("layernorm_bwd");
     if (rc) return rc;
-    layernorm_bwd_finalize_kernel<<<(3 * d + 31) / 32, 256, 0, st>>>(scratch, grid, dgamma, dbeta, dcolsum, d);
+    launch_pdl(layernorm_bwd_finalize_kernel, dim3((3 * d + 31) / 32), dim3(256), 0, st, (const float *)scratch, grid,
+               dgamma, dbeta, dcolsum, d);
     return check_launch("layernorm_bwd_finalize");
 }
 
@@ -559,7 +570,7 @@ int ecgvit_colsum(const void *x, float *out, int M, int N, int64_t ld, int dtype
     const int rows_per_block = (M + row_blocks - 1) / row_blocks;
     dim3 grid(col_blocks, (M + rows_per_block - 1) / rows_per_block);
     if (dtype == ECGVIT_BF16)
-        colsum_kernel<bf16><<<grid, 256, 0, as_stream(stream)>>>((const bf16 *)x, out, M, N, ld, rows_per_block);
+        launch_pdl(colsum_kernel<bf16>, grid, dim3(256), 0, as_stream(stream), (const bf16 *)x, out, M, N, ld, rows_per_block);
     else if (dtype == ECGVIT_F32)
         colsum_kernel<float><<<grid, 256, 0, as_stream(stream)>>>((const float *)x, out, M, N, ld, rows_per_block);
     else return fail(-1, "colsum: unknown dtype %d", dtype);
@@ -579,7 +590,7 @@ int ecgvit_dropout_bwd_copy(const void *dy, void *dym, float *dcolsum, int M, in
     const int rows_per_block = (M + row_blocks - 1) / row_blocks;
     dim3 grid(col_blocks, (M + rows_per_block - 1) / rows_per_block);
     if (dtype == ECGVIT_BF16)
-        dropout_bwd_copy_kernel<bf16><<<grid, 256, 0, as_stream(stream)>>>((const bf16 *)dy, (bf16 *)dym, dcolsum, M, N, ld, rows_per_block, drop);
+        launch_pdl(dropout_bwd_copy_kernel<bf16>, grid, dim3(256), 0, as_stream(stream), (const bf16 *)dy, (bf16 *)dym, dcolsum, M, N, ld, rows_per_block, drop);
     else if (dtype == ECGVIT_F32)
         dropout_bwd_copy_kernel<float><<<grid, 256, 0, as_stream(stream)>>>((const float *)dy, (float *)dym, dcolsum, M, N, ld, rows_per_block, drop);
     else return fail(-1, "dropout_bwd_copy: unknown dtype %d", dtype);

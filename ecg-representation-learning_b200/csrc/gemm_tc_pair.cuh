@@ -121,6 +121,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     uint64_t *aux_bar = tmem_empty_bar + 2;  // [epilogue warp][unit]
     uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(aux_bar + kNumEpilogueWarps * Cfg::EPI_TILES_PER_WARP);
 
+    pdl_launch_dependents();
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const uint32_t rank = ptx::cluster_ctarank();
@@ -152,6 +153,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     ptx::cluster_sync_all();
     ptx::tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    pdl_wait();  // everything above overlapped the previous kernel's tail; from here on global memory is touched
 
     const int tiles_m = (M + BM2 - 1) / BM2;
     const int tiles_n = (N + BN - 1) / BN;
