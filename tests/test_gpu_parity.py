@@ -149,6 +149,31 @@ def test_bf16_parity_with_oracle(cfg, batch):
     assert worst[0] >= BF16_GRAD_COS, worst
 
 
+@pytest.mark.parametrize('size,batch', [('debug', 6), ('tiny', 4), ('small', 3), ('large', 2)])
+def test_named_sizes_reference_geometry(size, batch):
+    """the reference's own named sizes at its default geometry (12 x 2560, patch 64 -> 41 tokens; ecg_vit.py:31-32,56-92);
+    'large' is BASELINE.json configs[4]'s model (d=1024, 24 layers, 16 heads)"""
+    torch.manual_seed(1)
+    oc = OracleConfig.from_defined(f'ecg-vit-{size}')
+    oc.hidden_dropout_prob = oc.attention_probs_dropout_prob = 0.0
+    oracle = OracleEcgVit(config=oc).train()
+    conf = EcgVitConfig.from_defined(f'ecg-vit-{size}')
+    conf.hidden_dropout_prob = conf.attention_probs_dropout_prob = 0.0
+    model = EcgVit(config=conf)
+    assert model.to_str() == f'EcgVit, {size}'
+    model.load_state_dict(oracle.state_dict(), strict=True)
+    model.cuda().train()
+    x, y = synthetic_batch(batch, length=2560, seed=21)
+    o = oracle(sample_values=x, labels=y)
+    o.loss.backward()
+    out = model(sample_values=x.cuda(), labels=y.cuda())
+    out.loss.backward()
+    assert rel(out.logits, o.logits) < BF16_TOL, rel(out.logits, o.logits)
+    assert rel(out.loss, o.loss) < BF16_TOL
+    worst = min((cosine(p.grad, q.grad), k) for (k, p), (_, q) in zip(model.named_parameters(), oracle.named_parameters()))
+    assert worst[0] >= BF16_GRAD_COS, worst
+
+
 def test_bf16_three_steps_track_the_oracle():
     oracle, model, x, y = make_pair(CFG1, 'bf16', 16)
     ot, tr = OracleTrainer(oracle), FusedTrainer(model)
