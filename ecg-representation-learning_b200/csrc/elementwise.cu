@@ -53,32 +53,43 @@ __global__ void embed_assemble_kernel(const T *__restrict__ e, const float *__re
     }
 }
 
-// backward: one CTA column-slab per token position j; each thread owns one column and walks the batch.
+// backward: grid (token position j, 32-column slab), block = 32 columns x 8 batch groups; the masked gradient rows are
+// copied to `de` on the way and the batch sums are folded through shared memory
 template <typename T>
-__global__ void embed_assemble_bwd_kernel(const T *__restrict__ dtok, T *__restrict__ de, float *__restrict__ dcls,
-                                          float *__restrict__ dpos, float *__restrict__ dbias, int B, int n_patch,
-                                          int d, DropoutParams drop) {
+__global__ void __launch_bounds__(256) embed_assemble_bwd_kernel(const T *__restrict__ dtok, T *__restrict__ de,
+                                                                  float *__restrict__ dcls, float *__restrict__ dpos,
+                                                                  float *__restrict__ dbias, int B, int n_patch, int d,
+                                                                  DropoutParams drop) {
+    __shared__ float red[8][33];
     const int N = n_patch + 1;
     const int j = blockIdx.x;
-    const int col = blockIdx.y * blockDim.x + threadIdx.x;
-    if (col >= d) return;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int col = blockIdx.y * 32 + tx;
     const bool dropping = drop.threshold != 0;
     const uint32_t seed = dropping ? __ldg(drop.seed) : 0u;
     float s = 0.f;
-    for (int b = 0; b < B; ++b) {
-        const int64_t idx = ((int64_t)b * N + j) * d + col;
-        float gf = to_f32(dtok[idx]);
-        if (dropping) gf *= dropout_one(drop, seed, static_cast<uint32_t>(idx));
-        const T g = from_f32<T>(gf);
-        s += to_f32(g);
-        if (j > 0) de[((int64_t)b * n_patch + (j - 1)) * d + col] = g;
+    if (col < d) {
+        for (int b = ty; b < B; b += 8) {
+            const int64_t idx = ((int64_t)b * N + j) * d + col;
+            float gf = to_f32(dtok[idx]);
+            if (dropping) gf *= dropout_one(drop, seed, static_cast<uint32_t>(idx));
+            const T g = from_f32<T>(gf);
+            s += to_f32(g);
+            if (j > 0) de[((int64_t)b * n_patch + (j - 1)) * d + col] = g;
+        }
     }
-    dpos[(int64_t)j * d + col] += s;
-    if (j == 0) dcls[col] += s;
-    else atomicAdd(dbias + col, s);
+    red[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0 && col < d) {
+        float t = 0.f;
+#pragma unroll
+        for (int y = 0; y < 8; ++y) t += red[y][tx];
+        dpos[(int64_t)j * d + col] += t;
+        if (j == 0) dcls[col] += t;
+        else atomicAdd(dbias + col, t);
+    }
 }
 
-// ---------------------------------------------------------------------------------------------------
 constexpr int LN_MAXV = 4;  // 4 x 8 elements per lane
 
 // LayerNorm backward (+ residual-gradient add, + column sums of the result for the bias gradient upstream).
@@ -474,11 +485,11 @@ int ecgvit_embed_assemble_bwd(const void *dtok, void *de, float *dcls, float *dp
                               int dtype, void *stream) {
     const DropoutParams drop = make_dropout(dropout_p, dropout_stream, dropout_seed);
     ECGVIT_REQUIRE(dtok && de && dcls && dpos && dbias && B > 0 && n_patch > 0 && d > 0, "embed_assemble_bwd: bad arguments");
-    dim3 grid(n_patch + 1, (d + 127) / 128);
+    dim3 grid(n_patch + 1, (d + 31) / 32);
     if (dtype == ECGVIT_BF16)
-        embed_assemble_bwd_kernel<bf16><<<grid, 128, 0, as_stream(stream)>>>((const bf16 *)dtok, (bf16 *)de, dcls, dpos, dbias, B, n_patch, d, drop);
+        embed_assemble_bwd_kernel<bf16><<<grid, 256, 0, as_stream(stream)>>>((const bf16 *)dtok, (bf16 *)de, dcls, dpos, dbias, B, n_patch, d, drop);
     else if (dtype == ECGVIT_F32)
-        embed_assemble_bwd_kernel<float><<<grid, 128, 0, as_stream(stream)>>>((const float *)dtok, (float *)de, dcls, dpos, dbias, B, n_patch, d, drop);
+        embed_assemble_bwd_kernel<float><<<grid, 256, 0, as_stream(stream)>>>((const float *)dtok, (float *)de, dcls, dpos, dbias, B, n_patch, d, drop);
     else return fail(-1, "embed_assemble_bwd: unknown dtype %d", dtype);
     return check_launch("embed_assemble_bwd");
 }

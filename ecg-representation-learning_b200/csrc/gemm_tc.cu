@@ -311,7 +311,7 @@ int launch_pair(const ecgvit_gemm_args *g, int split_k, cudaStream_t stream) {
     const int clusters = sm_count() / 2;
     const int grid = 2 * (units < clusters ? units : clusters);
     EpiParams ep{g->out, g->out2, g->aux, g->bias, g->ldo, make_dropout(g->dropout_p, g->dropout_stream, g->dropout_seed)};
-    cudaError_t le = launch_pdl(kern, dim3(grid), dim3(kNumThreads), Cfg::SMEM_BYTES, stream, ta, tb, to, to2, tx, g->M,
+    cudaError_t le = launch_pdl(kern, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, ta, tb, to, to2, tx, g->M,
                                 g->N, g->K, split_k, ep);
     if (le != cudaSuccess) return fail((int)le, "gemm_tc2 launch: %s", cudaGetErrorString(le));
     return check_launch("gemm_tc2");

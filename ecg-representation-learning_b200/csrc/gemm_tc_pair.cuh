@@ -20,18 +20,23 @@ template <int BN, bool B_MN> struct PairCfg {
     static constexpr int B_LOAD_ROWS = B_MN ? ((B_HALF + 63) / 64) * 64 : B_HALF;
     static constexpr int B_STAGE_BYTES = B_LOAD_ROWS * BK * 2;
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;          // per CTA
-    // epilogue staging: every epilogue warp owns four 32-row x 64-byte (32 bf16, SWIZZLE_64B) tiles
+    // epilogue: one warp per (TMEM lane quadrant, 64-column group) -> BN / 16 warps, 2 units of 32 columns each.
+    // More, narrower epilogue warps (16 at BN = 256) keep the 4 issue slots of the SM busy: the GELU / dropout
+    // epilogues are instruction bound and two warps per scheduler cannot hide their own latencies.
+    static constexpr int EPI_WARPS = BN / 16;
+    static constexpr int THREADS = 128 + 32 * EPI_WARPS;
+    static constexpr int UNITS_PER_WARP = 2;                                   // 32-column units per epilogue warp
+    // staging: every epilogue warp owns two 32-row x 64-byte (32 bf16, SWIZZLE_64B) tiles
     static constexpr int EPI_TILE_BYTES = 32 * 64;
-    static constexpr int EPI_TILES_PER_WARP = 4;
-    static constexpr int EPI_BYTES = kNumEpilogueWarps * EPI_TILES_PER_WARP * EPI_TILE_BYTES;  // 64 KB
-    static constexpr int NUM_BARRIERS = 2 * 8 + 4 + kNumEpilogueWarps * EPI_TILES_PER_WARP;
+    static constexpr int EPI_TILES_PER_WARP = 2;
+    static constexpr int EPI_BYTES = EPI_WARPS * EPI_TILES_PER_WARP * EPI_TILE_BYTES;
+    static constexpr int NUM_BARRIERS = 2 * 8 + 4 + EPI_WARPS * EPI_TILES_PER_WARP;
     static constexpr int PIPE_BUDGET = 232448 - 1024 - 1024 - EPI_BYTES;
     static constexpr int STAGES = (PIPE_BUDGET / STAGE_BYTES) > 8 ? 8 : (PIPE_BUDGET / STAGE_BYTES);
     static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
-    static constexpr int UNITS_PER_WARP = B_HALF / 32;                         // 32-column units per epilogue warp
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 + 1024;
     static_assert(NUM_BARRIERS * 8 + 16 <= 1024, "barrier block");
-    static_assert(B_HALF % 32 == 0 && UNITS_PER_WARP <= EPI_TILES_PER_WARP, "tile width");
+    static_assert(BN % 64 == 0, "tile width");
 };
 
 // byte offset of 16-byte chunk j (0..3) of row `lane` inside a 32 x 64-byte SWIZZLE_64B tile
@@ -45,16 +50,17 @@ __device__ __forceinline__ uint32_t sw64_offset(int lane, int j) {
 // The caller then issues one TMA store per tile (TMA clips rows >= M and columns >= N, so there are no guards here
 // except for the bias vector).
 template <int MODE>
-__device__ __forceinline__ void epilogue_unit32(const EpiParams &ep, int64_t row, int col_base, int N,
-                                                const uint32_t r[32], uint8_t *tile0, uint8_t *tile1, int lane) {
+__device__ __forceinline__ void epilogue_half16(const EpiParams &ep, int64_t row, int col_base, int N, int jbase,
+                                                const uint32_t r[16], uint8_t *tile0, uint8_t *tile1, int lane) {
     const bool drop = ep.drop.threshold != 0;  // kernel-uniform
     const uint32_t seed = drop ? __ldg(ep.drop.seed) : 0u;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int jj = 0; jj < 2; ++jj) {
+        const int j = jbase + jj;  // 16-byte chunk of the 32-column tile
         const int col = col_base + 8 * j;
         float v[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[8 * j + i]);
+        for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[8 * jj + i]);
         if (MODE != ECGVIT_EPI_DGELU && ep.bias != nullptr && col < N) {  // N % 8 == 0
             const float4 b0 = __ldg(reinterpret_cast<const float4 *>(ep.bias + col));
             const float4 b1 = __ldg(reinterpret_cast<const float4 *>(ep.bias + col + 4));
@@ -102,7 +108,7 @@ __device__ __forceinline__ void epilogue_unit32(const EpiParams &ep, int64_t row
 }
 
 template <int BN, bool A_MN, bool B_MN, int MODE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairCfg<BN, B_MN>::THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                 const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_out2,
                 const __grid_constant__ CUtensorMap tmap_aux, int M, int N, int K, int split_k, EpiParams ep) {
@@ -119,7 +125,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     uint64_t *tmem_full_bar = empty_bar + STAGES;
     uint64_t *tmem_empty_bar = tmem_full_bar + 2;
     uint64_t *aux_bar = tmem_empty_bar + 2;  // [epilogue warp][unit]
-    uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(aux_bar + kNumEpilogueWarps * Cfg::EPI_TILES_PER_WARP);
+    uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(aux_bar + Cfg::EPI_WARPS * Cfg::EPI_TILES_PER_WARP);
 
     pdl_launch_dependents();
     const int warp = threadIdx.x >> 5;
@@ -143,9 +149,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         }
         for (int a = 0; a < 2; ++a) {
             ptx::mbar_init(&tmem_full_bar[a], 1);
-            ptx::mbar_init(&tmem_empty_bar[a], 2 * kNumEpilogueWarps);
+            ptx::mbar_init(&tmem_empty_bar[a], 2 * Cfg::EPI_WARPS);
         }
-        for (int i = 0; i < kNumEpilogueWarps * Cfg::EPI_TILES_PER_WARP; ++i) ptx::mbar_init(&aux_bar[i], 1);
+        for (int i = 0; i < Cfg::EPI_WARPS * Cfg::EPI_TILES_PER_WARP; ++i) ptx::mbar_init(&aux_bar[i], 1);
         ptx::fence_mbar_init();
     }
     if (warp == 2) ptx::tmem_alloc_2sm(tmem_ptr_smem, Cfg::TMEM_COLS);
@@ -234,8 +240,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         }
     } else if (warp >= 4) {
         // ================================ epilogue (both CTAs, own 128 rows) ======================
-        const int q = warp & 3;
-        const int half = (warp - 4) >> 2;
+        const int q = warp & 3;              // TMEM lane quadrant this warp may access
+        const int group = (warp - 4) >> 2;   // 64-column group of the tile
         constexpr int UNITS = Cfg::UNITS_PER_WARP;
         uint8_t *tiles = epi_smem + (warp - 4) * Cfg::EPI_TILES_PER_WARP * Cfg::EPI_TILE_BYTES;
         uint64_t *my_aux_bar = aux_bar + (warp - 4) * Cfg::EPI_TILES_PER_WARP;
@@ -246,7 +252,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             const int row_base = tile_m * BM2 + rank * BM + q * 32;
-            const int col_warp = tile_n * BN + half * Cfg::B_HALF;  // first column of this warp's units
+            const int col_warp = tile_n * BN + group * 64;  // first column of this warp's two units
             if (MODE != ECGVIT_EPI_ATOMIC_F32) {
                 // staging tiles are reused every tile: the previous tile's TMA stores must have read them
                 if (lane == 0) {
@@ -267,18 +273,18 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             }
             ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
             ptx::tcgen05_fence_after();
-            const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + half * Cfg::B_HALF;
+            const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + group * 64;
+            const int64_t row = static_cast<int64_t>(row_base) + lane;
             if (MODE == ECGVIT_EPI_ATOMIC_F32) {
-                const int64_t row = static_cast<int64_t>(row_base) + lane;
 #pragma unroll 1
-                for (int i = 0; i < UNITS; ++i) {
-                    uint32_t r[32];
-                    ptx::tmem_ld_32x32(taddr0 + 32 * i, r);
+                for (int i = 0; i < 2 * UNITS; ++i) {
+                    uint32_t r[16];
+                    ptx::tmem_ld_32x16(taddr0 + 16 * i, r);
                     ptx::tmem_ld_wait();
                     if (row < M) {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const int col = col_warp + 32 * i + j * 8;
+                        for (int j = 0; j < 2; ++j) {
+                            const int col = col_warp + 16 * i + j * 8;
                             if (col < N) {
                                 float v[8];
 #pragma unroll
@@ -293,23 +299,26 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                 for (int i = 0; i < UNITS; ++i) {
                     const int col_base = col_warp + 32 * i;
                     if (col_base >= N) break;  // warp-uniform: the whole unit is outside the matrix
-                    uint32_t r[32];
-                    ptx::tmem_ld_32x32(taddr0 + 32 * i, r);
                     uint8_t *t0, *t1 = nullptr;
                     if (MODE == ECGVIT_EPI_BIAS_GELU) {
-                        // two (u, h) tile pairs, alternating: the pair used two units ago must have been read
-                        t0 = tiles + (i & 1) * 2 * Cfg::EPI_TILE_BYTES;
-                        t1 = t0 + Cfg::EPI_TILE_BYTES;
-                        if (i >= 2) {
-                            if (lane == 0) ptx::tma_store_wait_read<1>();
-                            __syncwarp();
-                        }
+                        // one (u, h) tile pair per warp: unit 1 reuses it once unit 0's stores have read it
+                        t0 = tiles;
+                        t1 = tiles + Cfg::EPI_TILE_BYTES;
                     } else {
                         t0 = tiles + i * Cfg::EPI_TILE_BYTES;
                         if (kHasAux) ptx::mbar_wait(&my_aux_bar[i], it & 1);
                     }
-                    ptx::tmem_ld_wait();
-                    epilogue_unit32<MODE>(ep, static_cast<int64_t>(row_base) + lane, col_base, N, r, t0, t1, lane);
+#pragma unroll 1
+                    for (int hh = 0; hh < 2; ++hh) {
+                        uint32_t r[16];
+                        ptx::tmem_ld_32x16(taddr0 + 32 * i + 16 * hh, r);
+                        ptx::tmem_ld_wait();
+                        if (MODE == ECGVIT_EPI_BIAS_GELU && i > 0 && hh == 0) {
+                            if (lane == 0) ptx::tma_store_wait_read<0>();
+                            __syncwarp();
+                        }
+                        epilogue_half16<MODE>(ep, row, col_base, N, 2 * hh, r, t0, t1, lane);
+                    }
                     ptx::fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
                     __syncwarp();
                     if (lane == 0) {

@@ -9,7 +9,8 @@ namespace {
 
 constexpr int HEAD_MAXV = 4;  // d <= 1024
 
-// one warp per sample: LayerNorm of the CLS row, then n_class dot products
+// one CTA (4 warps) per sample: every warp LayerNorms the CLS row redundantly (768 elements, cheaper than a barrier +
+// smem round trip), then the warps split the n_class dot products
 template <typename T>
 __global__ void __launch_bounds__(128) head_fwd_kernel(const T *__restrict__ tok, const float *__restrict__ gamma,
                                                         const float *__restrict__ beta, const float *__restrict__ w,
@@ -17,8 +18,8 @@ __global__ void __launch_bounds__(128) head_fwd_kernel(const T *__restrict__ tok
                                                         float *__restrict__ mean_out, float *__restrict__ rstd_out,
                                                         float *__restrict__ logits, int B, int N, int d, int n_class,
                                                         float eps) {
-    const int lane = threadIdx.x & 31;
-    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int b = blockIdx.x;
     if (b >= B) return;
     const T *xr = tok + (int64_t)b * N * d;
     float v[HEAD_MAXV][8];
@@ -52,11 +53,11 @@ __global__ void __launch_bounds__(128) head_fwd_kernel(const T *__restrict__ tok
             load8(beta + c, bt);
 #pragma unroll
             for (int k = 0; k < 8; ++k) v[i][k] = fmaf((v[i][k] - mean) * rstd, g[k], bt[k]);
-            store8(xn + (int64_t)b * d + c, v[i]);
+            if (warp == 0) store8(xn + (int64_t)b * d + c, v[i]);
         }
     }
-    if (lane == 0) { mean_out[b] = mean; rstd_out[b] = rstd; }
-    for (int cls = 0; cls < n_class; ++cls) {
+    if (warp == 0 && lane == 0) { mean_out[b] = mean; rstd_out[b] = rstd; }
+    for (int cls = warp; cls < n_class; cls += nwarp) {
         const float *wr = w + (int64_t)cls * d;
         float acc = 0.f;
 #pragma unroll
@@ -171,41 +172,66 @@ __global__ void __launch_bounds__(128) head_bwd_rows_kernel(const T *__restrict_
     }
 }
 
-// backward B: per column k: dgamma, dbeta of the head LayerNorm and the column sum of the CLS-row gradients
+// backward B: per column k: dgamma, dbeta of the head LayerNorm and the column sum of the CLS-row gradients.
+// block = 32 columns x 8 sample groups, smem tree at the end
 template <typename T>
-__global__ void head_bwd_cols_kernel(const T *__restrict__ tok, const T *__restrict__ dtok,
-                                     const float *__restrict__ dxn, const float *__restrict__ mean_in,
-                                     const float *__restrict__ rstd_in, float *__restrict__ dgamma,
-                                     float *__restrict__ dbeta, float *__restrict__ dcolsum, int B, int N, int d) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= d) return;
+__global__ void __launch_bounds__(256) head_bwd_cols_kernel(const T *__restrict__ tok, const T *__restrict__ dtok,
+                                                             const float *__restrict__ dxn,
+                                                             const float *__restrict__ mean_in,
+                                                             const float *__restrict__ rstd_in,
+                                                             float *__restrict__ dgamma, float *__restrict__ dbeta,
+                                                             float *__restrict__ dcolsum, int B, int N, int d) {
+    __shared__ float red[3][8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int k = blockIdx.x * 32 + tx;
     float sg = 0.f, sb = 0.f, sc = 0.f;
-    for (int b = 0; b < B; ++b) {
-        const float xh = (to_f32(tok[(int64_t)b * N * d + k]) - mean_in[b]) * rstd_in[b];
-        const float dv = dxn[(int64_t)b * d + k];
-        sg = fmaf(dv, xh, sg);
-        sb += dv;
-        sc += to_f32(dtok[(int64_t)b * N * d + k]);
+    if (k < d) {
+        for (int b = ty; b < B; b += 8) {
+            const float xh = (to_f32(tok[(int64_t)b * N * d + k]) - mean_in[b]) * rstd_in[b];
+            const float dv = dxn[(int64_t)b * d + k];
+            sg = fmaf(dv, xh, sg);
+            sb += dv;
+            sc += to_f32(dtok[(int64_t)b * N * d + k]);
+        }
     }
-    dgamma[k] += sg;
-    dbeta[k] += sb;
-    if (dcolsum != nullptr) dcolsum[k] += sc;
+    red[0][ty][tx] = sg; red[1][ty][tx] = sb; red[2][ty][tx] = sc;
+    __syncthreads();
+    if (ty == 0 && k < d) {
+        float a = 0.f, bsum = 0.f, c = 0.f;
+#pragma unroll
+        for (int y = 0; y < 8; ++y) { a += red[0][y][tx]; bsum += red[1][y][tx]; c += red[2][y][tx]; }
+        dgamma[k] += a;
+        dbeta[k] += bsum;
+        if (dcolsum != nullptr) dcolsum[k] += c;
+    }
 }
 
 // backward C: dW[c,k] += sum_b dlogits[b,c] xn[b,k];  db[c] += sum_b dlogits[b,c]
-__global__ void head_bwd_weight_kernel(const float *__restrict__ dlog, const float *__restrict__ xn,
-                                       float *__restrict__ dw, float *__restrict__ db, int B, int d, int n_class) {
+// grid (d/32, n_class), block = 32 columns x 8 sample groups
+__global__ void __launch_bounds__(256) head_bwd_weight_kernel(const float *__restrict__ dlog,
+                                                               const float *__restrict__ xn, float *__restrict__ dw,
+                                                               float *__restrict__ db, int B, int d, int n_class) {
+    __shared__ float red[2][8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int cls = blockIdx.y;
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= d) return;
+    const int k = blockIdx.x * 32 + tx;
     float s = 0.f, sb = 0.f;
-    for (int b = 0; b < B; ++b) {
-        const float dl = dlog[(int64_t)b * n_class + cls];
-        s = fmaf(dl, xn[(int64_t)b * d + k], s);
-        sb += dl;
+    if (k < d) {
+        for (int b = ty; b < B; b += 8) {
+            const float dl = dlog[(int64_t)b * n_class + cls];
+            s = fmaf(dl, xn[(int64_t)b * d + k], s);
+            sb += dl;
+        }
     }
-    dw[(int64_t)cls * d + k] += s;
-    if (k == 0) db[cls] += sb;
+    red[0][ty][tx] = s; red[1][ty][tx] = sb;
+    __syncthreads();
+    if (ty == 0 && k < d) {
+        float a = 0.f, bsum = 0.f;
+#pragma unroll
+        for (int y = 0; y < 8; ++y) { a += red[0][y][tx]; bsum += red[1][y][tx]; }
+        dw[(int64_t)cls * d + k] += a;
+        if (k == 0) db[cls] += bsum;
+    }
 }
 
 }  // namespace
@@ -223,7 +249,7 @@ int ecgvit_head_fwd(const void *tok, const float *gamma, const float *beta, cons
     ECGVIT_REQUIRE(d % 8 == 0 && d <= 8 * 32 * HEAD_MAXV, "head_fwd: d=%d must be a multiple of 8 and <= %d", d,
                    8 * 32 * HEAD_MAXV);
     ECGVIT_REQUIRE(labels == nullptr || loss != nullptr, "head_fwd: labels given but loss is null");
-    const int grid = (B + 3) / 4;
+    const int grid = B;
     if (dtype == ECGVIT_BF16)
         head_fwd_kernel<bf16><<<grid, 128, 0, as_stream(stream)>>>((const bf16 *)tok, gamma, beta, w, b, xn, mean, rstd, logits, B, N, d, n_class, eps);
     else if (dtype == ECGVIT_F32)
@@ -258,13 +284,13 @@ int ecgvit_head_bwd(const void *tok, const float *gamma, const float *w, const f
     const int grid = (B + 3) / 4;
     if (dtype == ECGVIT_BF16) {
         head_bwd_rows_kernel<bf16><<<grid, 128, 0, s>>>((const bf16 *)tok, gamma, w, labels, mean, rstd, logits, (bf16 *)dtok, dxn, dlog, B, N, d, n_class, coef);
-        head_bwd_cols_kernel<bf16><<<(d + 127) / 128, 128, 0, s>>>((const bf16 *)tok, (const bf16 *)dtok, dxn, mean, rstd, dgamma, dbeta, dcolsum, B, N, d);
+        head_bwd_cols_kernel<bf16><<<(d + 31) / 32, 256, 0, s>>>((const bf16 *)tok, (const bf16 *)dtok, dxn, mean, rstd, dgamma, dbeta, dcolsum, B, N, d);
     } else if (dtype == ECGVIT_F32) {
         head_bwd_rows_kernel<float><<<grid, 128, 0, s>>>((const float *)tok, gamma, w, labels, mean, rstd, logits, (float *)dtok, dxn, dlog, B, N, d, n_class, coef);
-        head_bwd_cols_kernel<float><<<(d + 127) / 128, 128, 0, s>>>((const float *)tok, (const float *)dtok, dxn, mean, rstd, dgamma, dbeta, dcolsum, B, N, d);
+        head_bwd_cols_kernel<float><<<(d + 31) / 32, 256, 0, s>>>((const float *)tok, (const float *)dtok, dxn, mean, rstd, dgamma, dbeta, dcolsum, B, N, d);
     } else return fail(-1, "head_bwd: unknown dtype %d", dtype);
-    dim3 gw((d + 127) / 128, n_class);
-    head_bwd_weight_kernel<<<gw, 128, 0, s>>>(dlog, xn, dw, db, B, d, n_class);
+    dim3 gw((d + 31) / 32, n_class);
+    head_bwd_weight_kernel<<<gw, 256, 0, s>>>(dlog, xn, dw, db, B, d, n_class);
     return check_launch("head_bwd");
 }
 
