@@ -116,7 +116,7 @@ def ptr(t):
 
 
 def dropout_keep_mask(seed, stream, p, index):
-    """host replica of the kernels' counter-based dropout (csrc/common.cuh `dropout_hash`): multiplier (0 or
+    """host replica of the kernels' counter-based dropout (csrc/common.cuh `dropout_hash`, two multiply-and-fold rounds): multiplier (0 or
     1/(1-p_q)) for every element index in the int64 tensor `index`; used by the tests to inject the SAME masks into the
     CPU oracle"""
     import torch
@@ -126,10 +126,19 @@ def dropout_keep_mask(seed, stream, p, index):
     m32 = 0xFFFFFFFF
     idx = index.to(torch.int64)
     pair = idx >> 1
-    h = (pair * 0x9E3779B1 + ((seed ^ ((stream * 0x85EBCA77 + 0xC2B2AE3D) & m32)) & m32)) & m32
-    h = h ^ (h >> 16); h = (h * 0x7feb352d) & m32
-    h = h ^ (h >> 15); h = (h * 0x846ca68b) & m32
-    h = h ^ (h >> 16)
+    key = (seed ^ ((stream * 0x85EBCA77 + 0xC2B2AE3D) & m32)) & m32
+
+    def mulfold(a, k):  # (a * k) as a 64-bit product, xor of its two 32-bit halves
+        a_lo, a_hi = a & 0xFFFF, a >> 16  # split so the int64 products cannot overflow
+        p0 = a_lo * k
+        p1 = a_hi * k
+        total_lo = (p0 + ((p1 & 0xFFFF) << 16))
+        lo = total_lo & m32
+        hi = ((p1 >> 16) + (total_lo >> 32)) & m32
+        return lo ^ hi
+
+    h = mulfold((pair ^ key) & m32, 0x9E3779B1)
+    h = mulfold(h, 0x7FEB352D)
     bits = torch.where((idx & 1) == 1, h >> 16, h & 0xFFFF)
     scale = 1.0 / (1.0 - thr / 65536.0)
     return torch.where(bits >= thr, torch.tensor(scale, dtype=torch.float32), torch.tensor(0.0, dtype=torch.float32))

@@ -244,7 +244,7 @@ template <bool kExact> __device__ __forceinline__ float gelu_grad(float u) {
 // ---- dropout ----------------------------------------------------------------------------------------
 // Counter-based: the keep decision of element `idx` of dropout site `stream` is a pure function of
 // (seed, stream, idx), so backward regenerates the mask instead of reading one from HBM.  One 32-bit hash
-// (lowbias32) decides an aligned PAIR of elements with 16 bits each: drop if bits < threshold = round(p * 65536).
+// decides an aligned PAIR of elements with 16 bits each: drop if bits < threshold = round(p * 65536).
 // nn.Dropout semantics: y = x * keep / (1 - p).  (torch's Philox stream cannot be reproduced bit-for-bit by any other
 // implementation; tests inject this mask into the oracle instead.)
 struct DropoutParams {
@@ -253,12 +253,14 @@ struct DropoutParams {
     uint32_t threshold;    // round(p * 65536)
     float scale;           // 1 / (1 - threshold / 65536)
 };
+// two rounds of multiply-and-fold (32 x 32 -> 64 bit product, xor of its halves): 5 issue slots per pair of elements
+// (IMAD.WIDE + LOP3 per round), against 9 for a xorshift-multiply hash -- the GELU epilogues are instruction bound
 __device__ __forceinline__ uint32_t dropout_hash(uint32_t seed, uint32_t stream, uint32_t pair) {
-    uint32_t h = pair * 0x9E3779B1u + (seed ^ (stream * 0x85EBCA77u + 0xC2B2AE3Du));
-    h ^= h >> 16; h *= 0x7feb352du;
-    h ^= h >> 15; h *= 0x846ca68bu;
-    h ^= h >> 16;
-    return h;
+    const uint32_t key = seed ^ (stream * 0x85EBCA77u + 0xC2B2AE3Du);
+    uint64_t m = static_cast<uint64_t>(pair ^ key) * 0x9E3779B1u;
+    uint32_t h = static_cast<uint32_t>(m) ^ static_cast<uint32_t>(m >> 32);
+    m = static_cast<uint64_t>(h) * 0x7FEB352Du;
+    return static_cast<uint32_t>(m) ^ static_cast<uint32_t>(m >> 32);
 }
 // multipliers (0 or scale) for elements idx (even) and idx + 1
 __device__ __forceinline__ void dropout_pair(const DropoutParams &d, uint32_t seed, uint32_t idx_even, float &m0,

@@ -129,8 +129,8 @@ int ecgvit_head_bwd(const void *tok, const float *gamma, const float *w, const f
                     int n_class, int reduction, float grad_scale, int dtype, void *stream);
 
 /* ---- dropout (nn.Dropout at the 5 sites per block + embedding of vit_pytorch; p wiring in ecg_vit.py:113-114).
- *      Counter-based: element `idx` of site `dropout_stream` is kept iff the 16 bits that lowbias32(seed, stream,
- *      idx >> 1) assigns to it are >= round(p * 65536); kept values are scaled by 1 / (1 - p).  `dropout_seed` points to
+ *      Counter-based: element `idx` of site `dropout_stream` is kept iff the 16 bits that hash(seed, stream,
+ *      idx >> 1) (two 32x32->64 multiply-and-fold rounds, csrc/common.cuh) assigns to it are >= round(p * 65536); kept values are scaled by 1 / (1 - p).  `dropout_seed` points to
  *      a DEVICE uint32 the host refreshes every step, so forward and backward regenerate the same mask and no mask is
  *      stored.  Element indices: row * ld + col for [M, ld] tensors; ((b*H + h) * Np + query) * Np + key with
  *      Np = N rounded up to 64 for attention probabilities.
