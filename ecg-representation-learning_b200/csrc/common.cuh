@@ -262,12 +262,14 @@ __device__ __forceinline__ uint32_t dropout_hash(uint32_t seed, uint32_t stream,
     m = static_cast<uint64_t>(h) * 0x7FEB352Du;
     return static_cast<uint32_t>(m) ^ static_cast<uint32_t>(m >> 32);
 }
-// multipliers (0 or scale) for elements idx (even) and idx + 1
+// multipliers (0 or scale) for elements idx (even) and idx + 1.  The 16-bit fields are compared in place
+// (high half against threshold << 16, low half after one shift) instead of being extracted first.
 __device__ __forceinline__ void dropout_pair(const DropoutParams &d, uint32_t seed, uint32_t idx_even, float &m0,
                                              float &m1) {
     const uint32_t h = dropout_hash(seed, d.stream, idx_even >> 1);
-    m0 = (h & 0xffffu) >= d.threshold ? d.scale : 0.f;
-    m1 = (h >> 16) >= d.threshold ? d.scale : 0.f;
+    const uint32_t t = d.threshold << 16;
+    m0 = (h << 16) >= t ? d.scale : 0.f;
+    m1 = h >= t ? d.scale : 0.f;
 }
 // multiplier of a single element (any parity)
 __device__ __forceinline__ float dropout_one(const DropoutParams &d, uint32_t seed, uint32_t idx) {

@@ -145,7 +145,9 @@ __device__ __forceinline__ float pair_sum(uint64_t v) {
 }
 
 // LayerNorm forward: one warp per row, NV 8-element vectors per lane (d <= 256 * NV), packed fp32x2 math,
-// two-pass statistics (mean, then centred sum of squares) like ATen.
+// two-pass statistics (mean, then centred sum of squares) like ATen.  Each warp works on TWO rows at a time so that
+// twice as many 128-bit loads are in flight per warp (the kernel is a single wave of ~1.4 rows per warp: it lives on
+// memory-level parallelism, not on occupancy).
 template <typename T, int NV>
 __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const T *__restrict__ x, const float *__restrict__ gamma,
                                                              const float *__restrict__ beta, T *__restrict__ y,
@@ -153,57 +155,73 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const T *__restrict_
                                                              int M, int d, float eps) {
     pdl_launch_dependents();
     pdl_wait();
+    constexpr int R = 2;
     const int lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;
+    const int64_t total_warps = (int64_t)gridDim.x * warps_per_block;
     const float inv_d = 1.0f / (float)d;
-    for (int64_t row = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < M;
-         row += (int64_t)gridDim.x * warps_per_block) {
-        const T *xr = x + row * d;
-        uint64_t v[NV][4];
-        uint64_t s2 = 0ull;
+    for (int64_t row0 = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5); row0 < M; row0 += R * total_warps) {
+        uint64_t v[R][NV][4];
+        bool live[R];
 #pragma unroll
-        for (int i = 0; i < NV; ++i) {
-            const int c = (i * 32 + lane) * 8;
-            if (c < d) {
-                Packed8<T> p;
-                ld_packed(p, xr + c);
-                unpack_pairs(p, v[i]);
+        for (int r = 0; r < R; ++r) {
+            const int64_t row = row0 + r * total_warps;
+            live[r] = row < M;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) s2 = add2(s2, v[i][k]);
-            }
-        }
-        const float mean = warp_sum(pair_sum(s2)) * inv_d;
-        const uint64_t nmean2 = splat2(-mean);
-        uint64_t sq2 = 0ull;
+            for (int i = 0; i < NV; ++i) {
+                const int c = (i * 32 + lane) * 8;
+                if (live[r] && c < d) {
+                    Packed8<T> p;
+                    ld_packed(p, x + row * d + c);
+                    unpack_pairs(p, v[r][i]);
+                } else {
 #pragma unroll
-        for (int i = 0; i < NV; ++i) {
-            const int c = (i * 32 + lane) * 8;
-            if (c < d) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    v[i][k] = add2(v[i][k], nmean2);  // centred
-                    sq2 = fma2(v[i][k], v[i][k], sq2);
+                    for (int k = 0; k < 4; ++k) v[r][i][k] = 0ull;
                 }
             }
         }
-        const float rstd = rsqrtf(warp_sum(pair_sum(sq2)) * inv_d + eps);
-        const uint64_t rstd2 = splat2(rstd);
-        T *yr = y + row * d;
 #pragma unroll
-        for (int i = 0; i < NV; ++i) {
-            const int c = (i * 32 + lane) * 8;
-            if (c < d) {
-                const uint64_t *g2 = reinterpret_cast<const uint64_t *>(gamma + c);
-                const uint64_t *b2 = reinterpret_cast<const uint64_t *>(beta + c);
-                uint64_t o[4];
+        for (int r = 0; r < R; ++r) {
+            if (!live[r]) continue;  // warp-uniform
+            const int64_t row = row0 + r * total_warps;
+            uint64_t s2 = 0ull;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) o[k] = fma2(mul2(v[i][k], rstd2), __ldg(g2 + k), __ldg(b2 + k));
-                store_pairs(yr + c, o);
+            for (int i = 0; i < NV; ++i)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) s2 = add2(s2, v[r][i][k]);  // lanes past d hold zeros
+            const float mean = warp_sum(pair_sum(s2)) * inv_d;
+            const uint64_t nmean2 = splat2(-mean);
+            uint64_t sq2 = 0ull;
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                const int c = (i * 32 + lane) * 8;
+                if (c < d) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        v[r][i][k] = add2(v[r][i][k], nmean2);  // centred
+                        sq2 = fma2(v[r][i][k], v[r][i][k], sq2);
+                    }
+                }
             }
-        }
-        if (lane == 0) {
-            if (mean_out) mean_out[row] = mean;
-            if (rstd_out) rstd_out[row] = rstd;
+            const float rstd = rsqrtf(warp_sum(pair_sum(sq2)) * inv_d + eps);
+            const uint64_t rstd2 = splat2(rstd);
+            T *yr = y + row * d;
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                const int c = (i * 32 + lane) * 8;
+                if (c < d) {
+                    const uint64_t *g2 = reinterpret_cast<const uint64_t *>(gamma + c);
+                    const uint64_t *b2 = reinterpret_cast<const uint64_t *>(beta + c);
+                    uint64_t o[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) o[k] = fma2(mul2(v[r][i][k], rstd2), __ldg(g2 + k), __ldg(b2 + k));
+                    store_pairs(yr + c, o);
+                }
+            }
+            if (lane == 0) {
+                if (mean_out) mean_out[row] = mean;
+                if (rstd_out) rstd_out[row] = rstd;
+            }
         }
     }
 }

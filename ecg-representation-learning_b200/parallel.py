@@ -33,7 +33,7 @@ def bucket_slices(layer_offsets, total, depth, bucket_layers):
 
 
 class BucketedGradReducer:
-    def __init__(self, model=None, group=None, bucket_layers=2, flat_g=None, layer_offsets=None, depth=None):
+    def __init__(self, model=None, group=None, bucket_layers=1, flat_g=None, layer_offsets=None, depth=None):
         self.group = group
         if model is not None:
             flat_g = model._flat_g

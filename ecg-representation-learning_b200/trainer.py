@@ -48,7 +48,7 @@ def get_train_args(args=None, n_train=None):
 class FusedTrainer:
     def __init__(self, model, learning_rate=3e-4, weight_decay=1e-2, betas=(0.9, 0.999), eps=1e-8,
                  schedule='constant', n_warmup=0, n_step=1 << 30, max_grad_norm=1.0, process_group=None,
-                 bucket_layers=2, use_cuda_graph=False, data_parallel=True):
+                 bucket_layers=1, use_cuda_graph=False, data_parallel=True):
         self.model = model
         self.lr, self.wd, self.betas, self.eps = learning_rate, weight_decay, betas, eps
         self.schedule, self.n_warmup, self.n_step = schedule, n_warmup, n_step

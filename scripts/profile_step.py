@@ -34,7 +34,8 @@ agg = collections.OrderedDict()
 for ev in prof.events():
     if ev.device_type != torch.autograd.DeviceType.CUDA:
         continue
-    name = re.sub(r'\(.*', '', ev.name).replace('void ', '').replace('ecgvit::(anonymous namespace)::', '')
+    name = ev.name.replace('(anonymous namespace)::', '').replace('void ', '').replace('ecgvit::', '')
+    name = re.sub(r'\(.*', '', name)
     a = agg.setdefault(name, [0, 0.0])
     a[0] += 1
     a[1] += ev.device_time if hasattr(ev, 'device_time') else ev.cuda_time
