@@ -48,6 +48,16 @@ def train_flops_per_sample(c):
     return 3 * (depth * (f_lin + f_attn) + f_head) + 2 * f_embed
 
 
+def gemm_traffic():
+    """average DRAM bytes per tcgen05-GEMM launch from the committed ncu capture of one step (profiles/)"""
+    path = os.path.join(ROOT, 'profiles', 'r01_step_final.json')
+    try:
+        fam = json.load(open(path))['gemm_family']
+        return fam['dram_bytes_per_launch'], 'profiles/r01_step_final.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, avg over the GEMM launches of one step)'
+    except Exception:
+        return None, 'no ncu capture committed'
+
+
 def measured_peaks():
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(path):
@@ -310,6 +320,7 @@ def main():
         peaks = measured_peaks()
         eager = ecg_b200.FusedTrainer(model, use_cuda_graph=False, data_parallel=False)
         model._after_layer_backward = None  # the profiling step runs on rank 0 alone: no collective
+        model._engine.side_stream = None    # single stream, so consecutive event deltas are per-call device times
         eager.step(x, y)
         torch.cuda.synchronize()
         _lib.profile[0] = []
@@ -340,7 +351,7 @@ def main():
         roofline = {
             'kernel': 'gemm_tc_kernel (tcgen05.mma kind::f16, all fwd/dgrad/wgrad launches of one step)',
             'bound': 'tensor', 'achieved': achieved, 'peak': peaks['tflops_sustained'], 'unit': 'TFLOP/s',
-            'frac': achieved / peaks['tflops_sustained'], 'traffic': None,
+            'frac': achieved / peaks['tflops_sustained'], 'traffic': gemm_traffic()[0], 'traffic_source': gemm_traffic()[1],
             'peak_source': f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step), of measured",
             'launches': n_gemm, 'avg_launch_ms': gemm_ms / n_gemm, 'flops_per_launch_avg': gemm_flops / n_gemm,
             'step_share': gemm_ms / step_ms_eager,

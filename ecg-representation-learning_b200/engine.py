@@ -16,6 +16,7 @@ Reference semantics: forward = vit_pytorch.ViT.forward via ecg_vit.py:140-149; b
 (train.py:280); optimizer = train.py:281-282.
 """
 import ctypes
+import os
 
 import torch
 
@@ -37,6 +38,11 @@ class StepEngine:
         self._cur = None
         # device scalar holding this step's dropout seed (refreshed by the host before every training forward)
         self.rng = torch.zeros(2, device=model._flat_p.device, dtype=torch.int32)
+        # Weight-gradient GEMMs do not feed the backward chain: issued on a side stream they become a parallel branch of
+        # the step graph and fill the SMs that the chain's kernels leave idle (partial last waves, launch ramps,
+        # memory-bound kernels).  ECGVIT_WGRAD_STREAM=0 keeps everything on one stream.
+        self.side_stream = torch.cuda.Stream(device=model._flat_p.device) \
+            if os.environ.get('ECGVIT_WGRAD_STREAM', '1') != '0' else None
         self._seed_counter = 0
         self.base_seed = 0x5EED
 
@@ -124,7 +130,8 @@ class StepEngine:
         w.dqkv = buf(M, 3 * inner)
         w.du = buf(M, mlp)
         w.de = buf(B * n, d)
-        w.dzm = buf(M, d)  # dropout-masked copy of a residual-stream gradient (only used when p > 0)
+        # dropout-masked copies of the residual-stream gradients (only used when p > 0): one per site of a block
+        w.dzm = [buf(M, d), buf(M, d)]
         w.ln_scratch = buf(int(self.lib.ecgvit_layernorm_bwd_scratch_floats(d)), dtype=torch.float32)
         self.ws[key] = w
         return w
@@ -228,48 +235,79 @@ class StepEngine:
             _lib.REDUCTION[w.reduction], float(grad_scale), dt, st), 'head_bwd')
         scale = float(dh) ** -0.5
 
-        def masked(g, bias_grad, site):
+        main, side = torch.cuda.current_stream(), self.side_stream
+
+        def masked(g, bias_grad, site, which):
             """gradient w.r.t. the output of a Linear that is followed by dropout (identity when p = 0)"""
             if p_blk == 0:
                 return g
-            _lib.check(lib.ecgvit_dropout_bwd_copy(g.data_ptr(), w.dzm.data_ptr(), bias_grad.data_ptr(), M, d, d, p_blk,
-                                                   site, seed_ptr, dt, st), 'dropout_bwd_copy')
-            return w.dzm
+            _lib.check(lib.ecgvit_dropout_bwd_copy(g.data_ptr(), w.dzm[which].data_ptr(), bias_grad.data_ptr(), M, d, d,
+                                                   p_blk, site, seed_ptr, dt, st), 'dropout_bwd_copy')
+            return w.dzm[which]
 
+        def wgrad(*args, **kw):
+            """weight-gradient GEMM on the side stream, ordered after everything issued so far on the main stream;
+            returns the event that marks its completion (None when there is no side stream)"""
+            if side is None:
+                self._gemm(*args, **kw)
+                return None
+            ready = torch.cuda.Event()
+            ready.record(main)
+            side.wait_event(ready)
+            with torch.cuda.stream(side):
+                self._gemm(*args, **kw)
+                done = torch.cuda.Event()
+                done.record(side)
+            return done
+
+        def before_overwrite(ev):
+            """the main stream may not overwrite a scratch buffer that a side-stream GEMM is still reading"""
+            if ev is not None:
+                main.wait_event(ev)
+
+        ev_ff2 = ev_ff1 = ev_out = ev_qkv = None
         for l in range(depth - 1, -1, -1):
             p = f'l{l}.'
             s_att, s_out, s_act, s_ff2 = 1 + 4 * l, 2 + 4 * l, 3 + 4 * l, 4 + 4 * l
             # ---- feed-forward branch: x[l+1] = y + drop(W2 drop(gelu(W1 ln2(y) + b1)) + b2)
-            dzl = masked(dz, gr[p + 'ff2.b'], s_ff2)
-            self._gemm(d, mlp, M, dzl, d, 0, w.h[l], mlp, 0, EPI_ATOMIC_F32, gr[p + 'ff2.w'], mlp, split_k=0)
+            before_overwrite(ev_ff2)   # dzm[0] was read by the previous layer's ff2 wgrad
+            dzl = masked(dz, gr[p + 'ff2.b'], s_ff2, 0)
+            ev_ff2 = wgrad(d, mlp, M, dzl, d, 0, w.h[l], mlp, 0, EPI_ATOMIC_F32, gr[p + 'ff2.w'], mlp, split_k=0)
+            before_overwrite(ev_ff1)   # du
             self._gemm(M, mlp, d, dzl, d, 1, wt[p + 'ff2.w'], mlp, 0, EPI_DGELU, w.du, mlp, aux=w.u[l],
                        drop=(p_blk, s_act))
             _lib.check(lib.ecgvit_colsum(w.du.data_ptr(), gr[p + 'ff1.b'].data_ptr(), M, mlp, mlp, dt, st), 'colsum')
-            self._gemm(mlp, d, M, w.du, mlp, 0, w.ln2[l], d, 0, EPI_ATOMIC_F32, gr[p + 'ff1.w'], d, split_k=0)
+            ev_ff1 = wgrad(mlp, d, M, w.du, mlp, 0, w.ln2[l], d, 0, EPI_ATOMIC_F32, gr[p + 'ff1.w'], d, split_k=0)
             self._gemm(M, d, mlp, w.du, mlp, 1, wt[p + 'ff1.w'], d, 0, EPI_STORE, w.dln, d)
+            before_overwrite(ev_out)   # dy / dzm[1] were read by the previous layer's out-proj wgrad
             _lib.check(lib.ecgvit_layernorm_bwd(
                 w.dln.data_ptr(), w.y[l].data_ptr(), pf[p + 'ln2.w'].data_ptr(), w.stat2[l][0].data_ptr(),
                 w.stat2[l][1].data_ptr(), dz.data_ptr(), dy.data_ptr(), gr[p + 'ln2.w'].data_ptr(),
                 gr[p + 'ln2.b'].data_ptr(), gr[p + 'out.b'].data_ptr() if p_blk == 0 else None,
                 w.ln_scratch.data_ptr(), M, d, dt, st), 'layernorm_bwd')
             # ---- attention branch: y = x + drop(Wo attn(Wqkv ln1(x)) + bo)
-            dyl = masked(dy, gr[p + 'out.b'], s_out)
-            self._gemm(d, inner, M, dyl, d, 0, w.o[l], inner, 0, EPI_ATOMIC_F32, gr[p + 'out.w'], inner, split_k=0)
+            dyl = masked(dy, gr[p + 'out.b'], s_out, 1)
+            ev_out = wgrad(d, inner, M, dyl, d, 0, w.o[l], inner, 0, EPI_ATOMIC_F32, gr[p + 'out.w'], inner, split_k=0)
             self._gemm(M, inner, d, dyl, d, 1, wt[p + 'out.w'], inner, 0, EPI_STORE, w.d_o, inner)
+            before_overwrite(ev_qkv)   # dqkv
             _lib.check(lib.ecgvit_attention_bwd(w.qkv[l].data_ptr(), w.o[l].data_ptr(), w.d_o.data_ptr(),
                                                 w.lse[l].data_ptr(), w.dqkv.data_ptr(), B, N, H, dh, scale, p_blk, s_att,
                                                 blk_seed, dt, st), 'attention_bwd')
-            self._gemm(3 * inner, d, M, w.dqkv, 3 * inner, 0, w.ln1[l], d, 0, EPI_ATOMIC_F32, gr[p + 'qkv.w'], d,
-                       split_k=0)
+            ev_qkv = wgrad(3 * inner, d, M, w.dqkv, 3 * inner, 0, w.ln1[l], d, 0, EPI_ATOMIC_F32, gr[p + 'qkv.w'], d,
+                           split_k=0)
             self._gemm(M, d, 3 * inner, w.dqkv, 3 * inner, 1, wt[p + 'qkv.w'], d, 0, EPI_STORE, w.dln, d)
             below_bias = gr[f'l{l - 1}.ff2.b'] if (l > 0 and p_blk == 0) else None
+            before_overwrite(ev_ff2)   # with p = 0 the ff2 wgrad reads dz itself, which LayerNorm' now rewrites
             _lib.check(lib.ecgvit_layernorm_bwd(
                 w.dln.data_ptr(), w.x[l].data_ptr(), pf[p + 'ln1.w'].data_ptr(), w.stat1[l][0].data_ptr(),
                 w.stat1[l][1].data_ptr(), dy.data_ptr(), dz.data_ptr(), gr[p + 'ln1.w'].data_ptr(),
                 gr[p + 'ln1.b'].data_ptr(), _lib.ptr(below_bias), w.ln_scratch.data_ptr(), M, d, dt, st),
                 'layernorm_bwd')
             if m._after_layer_backward is not None:
+                before_overwrite(ev_qkv)  # the bucket of layer l is complete only when its side-stream wgrads are
                 m._after_layer_backward(l)
+        for ev in (ev_ff2, ev_ff1, ev_out, ev_qkv):
+            before_overwrite(ev)  # join the side stream
         # ---- embedding: tok = [cls | a_patch We^T + be] + pos
         _lib.check(lib.ecgvit_embed_assemble_bwd(dz.data_ptr(), w.de.data_ptr(), gr['cls'].data_ptr(),
                                                  gr['pos'].data_ptr(), gr['embed.b'].data_ptr(), B, n, d, p_emb, 0,
