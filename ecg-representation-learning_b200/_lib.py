@@ -47,14 +47,17 @@ SIGNATURES = {
                              c_int, c_void_p],
     'ecgvit_layernorm_bwd_scratch_floats': [c_int],
     'ecgvit_layernorm_bwd': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                             c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
+                             c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_void_p, c_int, c_int, c_int,
+                             c_void_p],
     'ecgvit_gemm': [POINTER(GemmArgs), c_void_p],
     'ecgvit_attention_fwd': [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float, c_int,
                              c_void_p, c_int, c_void_p],
     'ecgvit_attention_bwd': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float,
                              c_float, c_int, c_void_p, c_int, c_void_p],
-    'ecgvit_head_fwd': [c_void_p] * 11 + [c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p],
-    'ecgvit_head_bwd': [c_void_p] * 15 + [c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p],
+    'ecgvit_head_fwd': [c_void_p] * 7 + [c_int] + [c_void_p] * 5 + [c_int, c_int, c_int, c_int, c_int, c_float, c_int,
+                                                                     c_void_p],
+    'ecgvit_head_bwd': [c_void_p] * 5 + [c_int] + [c_void_p] * 11 + [c_int, c_int, c_int, c_int, c_int, c_float, c_int,
+                                                                      c_void_p],
     'ecgvit_colsum': [c_void_p, c_void_p, c_int, c_int, c_int64, c_int, c_void_p],
     'ecgvit_grad_sumsq': [c_void_p, c_int64, c_void_p, c_void_p, c_void_p],
     'ecgvit_adamw_step': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p],

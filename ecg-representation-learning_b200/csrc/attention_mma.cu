@@ -103,6 +103,25 @@ __device__ __forceinline__ void frag_times_rows(float acc[DH / 8][4], const uint
     }
 }
 
+// acc (16 rows j0.. x DH) += W^T[j0:j0+16, :] * Z, with W stored [q][key] (pitch 72) and Z stored [q][d]
+template <int DH, int NT>
+__device__ __forceinline__ void transposed_times_rows(float acc[DH / 8][4], bf16 (*W)[NMAX + 8], bf16 (*Z)[DH + 8],
+                                                      int j0, int lane) {
+#pragma unroll
+    for (int kk = 0; kk < NT; ++kk) {
+        uint32_t a[4];
+        const int mi = lane >> 3;
+        ldsm_x4_t(a, &W[kk * 16 + (lane & 7) + (mi >> 1) * 8][j0 + (mi & 1) * 8]);
+#pragma unroll
+        for (int dp = 0; dp < DH / 16; ++dp) {
+            uint32_t b[4];
+            ldsm_x4_t(b, &Z[kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8][dp * 16 + (lane >> 4) * 8]);
+            mma16816(acc[2 * dp], a, b[0], b[1]);
+            mma16816(acc[2 * dp + 1], a, b[2], b[3]);
+        }
+    }
+}
+
 template <int DH>
 __device__ __forceinline__ void store_rows(bf16 *dst, int ld, float acc[DH / 8][4], int r0, int r1, int N, int t,
                                            float mul0, float mul1) {
@@ -200,16 +219,19 @@ __global__ void __launch_bounds__(128) attention_fwd_mma_kernel(const bf16 *__re
 }
 
 template <int DH, int NT>
-__global__ void __launch_bounds__(128, 5) attention_bwd_mma_kernel(const bf16 *__restrict__ qkv, const bf16 *__restrict__ o,
+__global__ void __launch_bounds__(128) attention_bwd_mma_kernel(const bf16 *__restrict__ qkv, const bf16 *__restrict__ o,
                                                                  const bf16 *__restrict__ d_o,
                                                                  const float *__restrict__ lse, bf16 *__restrict__ dqkv,
                                                                  int N, int H, float scale, DropoutParams drop) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     typedef bf16(*TileD)[DH + 8];
+    typedef bf16(*TileN)[NMAX + 8];
     TileD sQ = reinterpret_cast<TileD>(smem_raw);
     TileD sK = sQ + NMAX, sV = sK + NMAX, sdO = sV + NMAX;
-    float *sD = reinterpret_cast<float *>(sdO + NMAX);  // [NMAX] rowsum(dO * O)
-    float *sL = sD + NMAX;                              // [NMAX] log-sum-exp * log2(e)
+    TileN sP = reinterpret_cast<TileN>(sdO + NMAX);
+    TileN sdS = sP + NMAX;
+
+    float *sD = reinterpret_cast<float *>(sdS + NMAX);  // [NMAX] rowsum(dO * O)
     pdl_launch_dependents();
     pdl_wait();
 
@@ -254,8 +276,6 @@ __global__ void __launch_bounds__(128, 5) attention_bwd_mma_kernel(const bf16 *_
         for (int off = VPR / 2; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
         if ((i % VPR) == 0) sD[r] = part;
     }
-    if (threadIdx.x < NMAX)
-        sL[threadIdx.x] = threadIdx.x < N ? lse[((int64_t)b * H + h) * N + threadIdx.x] * LOG2E : 0.f;
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = warp * 16;
@@ -263,23 +283,24 @@ __global__ void __launch_bounds__(128, 5) attention_bwd_mma_kernel(const bf16 *_
     bf16 *dq = dqkv + (int64_t)b * N * ld + h * DH;
     const bool active = m0 < N;  // this warp owns query rows (and, later, key rows) m0 .. m0+15
 
-    if (!active) return;
-    const float sl2 = scale * LOG2E;
-    const bool dropping = drop.threshold != 0;
-    const uint32_t seed = dropping ? __ldg(drop.seed) : 0u;
-    const int r0 = m0 + g, r1 = r0 + 8;
-    {
-        // ---- query rows m0..m0+15:  S = Q K^T, dP = dO V^T, dS = P (mask dP - D) scale, dQ = dS K
-        const float D0 = sD[r0], D1 = sD[r1], l0 = sL[r0], l1 = sL[r1];
+    if (active) {
+        const int r0 = m0 + g, r1 = r0 + 8;
+        const float D0 = sD[r0], D1 = sD[r1];
+        const float *l = lse + ((int64_t)b * H + h) * N;
+        const float l0 = r0 < N ? l[r0] * LOG2E : 0.f, l1 = r1 < N ? l[r1] * LOG2E : 0.f;
+
         float s[2 * NT][4], dp[2 * NT][4];
-        rows_times_transposed<DH, NT>(s, sQ, sK, m0, lane);
-        rows_times_transposed<DH, NT>(dp, sdO, sV, m0, lane);
+        rows_times_transposed<DH, NT>(s, sQ, sK, m0, lane);    // S = Q K^T
+        rows_times_transposed<DH, NT>(dp, sdO, sV, m0, lane);  // dP = dO V^T
+        const float sl2 = scale * LOG2E;
+        const bool dropping = drop.threshold != 0;
+        const uint32_t seed = dropping ? __ldg(drop.seed) : 0u;
         const uint32_t base0 = (static_cast<uint32_t>(blockIdx.x) * NMAX + r0) * NMAX + 2 * t;
         uint32_t dsa[NT][4];
 #pragma unroll
         for (int j = 0; j < 2 * NT; ++j) {
             const int c = 8 * j + 2 * t;
-            float ds[4], mk[4] = {1.f, 1.f, 1.f, 1.f};
+            float p[4], ds[4], mk[4] = {1.f, 1.f, 1.f, 1.f};
             if (dropping) {
                 dropout_pair(drop, seed, base0 + 8 * j, mk[0], mk[1]);
                 dropout_pair(drop, seed, base0 + 8 * NMAX + 8 * j, mk[2], mk[3]);
@@ -289,10 +310,18 @@ __global__ void __launch_bounds__(128, 5) attention_bwd_mma_kernel(const bf16 *_
                 const bool valid = (c + (i & 1) < N) && ((i < 2 ? r0 : r1) < N);
                 const float pu = valid ? ex2_approx(s[j][i] * sl2 - (i < 2 ? l0 : l1)) : 0.f;  // softmax probability
                 ds[i] = pu * (dp[j][i] * mk[i] - (i < 2 ? D0 : D1)) * scale;                  // dS uses the undropped P
+                p[i] = pu * mk[i];                                                            // dV uses the dropped P
             }
-            dsa[j >> 1][(j & 1) * 2] = pack_bf16x2(ds[0], ds[1]);
-            dsa[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(ds[2], ds[3]);
+            const uint32_t p01 = pack_bf16x2(p[0], p[1]), p23 = pack_bf16x2(p[2], p[3]);
+            const uint32_t d01 = pack_bf16x2(ds[0], ds[1]), d23 = pack_bf16x2(ds[2], ds[3]);
+            *reinterpret_cast<uint32_t *>(&sP[r0][c]) = p01;
+            *reinterpret_cast<uint32_t *>(&sP[r1][c]) = p23;
+            *reinterpret_cast<uint32_t *>(&sdS[r0][c]) = d01;
+            *reinterpret_cast<uint32_t *>(&sdS[r1][c]) = d23;
+            dsa[j >> 1][(j & 1) * 2] = d01;
+            dsa[j >> 1][(j & 1) * 2 + 1] = d23;
         }
+        // dQ = dS K
         float acc[DH / 8][4];
 #pragma unroll
         for (int j = 0; j < DH / 8; ++j)
@@ -301,50 +330,27 @@ __global__ void __launch_bounds__(128, 5) attention_bwd_mma_kernel(const bf16 *_
         frag_times_rows<DH, NT>(acc, dsa, sK, lane);
         store_rows<DH>(dq, ld, acc, r0, r1, N, t, 1.f, 1.f);
     }
-    {
-        // ---- key rows m0..m0+15, recomputed TRANSPOSED so that P^T and dS^T come out of the MMAs already in A-fragment
-        //      layout: S^T = K Q^T, dP^T = V dO^T; dV = Pdrop^T dO, dK = dS^T Q.  (Twice the QK^T / dO V^T work, but no
-        //      probability tiles in shared memory, no second barrier and a third less shared memory per CTA.)
-        float st[2 * NT][4], dpt[2 * NT][4];
-        rows_times_transposed<DH, NT>(st, sK, sQ, m0, lane);
-        rows_times_transposed<DH, NT>(dpt, sV, sdO, m0, lane);
-        uint32_t pa[NT][4], dsa[NT][4];
-#pragma unroll
-        for (int j = 0; j < 2 * NT; ++j) {
-            const int c = 8 * j + 2 * t;  // query index of elements 0 / 2; elements 1 / 3 are query c + 1
-            float p[4], ds[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int q = c + (i & 1), key = (i < 2 ? r0 : r1);
-                const bool valid = q < N && key < N;
-                const float mk = dropping ? dropout_one(drop, seed, (static_cast<uint32_t>(blockIdx.x) * NMAX + q) * NMAX + key) : 1.f;
-                const float pu = valid ? ex2_approx(st[j][i] * sl2 - sL[q]) : 0.f;
-                ds[i] = pu * (dpt[j][i] * mk - sD[q]) * scale;
-                p[i] = pu * mk;
-            }
-            pa[j >> 1][(j & 1) * 2] = pack_bf16x2(p[0], p[1]);
-            pa[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(p[2], p[3]);
-            dsa[j >> 1][(j & 1) * 2] = pack_bf16x2(ds[0], ds[1]);
-            dsa[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(ds[2], ds[3]);
-        }
+    __syncthreads();
+    if (active) {
+        const int r0 = m0 + g, r1 = r0 + 8;  // now key rows
         float acc[DH / 8][4];
 #pragma unroll
         for (int j = 0; j < DH / 8; ++j)
 #pragma unroll
             for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
-        frag_times_rows<DH, NT>(acc, dsa, sQ, lane);  // dK = dS^T Q
+        transposed_times_rows<DH, NT>(acc, sdS, sQ, m0, lane);  // dK = dS^T Q
         store_rows<DH>(dq + inner, ld, acc, r0, r1, N, t, 1.f, 1.f);
 #pragma unroll
         for (int j = 0; j < DH / 8; ++j)
 #pragma unroll
             for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
-        frag_times_rows<DH, NT>(acc, pa, sdO, lane);  // dV = Pdrop^T dO
+        transposed_times_rows<DH, NT>(acc, sP, sdO, m0, lane);  // dV = P^T dO
         store_rows<DH>(dq + 2 * inner, ld, acc, r0, r1, N, t, 1.f, 1.f);
     }
 }
 
 template <int DH> constexpr size_t bwd_smem_bytes() {
-    return sizeof(bf16) * (4 * NMAX * (DH + 8)) + sizeof(float) * 2 * NMAX;
+    return sizeof(bf16) * (4 * NMAX * (DH + 8) + 2 * NMAX * (NMAX + 8)) + sizeof(float) * NMAX;
 }
 
 template <int DH, int NT>

@@ -229,14 +229,16 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const T *__restrict_
 // All per-element math runs on packed fp32x2 (FFMA2 / FADD2 / FMUL2): ~11 issue slots per element instead of ~25.
 //   dx = dy * (rstd * gamma) + x * B + C,  B = -rstd^2 * s2,  C = rstd * (mean * rstd * s2 - s1)
 //   with s1 = mean_c(dy * gamma), s2 = mean_c(dy * gamma * xhat)
-template <typename T, int NV>
+// kDrop: dx feeds a Linear through a dropout (to_out[1] / net[4] of the block below): additionally write
+// dxm = mask * dx / (1 - p) (that Linear's dgrad / wgrad operand) and make the column sums those of dxm (its bias grad).
+template <typename T, int NV, bool kDrop>
 __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const T *__restrict__ dy, const T *__restrict__ x,
                                                                 const float *__restrict__ gamma,
                                                                 const float *__restrict__ mean_in,
                                                                 const float *__restrict__ rstd_in, const T *dres, T *dx,
                                                                 float *__restrict__ dgamma, float *__restrict__ dbeta,
                                                                 float *__restrict__ dcolsum, float *__restrict__ partial,
-                                                                int M, int d) {
+                                                                int M, int d, T *__restrict__ dxm, DropoutParams drop) {
     extern __shared__ float red[];  // [warps][3][d] column partials, then [d] gamma
     pdl_launch_dependents();
     pdl_wait();
@@ -308,6 +310,17 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const T *__restri
                     for (int k = 0; k < 4; ++k) o2[k] = add2(o2[k], r2[k]);
                 }
                 store_pairs(dx + row * d + c, o2);
+                if (kDrop) {
+                    const uint32_t seed = __ldg(drop.seed);
+                    const uint32_t e0 = static_cast<uint32_t>(row * d + c);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        float m0, m1;
+                        dropout_pair(drop, seed, e0 + 2 * k, m0, m1);
+                        o2[k] = mul2(o2[k], pack2(m0, m1));
+                    }
+                    store_pairs(dxm + row * d + c, o2);
+                }
                 if (dcolsum != nullptr) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) acc_c[i][k] = add2(acc_c[i][k], o2[k]);
@@ -546,26 +559,32 @@ int64_t ecgvit_layernorm_bwd_scratch_floats(int d) { return (int64_t)LN_BWD_MAX_
 
 int ecgvit_layernorm_bwd(const void *dy, const void *x, const float *gamma, const float *mean, const float *rstd,
                          const void *dres, void *dx, float *dgamma, float *dbeta, float *dcolsum, float *scratch,
-                         int M, int d, int dtype, void *stream) {
+                         void *dxm, float dropout_p, int dropout_stream, const uint32_t *dropout_seed, int M, int d,
+                         int dtype, void *stream) {
     ECGVIT_REQUIRE(dy && x && gamma && mean && rstd && dx && dgamma && dbeta && scratch && M > 0,
                    "layernorm_bwd: bad arguments");
     ECGVIT_REQUIRE(d % 8 == 0 && d <= 8 * 32 * LN_MAXV, "layernorm_bwd: d=%d must be a multiple of 8 and <= %d", d,
                    8 * 32 * LN_MAXV);
+    const DropoutParams drop = make_dropout(dropout_p, dropout_stream, dropout_seed);
+    const bool dropping = drop.threshold != 0 && dxm != nullptr;
     int grid = grid_for((int64_t)M * 32, 256, 2);
     if (grid > LN_BWD_MAX_BLOCKS) grid = LN_BWD_MAX_BLOCKS;
     const size_t smem = (8 * 3 + 1) * (size_t)d * sizeof(float);
     const int nv = (d + 255) / 256;
     cudaStream_t st = as_stream(stream);
-#define ECGVIT_LN_BWD(TT, NVV)                                                                                         \
+#define ECGVIT_LN_BWD2(TT, NVV, DROP)                                                                                  \
     do {                                                                                                               \
         static bool attr_set = false;                                                                                  \
         if (!attr_set) {                                                                                               \
-            cudaFuncSetAttribute(layernorm_bwd_kernel<TT, NVV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 25 * 1024 * 4); \
+            cudaFuncSetAttribute(layernorm_bwd_kernel<TT, NVV, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                 25 * 1024 * 4);                                                                       \
             attr_set = true;                                                                                           \
         }                                                                                                              \
-        launch_pdl(layernorm_bwd_kernel<TT, NVV>, dim3(grid), dim3(256), smem, st, (const TT *)dy, (const TT *)x,     \
-                   gamma, mean, rstd, (const TT *)dres, (TT *)dx, dgamma, dbeta, dcolsum, scratch, M, d);              \
+        launch_pdl(layernorm_bwd_kernel<TT, NVV, DROP>, dim3(grid), dim3(256), smem, st, (const TT *)dy,              \
+                   (const TT *)x, gamma, mean, rstd, (const TT *)dres, (TT *)dx, dgamma, dbeta, dcolsum, scratch, M, d, \
+                   (TT *)dxm, drop);                                                                                   \
     } while (0)
+#define ECGVIT_LN_BWD(TT, NVV) do { if (dropping) ECGVIT_LN_BWD2(TT, NVV, true); else ECGVIT_LN_BWD2(TT, NVV, false); } while (0)
     if (dtype == ECGVIT_BF16) {
         switch (nv) {
             case 1: ECGVIT_LN_BWD(bf16, 1); break;
@@ -582,6 +601,7 @@ int ecgvit_layernorm_bwd(const void *dy, const void *x, const float *gamma, cons
         }
     } else return fail(-1, "layernorm_bwd: unknown dtype %d", dtype);
 #undef ECGVIT_LN_BWD
+#undef ECGVIT_LN_BWD2
     int rc = check_launch("layernorm_bwd");
     if (rc) return rc;
     launch_pdl(layernorm_bwd_finalize_kernel, dim3((3 * d + 31) / 32), dim3(256), 0, st, (const float *)scratch, grid,

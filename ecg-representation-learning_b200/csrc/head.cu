@@ -80,14 +80,22 @@ __device__ __forceinline__ float bce_with_logits(float z, float y) {
     return fmaxf(z, 0.f) - z * y + log1pf(expf(-fabsf(z)));
 }
 
+// `weight[labels.long()]` of ecg_vit.py:144-147: the element weight is looked up by the integer value of the label
+__device__ __forceinline__ float label_weight(const float *__restrict__ table, int n_weight, float y) {
+    if (table == nullptr) return 1.f;
+    const int i = min(max(static_cast<int>(y), 0), n_weight - 1);
+    return __ldg(table + i);
+}
+
 // single CTA, deterministic tree reduction
 __global__ void __launch_bounds__(1024) bce_loss_kernel(const float *__restrict__ logits,
                                                          const float *__restrict__ labels, float *__restrict__ loss,
-                                                         int n, int reduction) {
+                                                         int n, int reduction, const float *__restrict__ loss_weight,
+                                                         int n_weight) {
     __shared__ float red[32];
     float s = 0.f;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const float l = bce_with_logits(logits[i], labels[i]);
+        const float l = label_weight(loss_weight, n_weight, labels[i]) * bce_with_logits(logits[i], labels[i]);
         if (reduction == ECGVIT_REDUCTION_NONE) loss[i] = l;
         s += l;
     }
@@ -111,7 +119,8 @@ __global__ void __launch_bounds__(128) head_bwd_rows_kernel(const T *__restrict_
                                                              const float *__restrict__ rstd_in,
                                                              const float *__restrict__ logits, T *__restrict__ dtok,
                                                              float *__restrict__ dxn_out, float *__restrict__ dlog_out,
-                                                             int B, int N, int d, int n_class, float coef) {
+                                                             int B, int N, int d, int n_class, float coef,
+                                                             const float *__restrict__ loss_weight, int n_weight) {
     const int lane = threadIdx.x & 31;
     const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (b >= B) return;
@@ -122,7 +131,7 @@ __global__ void __launch_bounds__(128) head_bwd_rows_kernel(const T *__restrict_
         for (int k = 0; k < 8; ++k) dxn[i][k] = 0.f;
     for (int cls = 0; cls < n_class; ++cls) {
         const float z = logits[(int64_t)b * n_class + cls], y = labels[(int64_t)b * n_class + cls];
-        const float dl = coef * (1.0f / (1.0f + expf(-z)) - y);
+        const float dl = coef * label_weight(loss_weight, n_weight, y) * (1.0f / (1.0f + expf(-z)) - y);
         if (lane == 0) dlog_out[(int64_t)b * n_class + cls] = dl;
         const float *wr = w + (int64_t)cls * d;
 #pragma unroll
@@ -242,13 +251,15 @@ using namespace ecgvit;
 extern "C" {
 
 int ecgvit_head_fwd(const void *tok, const float *gamma, const float *beta, const float *w, const float *b,
-                    const float *labels, float *xn, float *mean, float *rstd, float *logits, float *loss, int B,
-                    int N, int d, int n_class, int reduction, float eps, int dtype, void *stream) {
+                    const float *labels, const float *loss_weight, int n_weight, float *xn, float *mean, float *rstd,
+                    float *logits, float *loss, int B, int N, int d, int n_class, int reduction, float eps, int dtype,
+                    void *stream) {
     ECGVIT_REQUIRE(tok && gamma && beta && w && b && xn && mean && rstd && logits, "head_fwd: null argument");
     ECGVIT_REQUIRE(B > 0 && N > 0 && n_class > 0, "head_fwd: bad sizes");
     ECGVIT_REQUIRE(d % 8 == 0 && d <= 8 * 32 * HEAD_MAXV, "head_fwd: d=%d must be a multiple of 8 and <= %d", d,
                    8 * 32 * HEAD_MAXV);
     ECGVIT_REQUIRE(labels == nullptr || loss != nullptr, "head_fwd: labels given but loss is null");
+    ECGVIT_REQUIRE(loss_weight == nullptr || n_weight >= 1, "head_fwd: loss_weight table needs n_weight >= 1");
     const int grid = B;
     if (dtype == ECGVIT_BF16)
         head_fwd_kernel<bf16><<<grid, 128, 0, as_stream(stream)>>>((const bf16 *)tok, gamma, beta, w, b, xn, mean, rstd, logits, B, N, d, n_class, eps);
@@ -258,14 +269,16 @@ int ecgvit_head_fwd(const void *tok, const float *gamma, const float *beta, cons
     int rc = check_launch("head_fwd");
     if (rc) return rc;
     if (labels != nullptr) {
-        bce_loss_kernel<<<1, 1024, 0, as_stream(stream)>>>(logits, labels, loss, B * n_class, reduction);
+        bce_loss_kernel<<<1, 1024, 0, as_stream(stream)>>>(logits, labels, loss, B * n_class, reduction, loss_weight,
+                                                              n_weight);
         rc = check_launch("bce_loss");
     }
     return rc;
 }
 
-int ecgvit_head_bwd(const void *tok, const float *gamma, const float *w, const float *labels, const float *xn,
-                    const float *mean, const float *rstd, const float *logits, void *dtok, float *dw, float *db,
+int ecgvit_head_bwd(const void *tok, const float *gamma, const float *w, const float *labels, const float *loss_weight,
+                    int n_weight, const float *xn, const float *mean, const float *rstd, const float *logits, void *dtok,
+                    float *dw, float *db,
                     float *dgamma, float *dbeta, float *dcolsum, float *scratch, int B, int N, int d, int n_class,
                     int reduction, float grad_scale, int dtype, void *stream) {
     ECGVIT_REQUIRE(tok && gamma && w && labels && xn && mean && rstd && logits && dtok && dw && db && dgamma &&
@@ -273,6 +286,7 @@ int ecgvit_head_bwd(const void *tok, const float *gamma, const float *w, const f
                    "head_bwd: null argument");
     ECGVIT_REQUIRE(reduction == ECGVIT_REDUCTION_MEAN || reduction == ECGVIT_REDUCTION_SUM,
                    "head_bwd: reduction must be mean or sum");
+    ECGVIT_REQUIRE(loss_weight == nullptr || n_weight >= 1, "head_bwd: loss_weight table needs n_weight >= 1");
     ECGVIT_REQUIRE(d % 8 == 0 && d <= 8 * 32 * HEAD_MAXV, "head_bwd: d=%d must be a multiple of 8 and <= %d", d,
                    8 * 32 * HEAD_MAXV);
     cudaStream_t s = as_stream(stream);
@@ -283,10 +297,10 @@ int ecgvit_head_bwd(const void *tok, const float *gamma, const float *w, const f
     float *dxn = scratch, *dlog = scratch + (size_t)B * d;
     const int grid = (B + 3) / 4;
     if (dtype == ECGVIT_BF16) {
-        head_bwd_rows_kernel<bf16><<<grid, 128, 0, s>>>((const bf16 *)tok, gamma, w, labels, mean, rstd, logits, (bf16 *)dtok, dxn, dlog, B, N, d, n_class, coef);
+        head_bwd_rows_kernel<bf16><<<grid, 128, 0, s>>>((const bf16 *)tok, gamma, w, labels, mean, rstd, logits, (bf16 *)dtok, dxn, dlog, B, N, d, n_class, coef, loss_weight, n_weight);
         head_bwd_cols_kernel<bf16><<<(d + 31) / 32, 256, 0, s>>>((const bf16 *)tok, (const bf16 *)dtok, dxn, mean, rstd, dgamma, dbeta, dcolsum, B, N, d);
     } else if (dtype == ECGVIT_F32) {
-        head_bwd_rows_kernel<float><<<grid, 128, 0, s>>>((const float *)tok, gamma, w, labels, mean, rstd, logits, (float *)dtok, dxn, dlog, B, N, d, n_class, coef);
+        head_bwd_rows_kernel<float><<<grid, 128, 0, s>>>((const float *)tok, gamma, w, labels, mean, rstd, logits, (float *)dtok, dxn, dlog, B, N, d, n_class, coef, loss_weight, n_weight);
         head_bwd_cols_kernel<float><<<(d + 31) / 32, 256, 0, s>>>((const float *)tok, (const float *)dtok, dxn, mean, rstd, dgamma, dbeta, dcolsum, B, N, d);
     } else return fail(-1, "head_bwd: unknown dtype %d", dtype);
     dim3 gw((d + 31) / 32, n_class);

@@ -37,7 +37,9 @@ class StepEngine:
         self.ws = {}
         self._cur = None
         # device scalar holding this step's dropout seed (refreshed by the host before every training forward)
-        self.rng = torch.zeros(2, device=model._flat_p.device, dtype=torch.int32)
+        self.device = model._flat_p.device
+        self._lw_key = self._lw_table = None
+        self.rng = torch.zeros(2, device=self.device, dtype=torch.int32)
         # Weight-gradient GEMMs do not feed the backward chain: issued on a side stream they become a parallel branch of
         # the step graph and fill the SMs that the chain's kernels leave idle (partial last waves, launch ramps,
         # memory-bound kernels).  ECGVIT_WGRAD_STREAM=0 keeps everything on one stream.
@@ -197,13 +199,25 @@ class StepEngine:
         _lib.check(lib.ecgvit_head_fwd(
             w.x[c.num_hidden_layers].data_ptr(), pf['head.ln.w'].data_ptr(), pf['head.ln.b'].data_ptr(),
             pf['head.w'].data_ptr(), pf['head.b'].data_ptr(), w.labels.data_ptr() if labels is not None else None,
-            w.xn.data_ptr(), w.hstat[0].data_ptr(), w.hstat[1].data_ptr(), w.logits.data_ptr(),
+            *self._loss_weight_table(), w.xn.data_ptr(), w.hstat[0].data_ptr(), w.hstat[1].data_ptr(), w.logits.data_ptr(),
             _lib.ptr(loss_buf), B, N, d, m.num_class, red, LN_EPS, dt, st), 'head_fwd')
         w.reduction = reduction
         loss = None
         if labels is not None:
             loss = w.loss_none if reduction == 'none' else w.loss[0]
         return loss, w.logits
+
+    def _loss_weight_table(self):
+        """(device pointer, length) of `EcgVit.loss_weight` (ecg_vit.py:144-147), or (None, 0) when unset; the table
+        is re-uploaded only when the attribute changes (never inside a captured step)"""
+        lw = self.model.loss_weight
+        if not lw:
+            return None, 0
+        key = tuple(float(v) for v in lw)
+        if self._lw_key != key:
+            self._lw_table = torch.tensor(key, dtype=torch.float32, device=self.device)
+            self._lw_key = key
+        return self._lw_table.data_ptr(), len(key)
 
     # ---- backward --------------------------------------------------------------------------------
     def backward(self, grad_scale=1.0, zero_grads=True):
@@ -230,7 +244,7 @@ class StepEngine:
         # and its bias gradient come from the masked copy, so the producers must not pre-sum the unmasked gradient
         _lib.check(lib.ecgvit_head_bwd(
             w.x[depth].data_ptr(), pf['head.ln.w'].data_ptr(), pf['head.w'].data_ptr(), w.labels.data_ptr(),
-            w.xn.data_ptr(), w.hstat[0].data_ptr(), w.hstat[1].data_ptr(), w.logits.data_ptr(), dz.data_ptr(),
+            *self._loss_weight_table(), w.xn.data_ptr(), w.hstat[0].data_ptr(), w.hstat[1].data_ptr(), w.logits.data_ptr(), dz.data_ptr(),
             gr['head.w'].data_ptr(), gr['head.b'].data_ptr(), gr['head.ln.w'].data_ptr(), gr['head.ln.b'].data_ptr(),
             gr[last + 'ff2.b'].data_ptr() if p_blk == 0 else None, w.head_scratch.data_ptr(), B, N, d, m.num_class,
             _lib.REDUCTION[w.reduction], float(grad_scale), dt, st), 'head_bwd')
@@ -271,8 +285,8 @@ class StepEngine:
             p = f'l{l}.'
             s_att, s_out, s_act, s_ff2 = 1 + 4 * l, 2 + 4 * l, 3 + 4 * l, 4 + 4 * l
             # ---- feed-forward branch: x[l+1] = y + drop(W2 drop(gelu(W1 ln2(y) + b1)) + b2)
-            before_overwrite(ev_ff2)   # dzm[0] was read by the previous layer's ff2 wgrad
-            dzl = masked(dz, gr[p + 'ff2.b'], s_ff2, 0)
+            if l == depth - 1:
+                dzl = masked(dz, gr[p + 'ff2.b'], s_ff2, 0)   # below the top block LayerNorm' writes the masked copy
             ev_ff2 = wgrad(d, mlp, M, dzl, d, 0, w.h[l], mlp, 0, EPI_ATOMIC_F32, gr[p + 'ff2.w'], mlp, split_k=0)
             before_overwrite(ev_ff1)   # du
             self._gemm(M, mlp, d, dzl, d, 1, wt[p + 'ff2.w'], mlp, 0, EPI_DGELU, w.du, mlp, aux=w.u[l],
@@ -281,13 +295,13 @@ class StepEngine:
             ev_ff1 = wgrad(mlp, d, M, w.du, mlp, 0, w.ln2[l], d, 0, EPI_ATOMIC_F32, gr[p + 'ff1.w'], d, split_k=0)
             self._gemm(M, d, mlp, w.du, mlp, 1, wt[p + 'ff1.w'], d, 0, EPI_STORE, w.dln, d)
             before_overwrite(ev_out)   # dy / dzm[1] were read by the previous layer's out-proj wgrad
+            dyl = w.dzm[1] if p_blk > 0 else dy
             _lib.check(lib.ecgvit_layernorm_bwd(
                 w.dln.data_ptr(), w.y[l].data_ptr(), pf[p + 'ln2.w'].data_ptr(), w.stat2[l][0].data_ptr(),
                 w.stat2[l][1].data_ptr(), dz.data_ptr(), dy.data_ptr(), gr[p + 'ln2.w'].data_ptr(),
-                gr[p + 'ln2.b'].data_ptr(), gr[p + 'out.b'].data_ptr() if p_blk == 0 else None,
-                w.ln_scratch.data_ptr(), M, d, dt, st), 'layernorm_bwd')
-            # ---- attention branch: y = x + drop(Wo attn(Wqkv ln1(x)) + bo)
-            dyl = masked(dy, gr[p + 'out.b'], s_out, 1)
+                gr[p + 'ln2.b'].data_ptr(), gr[p + 'out.b'].data_ptr(), w.ln_scratch.data_ptr(),
+                dyl.data_ptr() if p_blk > 0 else None, p_blk, s_out, blk_seed, M, d, dt, st), 'layernorm_bwd')
+            # ---- attention branch: y = x + drop(Wo attn(Wqkv ln1(x)) + bo); dyl = mask * dy / (1 - p)
             ev_out = wgrad(d, inner, M, dyl, d, 0, w.o[l], inner, 0, EPI_ATOMIC_F32, gr[p + 'out.w'], inner, split_k=0)
             self._gemm(M, inner, d, dyl, d, 1, wt[p + 'out.w'], inner, 0, EPI_STORE, w.d_o, inner)
             before_overwrite(ev_qkv)   # dqkv
@@ -297,13 +311,16 @@ class StepEngine:
             ev_qkv = wgrad(3 * inner, d, M, w.dqkv, 3 * inner, 0, w.ln1[l], d, 0, EPI_ATOMIC_F32, gr[p + 'qkv.w'], d,
                            split_k=0)
             self._gemm(M, d, 3 * inner, w.dqkv, 3 * inner, 1, wt[p + 'qkv.w'], d, 0, EPI_STORE, w.dln, d)
-            below_bias = gr[f'l{l - 1}.ff2.b'] if (l > 0 and p_blk == 0) else None
-            before_overwrite(ev_ff2)   # with p = 0 the ff2 wgrad reads dz itself, which LayerNorm' now rewrites
+            below_bias = gr[f'l{l - 1}.ff2.b'] if l > 0 else None
+            drop_below = p_blk > 0 and l > 0
+            before_overwrite(ev_ff2)   # this layer's ff2 wgrad reads dz (p = 0) / dzm[0], which LayerNorm' now rewrites
             _lib.check(lib.ecgvit_layernorm_bwd(
                 w.dln.data_ptr(), w.x[l].data_ptr(), pf[p + 'ln1.w'].data_ptr(), w.stat1[l][0].data_ptr(),
                 w.stat1[l][1].data_ptr(), dy.data_ptr(), dz.data_ptr(), gr[p + 'ln1.w'].data_ptr(),
-                gr[p + 'ln1.b'].data_ptr(), _lib.ptr(below_bias), w.ln_scratch.data_ptr(), M, d, dt, st),
-                'layernorm_bwd')
+                gr[p + 'ln1.b'].data_ptr(), _lib.ptr(below_bias), w.ln_scratch.data_ptr(),
+                w.dzm[0].data_ptr() if drop_below else None, p_blk if drop_below else 0.0, s_ff2 - 4,
+                blk_seed if drop_below else None, M, d, dt, st), 'layernorm_bwd')
+            dzl = w.dzm[0] if drop_below else dz
             if m._after_layer_backward is not None:
                 before_overwrite(ev_qkv)  # the bucket of layer l is complete only when its side-stream wgrads are
                 m._after_layer_backward(l)

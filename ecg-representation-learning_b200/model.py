@@ -176,8 +176,6 @@ class EcgVit(nn.Module):
         self._loss_reduction = r
 
     def forward(self, sample_values: torch.FloatTensor, labels: torch.LongTensor = None):
-        if self.loss_weight:
-            raise NotImplementedError('per-label loss_weight (ecg_vit.py:144-147) is not implemented in the fused head')
         self._prepare(sample_values.device)
         need_grad = torch.is_grad_enabled() and labels is not None and any(p.requires_grad for p in self.parameters())
         if self.training and (self.config.hidden_dropout_prob > 0 or self.config.attention_probs_dropout_prob > 0):

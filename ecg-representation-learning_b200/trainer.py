@@ -134,7 +134,8 @@ class FusedTrainer:
         return out
 
     def _graph_step(self, sample_values, labels):
-        key = (tuple(sample_values.shape), tuple(labels.shape))
+        lw = self.model.loss_weight
+        key = (tuple(sample_values.shape), tuple(labels.shape), tuple(float(v) for v in lw) if lw else None)
         if self._graph is None or self._graph_key != key:
             self._static_x = torch.empty_like(sample_values)
             self._static_y = torch.empty(labels.shape, device=labels.device, dtype=torch.float32)

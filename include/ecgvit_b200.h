@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define ECGVIT_ABI_VERSION 2
+#define ECGVIT_ABI_VERSION 3
 
 enum { ECGVIT_F32 = 0, ECGVIT_BF16 = 1 };
 
@@ -67,12 +67,16 @@ int ecgvit_embed_assemble_bwd(const void *dtok, void *de, float *dcls, float *dp
 /* ---- nn.LayerNorm(d, eps) forward (PreNorm.norm / mlp_head[0]); saves per-row mean and rstd (fp32) */
 int ecgvit_layernorm_fwd(const void *x, const float *gamma, const float *beta, void *y, float *mean,
                          float *rstd, int M, int d, float eps, int dtype, void *stream);
-/* backward: dx = (dres ? dres : 0) + LN'(dy); dgamma += ..; dbeta += ..; if dcolsum: dcolsum += colsum(dx).
+/* backward: dx = (dres ? dres : 0) + LN'(dy); dgamma += ..; dbeta += ..
+ * Without dropout (dxm NULL or p = 0): if dcolsum: dcolsum += colsum(dx).
+ * With dropout (dx feeds a Linear through nn.Dropout, see "dropout" below): dxm = mask * dx / (1 - p) is written as
+ * well and dcolsum += colsum(dxm).
  * scratch: fp32 workspace of ecgvit_layernorm_bwd_scratch_floats(d) elements (per-CTA column partials) */
 int64_t ecgvit_layernorm_bwd_scratch_floats(int d);
 int ecgvit_layernorm_bwd(const void *dy, const void *x, const float *gamma, const float *mean,
                          const float *rstd, const void *dres, void *dx, float *dgamma, float *dbeta,
-                         float *dcolsum, float *scratch, int M, int d, int dtype, void *stream);
+                         float *dcolsum, float *scratch, void *dxm, float dropout_p, int dropout_stream,
+                         const uint32_t *dropout_seed, int M, int d, int dtype, void *stream);
 
 /* ---- dense contraction  C[m,n] = sum_k A(m,k) * B(n,k)  with fused epilogue.
  *      Replaces nn.Linear forward / its autograd dgrad / wgrad (vit_pytorch Attention.to_qkv, to_out[0],
@@ -114,19 +118,24 @@ int ecgvit_attention_bwd(const void *qkv, const void *o, const void *d_o, const 
                          int B, int N, int H, int dh, float scale, float dropout_p, int dropout_stream,
                          const uint32_t *dropout_seed, int dtype, void *stream);
 
-/* ---- CLS pool + mlp_head (LayerNorm + Linear(d -> n_class)) + nn.BCEWithLogitsLoss (ecg_vit.py:118,148).
+/* ---- CLS pool + mlp_head (LayerNorm + Linear(d -> n_class)) + nn.BCEWithLogitsLoss (ecg_vit.py:118,144-148).
  *      tok [B*N, d]; logits fp32 [B, n_class]; loss: scalar (mean / sum) or [B, n_class] (none).
- *      labels may be NULL (logits only).  xn/mean/rstd are saved for backward. */
+ *      labels may be NULL (logits only).  xn/mean/rstd are saved for backward.
+ *      loss_weight: NULL, or the reference's `EcgVit.loss_weight` table (device fp32[n_weight]): element (b, k) of
+ *      the loss is multiplied by loss_weight[(long)labels[b, k]] (ecg_vit.py:144-147 `weight[labels.long()]`; the
+ *      index is clamped to the table, where torch would raise); 'mean' still divides by B * n_class. */
 int ecgvit_head_fwd(const void *tok, const float *gamma, const float *beta, const float *w, const float *b,
-                    const float *labels, float *xn, float *mean, float *rstd, float *logits, float *loss,
-                    int B, int N, int d, int n_class, int reduction, float eps, int dtype, void *stream);
+                    const float *labels, const float *loss_weight, int n_weight, float *xn, float *mean,
+                    float *rstd, float *logits, float *loss, int B, int N, int d, int n_class, int reduction,
+                    float eps, int dtype, void *stream);
 /* backward for reduction mean|sum with upstream gradient `grad_scale` (a host scalar, normally 1):
- *      dlogits = grad_scale * (sigmoid(z) - y) [/ (B*n_class)];  dw += ..; db += ..; dgamma/dbeta += ..;
+ *      dlogits = grad_scale * weight * (sigmoid(z) - y) [/ (B*n_class)];  dw += ..; db += ..; dgamma/dbeta += ..;
  *      dtok is FULLY written: LN' rows at the CLS positions, zeros elsewhere; dcolsum += sum_b dtok[b,0,:] */
-int ecgvit_head_bwd(const void *tok, const float *gamma, const float *w, const float *labels, const float *xn,
-                    const float *mean, const float *rstd, const float *logits, void *dtok, float *dw,
-                    float *db, float *dgamma, float *dbeta, float *dcolsum, float *scratch, int B, int N, int d,
-                    int n_class, int reduction, float grad_scale, int dtype, void *stream);
+int ecgvit_head_bwd(const void *tok, const float *gamma, const float *w, const float *labels,
+                    const float *loss_weight, int n_weight, const float *xn, const float *mean,
+                    const float *rstd, const float *logits, void *dtok, float *dw, float *db, float *dgamma,
+                    float *dbeta, float *dcolsum, float *scratch, int B, int N, int d, int n_class, int reduction,
+                    float grad_scale, int dtype, void *stream);
 
 /* ---- dropout (nn.Dropout at the 5 sites per block + embedding of vit_pytorch; p wiring in ecg_vit.py:113-114).
  *      Counter-based: element `idx` of site `dropout_stream` is kept iff the 16 bits that hash(seed, stream,

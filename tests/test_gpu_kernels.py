@@ -171,11 +171,26 @@ def test_layernorm_fwd_bwd(lib, dtype, d):
     scratch = torch.empty(int(lib.ecgvit_layernorm_bwd_scratch_floats(d)), device='cuda')
     L.check(lib.ecgvit_layernorm_bwd(dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
                                      dres.data_ptr(), dx.data_ptr(), dg.data_ptr(), db.data_ptr(), dc.data_ptr(),
-                                     scratch.data_ptr(), M, d, dtype, stream()), 'ln_bwd')
+                                     scratch.data_ptr(), None, 0.0, 0, None, M, d, dtype, stream()), 'ln_bwd')
     want_dx = xr.grad + dres.float()
     assert rel(dx, want_dx) < (1e-5 if dtype == L.F32 else 5e-3)
     assert rel(dg, gr.grad) < 1e-4 and rel(db, br.grad) < 1e-4
     assert rel(dc, want_dx.sum(0)) < (1e-4 if dtype == L.F32 else 1e-3)  # column sums of the unrounded result
+    # the dropout variant: same dx plus dxm = mask * dx / (1 - p), column sums of the masked values
+    p, site = 0.25, 7
+    seed = torch.tensor([1234567], dtype=torch.int64, device='cuda').to(torch.int32)
+    dx2, dxm = torch.empty_like(dx), torch.empty_like(dx)
+    dg2, db2, dc2 = (torch.zeros(d, device='cuda') for _ in range(3))
+    L.check(lib.ecgvit_layernorm_bwd(dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                     dres.data_ptr(), dx2.data_ptr(), dg2.data_ptr(), db2.data_ptr(), dc2.data_ptr(),
+                                     scratch.data_ptr(), dxm.data_ptr(), p, site, seed.data_ptr(), M, d, dtype,
+                                     stream()), 'ln_bwd_drop')
+    assert torch.equal(dx2, dx) and rel(dg2, dg) < 1e-6 and rel(db2, db) < 1e-6
+    mult = L.dropout_keep_mask(1234567, site, p, torch.arange(M * d)).reshape(M, d).cuda()
+    want_m = want_dx * mult
+    assert rel(dxm, want_m) < (1e-5 if dtype == L.F32 else 5e-3)
+    assert bool(((dxm == 0) | (mult > 0)).all())
+    assert rel(dc2, want_m.sum(0)) < (1e-4 if dtype == L.F32 else 1e-3)
 
 
 @pytest.mark.parametrize('dtype', [L.F32, L.BF16])
@@ -207,8 +222,11 @@ def test_attention_fwd_bwd(lib, dtype, cfg):
 
 @pytest.mark.parametrize('dtype', [L.F32, L.BF16])
 @pytest.mark.parametrize('reduction', ['mean', 'sum'])
-def test_head_fwd_bwd(lib, dtype, reduction):
+@pytest.mark.parametrize('weighted', [False, True])
+def test_head_fwd_bwd(lib, dtype, reduction, weighted):
     td = DT[dtype]
+    table = torch.tensor([0.7, 3.5], device='cuda') if weighted else None  # EcgVit.loss_weight (ecg_vit.py:144-147)
+    tp, nw = (table.data_ptr(), 2) if weighted else (None, 0)
     B, N, d, C = 9, 11, 256, 71
     tok = torch.randn(B * N, d, device='cuda').to(td)
     gamma, beta = torch.randn(d, device='cuda'), torch.randn(d, device='cuda')
@@ -218,21 +236,22 @@ def test_head_fwd_bwd(lib, dtype, reduction):
     logits, loss = torch.empty(B, C, device='cuda'), torch.empty(1, device='cuda')
     red = L.REDUCTION[reduction]
     L.check(lib.ecgvit_head_fwd(tok.data_ptr(), gamma.data_ptr(), beta.data_ptr(), w.data_ptr(), b.data_ptr(),
-                                labels.data_ptr(), xn.data_ptr(), mean.data_ptr(), rstd.data_ptr(), logits.data_ptr(),
-                                loss.data_ptr(), B, N, d, C, red, 1e-5, dtype, stream()), 'head')
+                                labels.data_ptr(), tp, nw, xn.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                logits.data_ptr(), loss.data_ptr(), B, N, d, C, red, 1e-5, dtype, stream()), 'head')
+    ew = table[labels.long()] if weighted else None
     tr = tok.float().requires_grad_(True)
     pr = [t.clone().requires_grad_(True) for t in (gamma, beta, w, b)]
     cls = tr.reshape(B, N, d)[:, 0]
     z = torch.nn.functional.linear(torch.nn.functional.layer_norm(cls, (d,), pr[0], pr[1], 1e-5), pr[2], pr[3])
-    want_loss = torch.nn.functional.binary_cross_entropy_with_logits(z, labels, reduction=reduction)
+    want_loss = torch.nn.functional.binary_cross_entropy_with_logits(z, labels, weight=ew, reduction=reduction)
     assert rel(logits, z) < 1e-5 and rel(loss[0], want_loss) < 1e-5
     want_loss.backward()
     dtok = torch.full((B * N, d), 7.0, device='cuda').to(td)
     grads = [torch.zeros_like(t) for t in (w, b, gamma, beta)]
     dcol = torch.zeros(d, device='cuda')
     scratch = torch.empty(B * d + B * C, device='cuda')
-    L.check(lib.ecgvit_head_bwd(tok.data_ptr(), gamma.data_ptr(), w.data_ptr(), labels.data_ptr(), xn.data_ptr(),
-                                mean.data_ptr(), rstd.data_ptr(), logits.data_ptr(), dtok.data_ptr(),
+    L.check(lib.ecgvit_head_bwd(tok.data_ptr(), gamma.data_ptr(), w.data_ptr(), labels.data_ptr(), tp, nw,
+                                xn.data_ptr(), mean.data_ptr(), rstd.data_ptr(), logits.data_ptr(), dtok.data_ptr(),
                                 grads[0].data_ptr(), grads[1].data_ptr(), grads[2].data_ptr(), grads[3].data_ptr(),
                                 dcol.data_ptr(), scratch.data_ptr(), B, N, d, C, red, 1.0, dtype, stream()), 'head_bwd')
     tol = 1e-5 if dtype == L.F32 else 5e-3
@@ -243,9 +262,10 @@ def test_head_fwd_bwd(lib, dtype, reduction):
     # 'none' reduction, forward only
     ln = torch.empty(B, C, device='cuda')
     L.check(lib.ecgvit_head_fwd(tok.data_ptr(), gamma.data_ptr(), beta.data_ptr(), w.data_ptr(), b.data_ptr(),
-                                labels.data_ptr(), xn.data_ptr(), mean.data_ptr(), rstd.data_ptr(), logits.data_ptr(),
-                                ln.data_ptr(), B, N, d, C, L.REDUCTION['none'], 1e-5, dtype, stream()), 'head')
-    assert rel(ln, torch.nn.functional.binary_cross_entropy_with_logits(z, labels, reduction='none')) < 1e-5
+                                labels.data_ptr(), tp, nw, xn.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                logits.data_ptr(), ln.data_ptr(), B, N, d, C, L.REDUCTION['none'], 1e-5, dtype,
+                                stream()), 'head')
+    assert rel(ln, torch.nn.functional.binary_cross_entropy_with_logits(z, labels, weight=ew, reduction='none')) < 1e-5
 
 
 @pytest.mark.parametrize('dtype', [L.F32, L.BF16])
