@@ -47,11 +47,11 @@ __device__ __forceinline__ uint32_t sw64_offset(int lane, int j) {
 // Epilogue math for 32 consecutive accumulator columns of one row (thread = row).  Results are written as bf16 into
 // the warp's swizzled staging tile(s); for BIAS_RES / DGELU the tile already holds the aux operand (residual /
 // pre-activation), fetched by TMA while the mainloop was still running, and is updated in place.
-// The caller then issues one TMA store per tile (TMA clips rows >= M and columns >= N, so there are no guards here
-// except for the bias vector).
+// The caller then issues one TMA store per tile (TMA clips rows >= M and columns >= N, so there are no guards here).
 template <int MODE>
-__device__ __forceinline__ void epilogue_half16(const EpiParams &ep, int64_t row, int col_base, int N, int jbase,
-                                                const uint32_t r[16], uint8_t *tile0, uint8_t *tile1, int lane) {
+__device__ __forceinline__ void epilogue_half16(const EpiParams &ep, int64_t row, int col_base, int jbase,
+                                                const uint32_t r[16], uint8_t *tile0, uint8_t *tile1, int lane,
+                                                float bias_lane) {
     const bool drop = ep.drop.threshold != 0;  // kernel-uniform
     const uint32_t seed = drop ? __ldg(ep.drop.seed) : 0u;
 #pragma unroll
@@ -61,11 +61,11 @@ __device__ __forceinline__ void epilogue_half16(const EpiParams &ep, int64_t row
         float v[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[8 * jj + i]);
-        if (MODE != ECGVIT_EPI_DGELU && ep.bias != nullptr && col < N) {  // N % 8 == 0
-            const float4 b0 = __ldg(reinterpret_cast<const float4 *>(ep.bias + col));
-            const float4 b1 = __ldg(reinterpret_cast<const float4 *>(ep.bias + col + 4));
-            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-            v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+        if (MODE != ECGVIT_EPI_DGELU && ep.bias != nullptr) {
+            // lane c of the warp holds the bias of column c of this 32-column unit (fetched one tile ahead, so no
+            // global-load latency sits between the TMEM load and the math); 0 beyond N
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] += __shfl_sync(0xffffffffu, bias_lane, 8 * j + i);
         }
         const uint32_t soff = sw64_offset(lane, j);
         const uint32_t eidx = static_cast<uint32_t>(row * ep.ldo + col);  // element index of v[0] (even)
@@ -169,19 +169,20 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 
     if (warp == 0) {
         // ================================ TMA producer (both CTAs) ================================
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int u = cluster_id; u < num_units; u += num_clusters) {
-                const int tile_n = u % tiles_n;
-                const int tile_m = (u / tiles_n) % tiles_m;
-                const int split = u / (tiles_n * tiles_m);
-                const int kb0 = split * kb_per_split;
-                const int kb1 = min(kb0 + kb_per_split, kb_total);
-                const int row0 = tile_m * BM2 + rank * BM;          // this CTA's rows of A
-                const int col0 = tile_n * BN + rank * Cfg::B_HALF;  // this CTA's rows of B
-                for (int kb = kb0; kb < kb1; ++kb) {
-                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+        // the whole warp walks the loop (warp-uniform control flow and addresses); one elected lane issues
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int u = cluster_id; u < num_units; u += num_clusters) {
+            const int tile_n = u % tiles_n;
+            const int tile_m = (u / tiles_n) % tiles_m;
+            const int split = u / (tiles_n * tiles_m);
+            const int kb0 = split * kb_per_split;
+            const int kb1 = min(kb0 + kb_per_split, kb_total);
+            const int row0 = tile_m * BM2 + rank * BM;          // this CTA's rows of A
+            const int col0 = tile_n * BN + rank * Cfg::B_HALF;  // this CTA's rows of B
+            for (int kb = kb0; kb < kb1; ++kb) {
+                ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                if (ptx::elect_one()) {
                     uint8_t *sa = smem + stage * Cfg::STAGE_BYTES;
                     uint8_t *sb = sa + A_STAGE_BYTES;
                     if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
@@ -199,14 +200,21 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                         for (int j = 0; j < Cfg::B_LOAD_ROWS / 64; ++j)
                             ptx::tma_load_2d_2sm(sb + j * 8192, &tmap_b, &full_bar[stage], col0 + j * 64, kb * BK);
                     }
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
         // ================================ MMA issuer (leader CTA only) ============================
-        if (leader && lane == 0) {
+        if (leader) {
             constexpr uint32_t idesc = ptx::make_idesc_bf16(BM2, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+            // descriptors of stage 0 / k = 0; every other (stage, k) only moves the 14-bit start-address field
+            const uint32_t smem_base = ptx::smem_u32(smem);
+            const uint64_t da0 = A_MN ? ptx::make_smem_desc(smem_base, 8192, 1024) : ptx::make_smem_desc(smem_base, 16, 1024);
+            const uint64_t db0 = B_MN ? ptx::make_smem_desc(smem_base + A_STAGE_BYTES, 8192, 1024)
+                                      : ptx::make_smem_desc(smem_base + A_STAGE_BYTES, 16, 1024);
+            constexpr uint32_t A_KSTEP = (A_MN ? 2048 : 32) >> 4, B_KSTEP = (B_MN ? 2048 : 32) >> 4;
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
@@ -222,20 +230,20 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                 for (int kb = kb0; kb < kb1; ++kb) {
                     ptx::mbar_wait(&full_bar[stage], phase);
                     ptx::tcgen05_fence_after();
-                    const uint32_t sa = ptx::smem_u32(smem + stage * Cfg::STAGE_BYTES);
-                    const uint32_t sb = sa + A_STAGE_BYTES;
+                    if (ptx::elect_one()) {
+                        const uint32_t stage_off = static_cast<uint32_t>(stage * Cfg::STAGE_BYTES) >> 4;
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k) {
-                        const uint64_t da = A_MN ? ptx::make_smem_desc(sa + k * 2048, 8192, 1024)
-                                                 : ptx::make_smem_desc(sa + k * 32, 16, 1024);
-                        const uint64_t db = B_MN ? ptx::make_smem_desc(sb + k * 2048, 8192, 1024)
-                                                 : ptx::make_smem_desc(sb + k * 32, 16, 1024);
-                        ptx::umma_bf16_2sm(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                        for (int k = 0; k < BK / UMMA_K; ++k)
+                            ptx::umma_bf16_2sm(tmem_d, da0 + (stage_off + k * A_KSTEP), db0 + (stage_off + k * B_KSTEP),
+                                               idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                        ptx::umma_commit_2sm(&empty_bar[stage], 0b11);  // frees the stage in both CTAs
                     }
-                    ptx::umma_commit_2sm(&empty_bar[stage], 0b11);  // frees the stage in both CTAs
+                    __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                ptx::umma_commit_2sm(&tmem_full_bar[acc], 0b11);  // both CTAs' epilogues may drain their half
+                if (ptx::elect_one())
+                    ptx::umma_commit_2sm(&tmem_full_bar[acc], 0b11);  // both CTAs' epilogues may drain their half
+                __syncwarp();
             }
         }
     } else if (warp >= 4) {
@@ -245,8 +253,19 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         constexpr int UNITS = Cfg::UNITS_PER_WARP;
         uint8_t *tiles = epi_smem + (warp - 4) * Cfg::EPI_TILES_PER_WARP * Cfg::EPI_TILE_BYTES;
         uint64_t *my_aux_bar = aux_bar + (warp - 4) * Cfg::EPI_TILES_PER_WARP;
+        // bias of the warp's two 32-column units, one column per lane, loaded ONE TILE AHEAD
+        const bool has_bias = MODE != ECGVIT_EPI_DGELU && MODE != ECGVIT_EPI_ATOMIC_F32 && ep.bias != nullptr;
+        float next_bias0 = 0.f, next_bias1 = 0.f;
+        auto fetch_bias = [&](int unit) {
+            const int c = (unit % tiles_n) * BN + group * 64 + lane;
+            next_bias0 = (c < N) ? __ldg(ep.bias + c) : 0.f;
+            next_bias1 = (c + 32 < N) ? __ldg(ep.bias + c + 32) : 0.f;
+        };
+        if (has_bias && cluster_id < num_units) fetch_bias(cluster_id);
         int it = 0;
         for (int u = cluster_id; u < num_units; u += num_clusters, ++it) {
+            const float bias0 = next_bias0, bias1 = next_bias1;
+            if (has_bias && u + num_clusters < num_units) fetch_bias(u + num_clusters);
             const int tile_n = u % tiles_n;
             const int tile_m = (u / tiles_n) % tiles_m;
             const int acc = it & 1;
@@ -295,10 +314,16 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                     }
                 }
             } else {
+                // units entirely outside the matrix are skipped (warp-uniform)
+                const int n_units = (col_warp >= N) ? 0 : ((UNITS > 1 && col_warp + 32 < N) ? UNITS : 1);
+                // TMEM loads are software-pipelined over the 16-column halves: the load of half s + 1 is in flight
+                // while half s is being computed (two register buffers)
+                uint32_t ra[16], rb[16];
+                if (n_units > 0) ptx::tmem_ld_32x16(taddr0, ra);
 #pragma unroll 1
-                for (int i = 0; i < UNITS; ++i) {
+                for (int i = 0; i < n_units; ++i) {
                     const int col_base = col_warp + 32 * i;
-                    if (col_base >= N) break;  // warp-uniform: the whole unit is outside the matrix
+                    const float bias_lane = (i == 0) ? bias0 : bias1;
                     uint8_t *t0, *t1 = nullptr;
                     if (MODE == ECGVIT_EPI_BIAS_GELU) {
                         // one (u, h) tile pair per warp: unit 1 reuses it once unit 0's stores have read it
@@ -308,17 +333,16 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                         t0 = tiles + i * Cfg::EPI_TILE_BYTES;
                         if (kHasAux) ptx::mbar_wait(&my_aux_bar[i], it & 1);
                     }
-#pragma unroll 1
-                    for (int hh = 0; hh < 2; ++hh) {
-                        uint32_t r[16];
-                        ptx::tmem_ld_32x16(taddr0 + 32 * i + 16 * hh, r);
-                        ptx::tmem_ld_wait();
-                        if (MODE == ECGVIT_EPI_BIAS_GELU && i > 0 && hh == 0) {
-                            if (lane == 0) ptx::tma_store_wait_read<0>();
-                            __syncwarp();
-                        }
-                        epilogue_half16<MODE>(ep, row, col_base, N, 2 * hh, r, t0, t1, lane);
+                    ptx::tmem_ld_wait_bind(ra);
+                    ptx::tmem_ld_32x16(taddr0 + 32 * i + 16, rb);
+                    if (MODE == ECGVIT_EPI_BIAS_GELU && i > 0) {
+                        if (lane == 0) ptx::tma_store_wait_read<0>();
+                        __syncwarp();
                     }
+                    epilogue_half16<MODE>(ep, row, col_base, 0, ra, t0, t1, lane, bias_lane);
+                    ptx::tmem_ld_wait_bind(rb);
+                    if (i + 1 < n_units) ptx::tmem_ld_32x16(taddr0 + 32 * (i + 1), ra);
+                    epilogue_half16<MODE>(ep, row, col_base, 2, rb, t0, t1, lane, bias_lane);
                     ptx::fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
                     __syncwarp();
                     if (lane == 0) {

@@ -44,6 +44,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     }
 }
 
+// one lane of a fully converged warp (the lowest), chosen by the hardware: unlike `if (lane == 0)` the surrounding code
+// stays warp-uniform, so ptxas keeps addresses / descriptors in uniform registers instead of moving them there with
+// ELECT + R2UR + a BRA.U.ANY waterfall around every UTMALDG / UTCHMMA
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- proxies / fences -----------------------------------------------------------------------------
 __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -121,6 +134,15 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t r[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// same, and ties the 16 destination registers of an earlier tcgen05.ld to the wait, so that no use of them can be
+// scheduled above it while another (prefetching) tcgen05.ld is in flight
+__device__ __forceinline__ void tmem_ld_wait_bind(uint32_t r[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :
+                 : "memory");
 }
 
 // ---- UMMA descriptors (see cute/arch/mma_sm100_desc.hpp for the field layout) ---------------------
