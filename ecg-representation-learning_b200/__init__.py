@@ -9,7 +9,9 @@ from .config import EcgVitConfig
 from .model import EcgVit, ModelOutput
 from .trainer import FusedTrainer, get_train_args, lr_multiplier
 from .optim import FusedAdamW, clip_grad_norm_
+from .transform import InputPipeline
+from .metrics import get_accuracy, evaluate
 from . import _lib
 
 __all__ = ['EcgVitConfig', 'EcgVit', 'ModelOutput', 'FusedTrainer', 'FusedAdamW', 'clip_grad_norm_',
-           'get_train_args', 'lr_multiplier']
+           'get_train_args', 'lr_multiplier', 'InputPipeline', 'get_accuracy', 'evaluate']

@@ -37,6 +37,8 @@ SIGNATURES = {
     'ecgvit_last_error': [],
     'ecgvit_device_ok': [],
     'ecgvit_patchify': [c_void_p, c_void_p, c_int, c_int, c_int64, c_int, c_int, c_int, c_void_p],
+    'ecgvit_patchify_transform': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_int, c_int,
+                                  c_int, c_int, c_void_p],
     'ecgvit_embed_assemble': [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int, c_void_p,
                               c_int, c_void_p],
     'ecgvit_embed_assemble_bwd': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int,
@@ -50,6 +52,8 @@ SIGNATURES = {
                              c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_void_p, c_int, c_int, c_int,
                              c_void_p],
     'ecgvit_gemm': [POINTER(GemmArgs), c_void_p],
+    'ecgvit_eval_metrics_scratch_bytes': [c_int],
+    'ecgvit_eval_metrics': [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p],
     'ecgvit_attention_fwd': [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float, c_int,
                              c_void_p, c_int, c_void_p],
     'ecgvit_attention_bwd': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float,
@@ -64,7 +68,8 @@ SIGNATURES = {
     'ecgvit_grad_scale_by_clip': [c_void_p, c_int64, c_void_p, c_void_p, c_void_p],
     'ecgvit_cast_f32_to_bf16': [c_void_p, c_void_p, c_int64, c_void_p],
 }
-_RESTYPES = {'ecgvit_last_error': c_char_p, 'ecgvit_layernorm_bwd_scratch_floats': c_int64}
+_RESTYPES = {'ecgvit_last_error': c_char_p, 'ecgvit_layernorm_bwd_scratch_floats': c_int64,
+             'ecgvit_eval_metrics_scratch_bytes': c_int64}
 
 _lib = None
 
@@ -92,7 +97,7 @@ def last_error():
 
 
 # kernels launched per successful entry-point call (memsets are not kernels); feeds bench.py's `gpu_launches`
-KERNELS_PER_CALL = {'head_fwd': 2, 'head_bwd': 3, 'layernorm_bwd': 2, 'grad_sumsq': 2}
+KERNELS_PER_CALL = {'head_fwd': 2, 'head_bwd': 3, 'layernorm_bwd': 2, 'grad_sumsq': 2, 'eval_metrics': 3}
 launch_counter = [0]
 
 

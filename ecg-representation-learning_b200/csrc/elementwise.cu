@@ -26,6 +26,39 @@ __global__ void patchify_kernel(const float *__restrict__ x, T *__restrict__ a, 
     for (int i = threadIdx.x; i < PC; i += blockDim.x) out[i] = from_f32<T>(tile[i]);
 }
 
+// patchify with the reference's input pipeline fused in front of it (preprocess/transform.py, applied per record by
+// EcgDataset.__getitem__ in this order): Normalize (x - mean[c]) / std[c]  ->  TimeEndPad (zeros from L_valid on)  ->
+// TimeOut (zeros on [start, start + len) of every lead of sample b).  IEEE subtract / divide, so fp32 results are
+// bit-identical to numpy's; the transformed signal itself is never written to memory.
+template <typename T>
+__global__ void patchify_transform_kernel(const float *__restrict__ x, const float *__restrict__ mean,
+                                          const float *__restrict__ stdev, const int *__restrict__ spans,
+                                          T *__restrict__ a, int C, int64_t x_ld, int L_valid, int n_patch, int P) {
+    extern __shared__ float tile[];  // [P*C] in output order
+    const int w = blockIdx.x % n_patch;
+    const int b = blockIdx.x / n_patch;
+    const int PC = P * C;
+    const float *xb = x + (int64_t)b * C * x_ld;
+    int cut0 = 0, cut1 = 0;  // zeroed span of this sample
+    if (spans != nullptr) {
+        cut0 = spans[2 * b];
+        cut1 = cut0 + spans[2 * b + 1];
+    }
+    for (int i = threadIdx.x; i < PC; i += blockDim.x) {
+        const int c = i / P, t = i - c * P;
+        const int pos = w * P + t;
+        float v = 0.f;
+        if (pos < L_valid && !(pos >= cut0 && pos < cut1)) {
+            v = xb[(int64_t)c * x_ld + pos];
+            if (mean != nullptr) v = __fdiv_rn(__fsub_rn(v, mean[c]), stdev[c]);
+        }
+        tile[t * C + c] = v;
+    }
+    __syncthreads();
+    T *out = a + (int64_t)blockIdx.x * PC;
+    for (int i = threadIdx.x; i < PC; i += blockDim.x) out[i] = from_f32<T>(tile[i]);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // tok[b,0,:] = cls + pos[0];  tok[b,1+w,:] = e[b*n+w,:] + pos[1+w,:]
 template <typename T>
@@ -494,6 +527,25 @@ int ecgvit_patchify(const float *x, void *a, int B, int C, int64_t x_ld, int n_p
         patchify_kernel<float><<<grid, 256, smem, as_stream(stream)>>>(x, (float *)a, C, x_ld, n_patch, P);
     else return fail(-1, "patchify: unknown dtype %d", dtype);
     return check_launch("patchify");
+}
+
+int ecgvit_patchify_transform(const float *x, const float *mean, const float *stdev, const int *spans, void *a, int B,
+                              int C, int64_t x_ld, int L_valid, int n_patch, int P, int dtype, void *stream) {
+    ECGVIT_REQUIRE(x && a && B > 0 && C > 0 && n_patch > 0 && P > 0, "patchify_transform: bad arguments");
+    ECGVIT_REQUIRE((mean == nullptr) == (stdev == nullptr), "patchify_transform: mean and std come together");
+    ECGVIT_REQUIRE(L_valid > 0 && L_valid <= x_ld, "patchify_transform: L_valid=%d outside (0, x_ld=%lld]", L_valid,
+                   (long long)x_ld);
+    ECGVIT_REQUIRE((int64_t)n_patch * P >= L_valid, "patchify_transform: n_patch*P=%d drops samples of L_valid=%d",
+                   n_patch * P, L_valid);
+    const size_t smem = (size_t)P * C * sizeof(float);
+    ECGVIT_REQUIRE(smem <= 48 * 1024, "patchify_transform: patch of %d x %d elements exceeds 48 KB staging", P, C);
+    const int grid = B * n_patch;
+    if (dtype == ECGVIT_BF16)
+        patchify_transform_kernel<bf16><<<grid, 256, smem, as_stream(stream)>>>(x, mean, stdev, spans, (bf16 *)a, C, x_ld, L_valid, n_patch, P);
+    else if (dtype == ECGVIT_F32)
+        patchify_transform_kernel<float><<<grid, 256, smem, as_stream(stream)>>>(x, mean, stdev, spans, (float *)a, C, x_ld, L_valid, n_patch, P);
+    else return fail(-1, "patchify_transform: unknown dtype %d", dtype);
+    return check_launch("patchify_transform");
 }
 
 int ecgvit_embed_assemble(const void *e, const float *cls, const float *pos, void *tok, int B, int n_patch, int d,

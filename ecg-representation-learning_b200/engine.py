@@ -39,6 +39,7 @@ class StepEngine:
         # device scalar holding this step's dropout seed (refreshed by the host before every training forward)
         self.device = model._flat_p.device
         self._lw_key = self._lw_table = None
+        self._spans = {}
         self.rng = torch.zeros(2, device=self.device, dtype=torch.int32)
         # Weight-gradient GEMMs do not feed the backward chain: issued on a side stream they become a parallel branch of
         # the step graph and fill the SMs that the chain's kernels leave idle (partial last waves, launch ramps,
@@ -150,7 +151,9 @@ class StepEngine:
         assert x.shape[1] == c.num_channels
         if x.stride(2) != 1 or x.stride(0) != x.shape[1] * x.stride(1):
             x = x.contiguous()
-        B, C, L = x.shape
+        B, C, L_in = x.shape
+        pipe = m.input_pipeline
+        L = L_in if pipe is None else pipe.padded_length(L_in)  # TimeEndPad happens inside the gather
         w = self.workspace(B, L)
         self._cur = w
         P, d, mlp, H = c.patch_size, c.hidden_size, c.intermediate_size, c.num_attention_heads
@@ -159,7 +162,16 @@ class StepEngine:
         wt = m._weights()  # GEMM operand views (bf16 shadow or fp32 master)
         pf = m._params_f32()  # fp32 master views (biases, LayerNorm, cls, pos, head)
 
-        _lib.check(lib.ecgvit_patchify(x.data_ptr(), w.a_patch.data_ptr(), B, C, x.stride(1), n, P, dt, st), 'patchify')
+        if pipe is None:
+            _lib.check(lib.ecgvit_patchify(x.data_ptr(), w.a_patch.data_ptr(), B, C, x.stride(1), n, P, dt, st),
+                       'patchify')
+        else:
+            # raw records in: Normalize -> TimeEndPad -> TimeOut (training only) fused into the gather
+            mean, std = pipe.device_stats(x.device)
+            spans = self.span_buffer(B) if (pipe.timeout is not None and m.training) else None
+            _lib.check(lib.ecgvit_patchify_transform(x.data_ptr(), _lib.ptr(mean), _lib.ptr(std), _lib.ptr(spans),
+                                                     w.a_patch.data_ptr(), B, C, x.stride(1), L_in, n, P, dt, st),
+                       'patchify_transform')
         # e = a_patch @ We^T + be
         self._gemm(B * n, d, P * C, w.a_patch, P * C, 1, wt['embed.w'], P * C, 1, EPI_STORE, w.e, d,
                    bias=pf['embed.b'])
@@ -206,6 +218,18 @@ class StepEngine:
         if labels is not None:
             loss = w.loss_none if reduction == 'none' else w.loss[0]
         return loss, w.logits
+
+    def span_buffer(self, B):
+        """device int32 [B, 2] (start, length) of the TimeOut span of every record; a persistent buffer, so a captured
+        step reads whatever `set_spans` wrote last"""
+        buf = self._spans.get(B)
+        if buf is None:
+            buf = self._spans[B] = torch.zeros(B, 2, device=self.device, dtype=torch.int32)
+        return buf
+
+    def set_spans(self, spans):
+        """spans: int [B, 2] (host or device), see `InputPipeline.draw_spans`"""
+        self.span_buffer(spans.shape[0]).copy_(spans.to(torch.int32), non_blocking=True)
 
     def _loss_weight_table(self):
         """(device pointer, length) of `EcgVit.loss_weight` (ecg_vit.py:144-147), or (None, 0) when unset; the table

@@ -144,6 +144,9 @@ class EcgVit(nn.Module):
                        emb_dropout=config.attention_probs_dropout_prob)  # embedding (ecg_vit.py:114)
         self._loss_reduction = loss_reduction
         self.loss_weight = None
+        # optional `transform.InputPipeline`: forward then takes RAW records and the per-record transforms of the
+        # reference's dataset (Normalize / TimeEndPad / TimeOut) run inside the patch gather
+        self.input_pipeline = None
 
         C, L = config.num_channels, config.max_signal_length
         cls_nm = self.__class__.__qualname__
@@ -175,8 +178,15 @@ class EcgVit(nn.Module):
     def loss_reduction(self, r):
         self._loss_reduction = r
 
-    def forward(self, sample_values: torch.FloatTensor, labels: torch.LongTensor = None):
+    def forward(self, sample_values: torch.FloatTensor, labels: torch.LongTensor = None, time_out_spans=None):
+        """`time_out_spans` (only with an `input_pipeline` that has TimeOut, training mode): int [B, 2] (start, length)
+        per record; drawn on the host like the reference's TimeOut when omitted."""
         self._prepare(sample_values.device)
+        pipe = self.input_pipeline
+        if pipe is not None and pipe.timeout is not None and self.training:
+            if time_out_spans is None:
+                time_out_spans = pipe.draw_spans(sample_values.shape[0], pipe.padded_length(sample_values.shape[2]))
+            self._engine.set_spans(time_out_spans)
         need_grad = torch.is_grad_enabled() and labels is not None and any(p.requires_grad for p in self.parameters())
         if self.training and (self.config.hidden_dropout_prob > 0 or self.config.attention_probs_dropout_prob > 0):
             self._engine.new_dropout_seed()  # masks of this forward; its backward regenerates them from the same seed

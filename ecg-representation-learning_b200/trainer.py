@@ -114,12 +114,18 @@ class FusedTrainer:
                                               self.stats.data_ptr(), st), 'adamw_step')
         return loss, logits
 
-    def step(self, sample_values, labels):
+    def step(self, sample_values, labels, time_out_spans=None):
         """One optimisation step on device-resident fp32 inputs; returns (loss, logits) device tensors (no sync).
 
-        The returned tensors are views of workspace buffers: valid until the next step."""
+        The returned tensors are views of workspace buffers: valid until the next step.  With an `input_pipeline` on
+        the model, `sample_values` are raw records; `time_out_spans` as in `EcgVit.forward`."""
         self._ensure_state(sample_values.device)
         self._upload_hyper()
+        pipe = self.model.input_pipeline
+        if pipe is not None and pipe.timeout is not None and self.model.training:
+            if time_out_spans is None:
+                time_out_spans = pipe.draw_spans(sample_values.shape[0], pipe.padded_length(sample_values.shape[2]))
+            self.model._engine.set_spans(time_out_spans)  # a persistent device buffer: the captured graph reads it
         cfg = self.model.config
         if self.model.training and (cfg.hidden_dropout_prob > 0 or cfg.attention_probs_dropout_prob > 0):
             self.model._engine.new_dropout_seed()  # a device scalar: the captured graph reads the fresh value
@@ -135,7 +141,9 @@ class FusedTrainer:
 
     def _graph_step(self, sample_values, labels):
         lw = self.model.loss_weight
-        key = (tuple(sample_values.shape), tuple(labels.shape), tuple(float(v) for v in lw) if lw else None)
+        pipe = self.model.input_pipeline
+        key = (tuple(sample_values.shape), tuple(labels.shape), tuple(float(v) for v in lw) if lw else None,
+               None if pipe is None else (id(pipe), pipe.pad, pipe.timeout, self.model.training))
         if self._graph is None or self._graph_key != key:
             self._static_x = torch.empty_like(sample_values)
             self._static_y = torch.empty(labels.shape, device=labels.device, dtype=torch.float32)

@@ -53,6 +53,16 @@ int ecgvit_device_ok(void);
 int ecgvit_patchify(const float *x, void *a, int B, int C, int64_t x_ld, int n_patch, int P, int dtype,
                     void *stream);
 
+/* ---- the same gather with the reference's per-record input pipeline fused in front:
+ *      preprocess/transform.py:18-35 Normalize ((x - mean[c]) / std[c], fp32 IEEE, bit-identical to numpy),
+ *      :140-154 TimeEndPad (zeros from sample L_valid on, up to n_patch * P) and :175-185 TimeOut (zeros on
+ *      [spans[2b], spans[2b] + spans[2b+1]) of every lead of record b), in the order EcgDataset.__getitem__ /
+ *      ptb_dataset.py:132-149 apply them.  x [B, C, x_ld] raw fp32 records with L_valid <= x_ld samples per lead;
+ *      mean / std device fp32[C] or both NULL; spans device int32[B, 2] or NULL. */
+int ecgvit_patchify_transform(const float *x, const float *mean, const float *stdev, const int *spans, void *a,
+                              int B, int C, int64_t x_ld, int L_valid, int n_patch, int P, int dtype,
+                              void *stream);
+
 /* ---- CLS concat + positional add: replaces torch.cat(cls, x); x += pos_embedding[:, :n+1]
  *      tok[b,0,:] = cls + pos[0];  tok[b,1+w,:] = e[b*n_patch+w,:] + pos[1+w]  (e already holds the bias) */
 int ecgvit_embed_assemble(const void *e, const float *cls, const float *pos, void *tok, int B, int n_patch,
@@ -136,6 +146,19 @@ int ecgvit_head_bwd(const void *tok, const float *gamma, const float *w, const f
                     const float *rstd, const float *logits, void *dtok, float *dw, float *db, float *dgamma,
                     float *dbeta, float *dcolsum, float *scratch, int B, int N, int d, int n_class, int reduction,
                     float grad_scale, int dtype, void *stream);
+
+/* ---- evaluation metrics on the device: replaces the sklearn calls of
+ *      ecg_transformer/util/train.py:12-56 `get_accuracy(preds, labels)`.
+ *      preds (probabilities, fp32) and labels (multi-hot fp32) are [n_rows, n_class] device arrays.
+ *      out (device double[6 + n_class]): [0] binary_accuracy, [1] weighted_binary_accuracy,
+ *      [2] binary_negative_recall, [3] binary_positive_recall (names AND the swapped y_true / y_pred of
+ *      util/train.py:47-55 kept), [4] macro_auc over the classes that have both labels (NaN if none),
+ *      [5] how many such classes, [6 + c] AUROC of class c (NaN when undefined).  AUROC = exact integer
+ *      Mann-Whitney count (ties 1/2) / (n+ n-), what sklearn's roc_auc_score evaluates to.
+ *      scratch: ecgvit_eval_metrics_scratch_bytes(n_class) bytes of device memory (zeroed by the call). */
+int64_t ecgvit_eval_metrics_scratch_bytes(int n_class);
+int ecgvit_eval_metrics(const float *preds, const float *labels, int64_t n_rows, int n_class, int with_auc,
+                        void *scratch, double *out, void *stream);
 
 /* ---- dropout (nn.Dropout at the 5 sites per block + embedding of vit_pytorch; p wiring in ecg_vit.py:113-114).
  *      Counter-based: element `idx` of site `dropout_stream` is kept iff the 16 bits that hash(seed, stream,

@@ -155,3 +155,22 @@ def test_bucketed_reducer_world_size_2_gloo(tmp_path):
                                       stderr=subprocess.STDOUT, text=True))
     outs = [p.communicate(timeout=180)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), '\n'.join(outs)
+
+
+def test_input_pipeline_host_side_matches_reference_draws():
+    """InputPipeline.padded_length / draw_spans replay TimeEndPad's length rule and TimeOut's RNG calls
+    (transform.py:147-151,180-183): under the seed the golden vectors were made with, the spans are identical"""
+    import numpy as np
+    g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'input_transform.npz'))
+    for case in ('ragged', 'full_block', 'long'):
+        rec, k = g[f'{case}/records'], int(g[f'{case}/k'])
+        pipe = ecg_b200.InputPipeline(normalize=dict(mean=g['mean'], std=g['std']), pad=k, timeout=True)
+        Lp = pipe.padded_length(rec.shape[-1])
+        assert Lp == g[f'{case}/eval'].shape[-1]
+        torch.manual_seed(1234)
+        spans = pipe.draw_spans(rec.shape[0], Lp)
+        assert spans.dtype == torch.int32 and np.array_equal(spans.numpy(), g[f'{case}/spans'])
+    assert ecg_b200.InputPipeline(pad=50).padded_length(2500) == 2550
+    assert ecg_b200.InputPipeline().padded_length(2500) == 2500
+    with pytest.raises(AssertionError):
+        ecg_b200.InputPipeline(pad=True)

@@ -1,5 +1,7 @@
 """CPU tier: pins the travelling oracle against (a) the committed golden vectors generated through the reference's
 own wrapper and (b), where /root/reference exists, the reference wrapper itself."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -106,3 +108,56 @@ def test_oracle_matches_reference_wrapper():
         assert (c.hidden_size, c.num_hidden_layers, c.num_attention_heads, c.intermediate_size) == dims
     args = get_train_args()
     assert (args['learning_rate'], args['weight_decay'], args['warmup_ratio'], args['schedule']) == (3e-4, 1e-2, 0.05, 'cosine')
+
+
+# ---- input transforms: oracle/transforms.py pinned by vectors the reference's own classes produced
+@pytest.fixture(scope='module')
+def transform_golden():
+    return np.load(os.path.join(os.path.dirname(__file__), 'golden', 'input_transform.npz'))
+
+
+@pytest.mark.parametrize('case', ['ragged', 'full_block', 'long'])
+def test_transform_oracle_matches_reference_vectors(transform_golden, case):
+    from oracle import transforms
+    g = transform_golden
+    rec, k = g[f'{case}/records'], int(g[f'{case}/k'])
+    got_eval = transforms.pipeline(rec, g['mean'], g['std'], pad=k)
+    got_train = transforms.pipeline(rec, g['mean'], g['std'], pad=k, spans=g[f'{case}/spans'])
+    assert got_eval.dtype == np.float32
+    assert np.array_equal(got_eval, g[f'{case}/eval'])      # bit-exact
+    assert np.array_equal(got_train, g[f'{case}/train'])    # masking bit-exact
+    if case == 'full_block':
+        assert got_eval.shape[-1] == rec.shape[-1] + k      # TimeEndPad pads a whole block when L % k == 0
+
+
+def test_transform_oracle_matches_reference_classes_live():
+    """when the reference tree is present (build container), run its classes directly against the restatement"""
+    if not os.path.isdir('/root/reference/ecg_transformer'):
+        pytest.skip('reference tree not present')
+    import importlib
+    from oracle import transforms
+    ref_shim.install()
+    T = importlib.import_module('ecg_transformer.preprocess.transform')
+    rng = np.random.default_rng(5)
+    rec = rng.standard_normal((12, 333)).astype(np.float32)
+    mean, std = rng.standard_normal(12) * 0.05, rng.random(12) * 0.3 + 0.1
+    want = T.TimeEndPad(64, pad_kwargs=dict(mode='constant', constant_values=0))(T.Normalize(mean=mean, std=std)(rec))
+    torch.manual_seed(9)
+    want_train = T.TimeOut()(want.copy())
+    torch.manual_seed(9)
+    s, l = transforms.draw_time_out_span(want.shape[-1])
+    got = transforms.pipeline(rec[None], mean, std, pad=64, spans=[(s, l)])[0]
+    assert np.array_equal(got, want_train)
+
+
+# ---- evaluation metrics (SURVEY 8f rank 2): oracle/metrics.py pinned by the reference's own get_accuracy outputs
+@pytest.mark.parametrize('case', ['sparse', 'ties', 'tiny'])
+def test_metrics_oracle_matches_reference_vectors(case):
+    from oracle import metrics
+    g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'eval_metrics.npz'))
+    scalars, per_class = metrics.get_accuracy(g[f'{case}/preds'], g[f'{case}/labels'])
+    assert np.allclose(scalars, g[f'{case}/scalars'], rtol=1e-12, atol=0)
+    want = g[f'{case}/per_class_auc']
+    assert np.array_equal(np.isnan(per_class), np.isnan(want))
+    assert np.allclose(per_class[~np.isnan(want)], want[~np.isnan(want)], rtol=1e-12, atol=0)
+    assert np.isnan(per_class[5]) and np.isnan(per_class[9])      # single-label classes are filtered (util/train.py:29)
