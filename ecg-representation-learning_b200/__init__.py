@@ -6,7 +6,7 @@ The directory name follows the build contract (`ecg-representation-learning_b200
 through the shim at the repo root.
 """
 from .config import EcgVitConfig
-from .model import EcgVit, ModelOutput
+from .model import EcgVit, ModelOutput, Recorder
 from .trainer import FusedTrainer, get_train_args, lr_multiplier
 from .optim import FusedAdamW, clip_grad_norm_
 from .transform import InputPipeline
@@ -14,4 +14,4 @@ from .metrics import get_accuracy, evaluate
 from . import _lib
 
 __all__ = ['EcgVitConfig', 'EcgVit', 'ModelOutput', 'FusedTrainer', 'FusedAdamW', 'clip_grad_norm_',
-           'get_train_args', 'lr_multiplier', 'InputPipeline', 'get_accuracy', 'evaluate']
+           'get_train_args', 'lr_multiplier', 'InputPipeline', 'Recorder', 'get_accuracy', 'evaluate']

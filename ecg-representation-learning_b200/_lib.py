@@ -52,6 +52,7 @@ SIGNATURES = {
                              c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_void_p, c_int, c_int, c_int,
                              c_void_p],
     'ecgvit_gemm': [POINTER(GemmArgs), c_void_p],
+    'ecgvit_attention_probs': [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_int64, c_int, c_void_p],
     'ecgvit_eval_metrics_scratch_bytes': [c_int],
     'ecgvit_eval_metrics': [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p],
     'ecgvit_attention_fwd': [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float, c_int,

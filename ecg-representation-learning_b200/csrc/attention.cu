@@ -13,9 +13,79 @@ int attention_bwd_mma(const void *qkv, const void *o, const void *d_o, const flo
 bool attention_mma_supported(int N, int dh);
 }  // namespace ecgvit
 
+namespace ecgvit {
+namespace {
+
+// Slow path for vit_pytorch's Recorder (hooks Attention.attend; reference use ecg_vit.py:176-193): the softmax
+// probabilities themselves, which the training kernels never materialise.  One warp per (b, h, query row): a lane owns
+// keys lane, lane + 32, ...; raw scores are parked in the output row, then exponentiated and normalised in place.
+template <typename T>
+__global__ void __launch_bounds__(128) attention_probs_kernel(const T *__restrict__ qkv, float *__restrict__ probs,
+                                                               int B, int N, int H, int dh, float scale,
+                                                               int64_t batch_stride) {
+    extern __shared__ float s_q[];  // [4 warps][dh]
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t row = (int64_t)blockIdx.x * 4 + wib;  // (b * H + h) * N + i
+    if (row >= (int64_t)B * H * N) return;
+    const int i = (int)(row % N);
+    const int h = (int)((row / N) % H);
+    const int64_t b = row / ((int64_t)N * H);
+    const int inner = H * dh;
+    const int64_t ld = 3 * (int64_t)inner;
+    float *q = s_q + wib * dh;
+    const T *qrow = qkv + (b * N + i) * ld + h * dh;
+    for (int c = lane; c < dh; c += 32) q[c] = to_f32(qrow[c]);
+    __syncwarp();
+    float *out = probs + b * batch_stride + ((int64_t)h * N + i) * N;
+    float mx = -INFINITY;
+    for (int j = lane; j < N; j += 32) {
+        const T *krow = qkv + (b * N + j) * ld + inner + h * dh;
+        float acc = 0.f;
+        for (int c = 0; c < dh; c += 8) {
+            float kv[8];
+            load8(krow + c, kv);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc = fmaf(q[c + k], kv[k], acc);
+        }
+        acc *= scale;
+        out[j] = acc;
+        mx = fmaxf(mx, acc);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < N; j += 32) {
+        const float e = expf(out[j] - mx);
+        out[j] = e;
+        sum += e;
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.0f / sum;
+    for (int j = lane; j < N; j += 32) out[j] *= inv;
+}
+
+}  // namespace
+}  // namespace ecgvit
+
 using namespace ecgvit;
 
 extern "C" {
+
+int ecgvit_attention_probs(const void *qkv, float *probs, int B, int N, int H, int dh, float scale,
+                           int64_t batch_stride, int dtype, void *stream) {
+    ECGVIT_REQUIRE(qkv && probs && B > 0 && N > 0 && H > 0, "attention_probs: bad arguments");
+    ECGVIT_REQUIRE(dh % 8 == 0, "attention_probs: head dim %d must be a multiple of 8", dh);
+    ECGVIT_REQUIRE(batch_stride >= (int64_t)H * N * N, "attention_probs: batch stride %lld < H*N*N",
+                   (long long)batch_stride);
+    const int64_t rows = (int64_t)B * H * N;
+    const unsigned grid = (unsigned)((rows + 3) / 4);
+    const size_t smem = 4 * (size_t)dh * sizeof(float);
+    if (dtype == ECGVIT_BF16)
+        attention_probs_kernel<bf16><<<grid, 128, smem, as_stream(stream)>>>((const bf16 *)qkv, probs, B, N, H, dh, scale, batch_stride);
+    else if (dtype == ECGVIT_F32)
+        attention_probs_kernel<float><<<grid, 128, smem, as_stream(stream)>>>((const float *)qkv, probs, B, N, H, dh, scale, batch_stride);
+    else return fail(-1, "attention_probs: unknown dtype %d", dtype);
+    return check_launch("attention_probs");
+}
 
 int ecgvit_attention_fwd(const void *qkv, void *o, float *lse, int B, int N, int H, int dh, float scale,
                          float dropout_p, int dropout_stream, const uint32_t *dropout_seed, int dtype, void *stream) {

@@ -141,8 +141,10 @@ class StepEngine:
         return w
 
     # ---- forward ---------------------------------------------------------------------------------
-    def forward(self, sample_values, labels=None, reduction='mean'):
-        """sample_values: fp32 cuda [B, C, L]; returns (loss | None, logits) as views of workspace buffers."""
+    def forward(self, sample_values, labels=None, reduction='mean', record_attention=False):
+        """sample_values: fp32 cuda [B, C, L]; returns (loss | None, logits) as views of workspace buffers.
+        record_attention: also materialise every layer's softmax probabilities (slow path for `Recorder`); they are
+        left in `self.recorded_attention`, fp32 [B, layers, heads, N, N]."""
         m, lib, st = self.model, self.lib, self._stream
         c = m.config
         dt = m._dtype_code
@@ -191,6 +193,13 @@ class StepEngine:
                                                 w.ln1[l].data_ptr(), w.stat1[l][0].data_ptr(), w.stat1[l][1].data_ptr(),
                                                 M, d, LN_EPS, dt, st), 'layernorm_fwd')
             self._gemm(M, 3 * inner, d, w.ln1[l], d, 1, wt[p + 'qkv.w'], d, 1, EPI_STORE, w.qkv[l], 3 * inner)
+            if record_attention:
+                if l == 0:
+                    self.recorded_attention = torch.empty(B, c.num_hidden_layers, H, N, N, device=x.device,
+                                                          dtype=torch.float32)
+                rec = self.recorded_attention
+                _lib.check(lib.ecgvit_attention_probs(w.qkv[l].data_ptr(), rec[:, l].data_ptr(), B, N, H, dh, scale,
+                                                      rec.stride(0), dt, st), 'attention_probs')
             _lib.check(lib.ecgvit_attention_fwd(w.qkv[l].data_ptr(), w.o[l].data_ptr(), w.lse[l].data_ptr(), B, N, H, dh,
                                                 scale, p_blk, s_att, blk_seed, dt, st), 'attention_fwd')
             self._gemm(M, d, inner, w.o[l], inner, 1, wt[p + 'out.w'], inner, 1, EPI_BIAS_RES, w.y[l], d,

@@ -10,6 +10,8 @@ clipping, AdamW and the DDP all-reduce are single passes over contiguous memory.
 """
 from collections import namedtuple, OrderedDict
 
+import weakref
+
 import torch
 from torch import nn
 
@@ -142,6 +144,7 @@ class EcgVit(nn.Module):
                        channels=config.num_channels, dim_head=hd_sz // n_head,
                        dropout=config.hidden_dropout_prob,              # attention + feed-forward (ecg_vit.py:113)
                        emb_dropout=config.attention_probs_dropout_prob)  # embedding (ecg_vit.py:114)
+        self.vit._owner = weakref.ref(self)  # lets `Recorder(model.vit)` reach the kernels (not a module: no cycle)
         self._loss_reduction = loss_reduction
         self.loss_weight = None
         # optional `transform.InputPipeline`: forward then takes RAW records and the per-record transforms of the
@@ -294,3 +297,45 @@ class EcgVit(nn.Module):
     def _grad_views(self):
         names = self._short_names()
         return [self._views_g[k] for k in names.values()]
+
+
+class Recorder(nn.Module):
+    """`vit_pytorch.recorder.Recorder` for the fused model: `Recorder(model.vit)(img)` returns
+    `(logits, attns[b, layers, heads, n, n])`, the per-layer softmax probabilities the reference's `EcgVitVisualizer`
+    reads (`ecg_vit.py:176-193`; `img` is `[B, C, 1, L]`, the dummy height axis the reference adds).  vit_pytorch
+    collects them with forward hooks on `Attention.attend`; here a slow-path kernel writes them next to the fused
+    attention (which never materialises them).  Dropout is not applied to the recorded probabilities (the hook sits on
+    the Softmax), and the pass runs in whatever mode the model is in, as in vit_pytorch."""
+
+    def __init__(self, vit, device=None):
+        super().__init__()
+        owner = getattr(vit, '_owner', None)
+        if owner is None or owner() is None:
+            raise RuntimeError('Recorder needs the `.vit` of an ecg_b200.EcgVit')
+        self.vit = vit
+        self.device = device
+        self.ejected = False
+        self.recordings = []
+
+    def eject(self):
+        self.ejected = True
+        self.recordings = []
+        return self.vit
+
+    def clear(self):
+        self.recordings = []
+
+    def forward(self, img):
+        assert not self.ejected, 'recorder has been ejected, cannot be used anymore'
+        self.clear()
+        model = self.vit._owner()
+        assert img.dim() == 4 and img.shape[2] == 1, 'expected [B, C, 1, L] (height axis of 1, ecg_vit.py:141)'
+        model._prepare(img.device)
+        if model.training and (model.config.hidden_dropout_prob > 0 or model.config.attention_probs_dropout_prob > 0):
+            model._engine.new_dropout_seed()
+        with torch.no_grad():
+            _, logits = model._engine.forward(img.squeeze(2), None, model.loss_reduction, record_attention=True)
+        attns = model._engine.recorded_attention
+        target = self.device if self.device is not None else img.device
+        self.recordings = [attns[:, l] for l in range(attns.shape[1])]
+        return logits.clone(), attns.to(target)

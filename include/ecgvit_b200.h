@@ -128,6 +128,12 @@ int ecgvit_attention_bwd(const void *qkv, const void *o, const void *d_o, const 
                          int B, int N, int H, int dh, float scale, float dropout_p, int dropout_stream,
                          const uint32_t *dropout_seed, int dtype, void *stream);
 
+/* slow path for vit_pytorch's Recorder / the reference's EcgVitVisualizer (ecg_vit.py:176-193): the softmax
+ * probabilities of one layer, fp32, probs[b * batch_stride + (h * N + i) * N + j] (no dropout: Recorder hooks
+ * `attend`, the Softmax itself).  batch_stride >= H*N*N lets a [B, layers, H, N, N] tensor be filled layer by layer. */
+int ecgvit_attention_probs(const void *qkv, float *probs, int B, int N, int H, int dh, float scale,
+                           int64_t batch_stride, int dtype, void *stream);
+
 /* ---- CLS pool + mlp_head (LayerNorm + Linear(d -> n_class)) + nn.BCEWithLogitsLoss (ecg_vit.py:118,144-148).
  *      tok [B*N, d]; logits fp32 [B, n_class]; loss: scalar (mean / sum) or [B, n_class] (none).
  *      labels may be NULL (logits only).  xn/mean/rstd are saved for backward.

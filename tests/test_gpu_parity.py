@@ -280,3 +280,66 @@ def test_base_model_full_batch_properties():
     tr.check_finite()
     assert np.isfinite(l) and l < l0
     assert torch.equal(model._shadow, model._flat_p.bfloat16())
+
+
+# ---- Recorder slow path + checkpoint round trip ---------------------------------------------------
+@pytest.mark.parametrize('dtype', ['fp32', 'bf16'])
+def test_recorder_attention_maps_match_oracle(dtype):
+    from oracle.vit_restated import Recorder as OracleRecorder
+    oracle, model, x, _ = make_pair(GOLDEN_CFG, dtype, 2)
+    oracle.eval(), model.eval()
+    rec_o = OracleRecorder(oracle.vit)
+    with torch.no_grad():
+        want_logits, want_attn = rec_o(x.unsqueeze(-2))                 # the call of ecg_vit.py:177-179
+    rec_o.eject()
+    rec = ecg_b200.Recorder(model.vit)
+    logits, attn = rec(x.cuda().unsqueeze(-2))
+    assert attn.shape == want_attn.shape                                # (b, layers, heads, n, n)
+    tol = FP32_TOL if dtype == 'fp32' else BF16_TOL
+    assert rel(attn, want_attn) < tol and rel(logits, want_logits) < tol
+    assert float((attn.sum(-1) - 1).abs().max()) < 1e-5
+    # the roll-out of EcgVitVisualizer.__call__ (ecg_vit.py:184-193) on top of both
+    def rollout(a):
+        a = a[0].double().cpu().mean(dim=0)
+        a = a + torch.eye(a.size(1), dtype=a.dtype)
+        a = a / a.sum(dim=-1, keepdim=True)
+        res = torch.empty_like(a)
+        res[0] = a[0]
+        for i in range(1, a.size(0)):
+            res[i] = a[i] @ a[i - 1]
+        res = res[:, 0, 1:]
+        return res / res.max()
+    assert rel(rollout(attn), rollout(want_attn)) < tol
+    assert rec.eject() is model.vit
+    with pytest.raises(AssertionError):
+        rec(x.cuda().unsqueeze(-2))
+    out = model(sample_values=x.cuda())                                 # the fused path is untouched afterwards
+    assert rel(out.logits, want_logits) < tol
+
+
+def test_reference_format_checkpoint_round_trip(tmp_path):
+    """train.py:297-300 saves `model.state_dict()`; ecg_vit.py:152-161 loads it with strict=True"""
+    oracle, model, x, y = make_pair(GOLDEN_CFG, 'fp32', 2)
+    path = tmp_path / 'model - reference format.pt'
+    torch.save(oracle.state_dict(), path)                               # what the reference trainer writes
+    fresh = EcgVit(config=EcgVitConfig(compute_dtype='fp32', **GOLDEN_CFG))
+    fresh.load_state_dict(torch.load(path, map_location='cpu'), strict=True)
+    fresh.cuda().eval()
+    oracle.eval()
+    with torch.no_grad():
+        want = oracle(sample_values=x, labels=y)
+    got = fresh(sample_values=x.cuda(), labels=y.cuda())
+    assert rel(got.logits, want.logits) < FP32_TOL
+    # and back: a checkpoint written by the fused model (after a fused step) loads into the reference-side module
+    tr = FusedTrainer(fresh.train(), use_cuda_graph=False, data_parallel=False)
+    tr.step(x.cuda(), y.cuda())
+    path2 = tmp_path / 'model - fused.pt'
+    torch.save(fresh.state_dict(), path2)
+    sd = torch.load(path2, map_location='cpu')
+    assert list(sd.keys()) == list(oracle.state_dict().keys())
+    oracle.load_state_dict(sd, strict=True)
+    oracle.eval(), fresh.eval()
+    with torch.no_grad():
+        want = oracle(sample_values=x, labels=y)
+    got = fresh(sample_values=x.cuda(), labels=y.cuda())
+    assert rel(got.logits, want.logits) < FP32_TOL
