@@ -343,3 +343,31 @@ def test_reference_format_checkpoint_round_trip(tmp_path):
         want = oracle(sample_values=x, labels=y)
     got = fresh(sample_values=x.cuda(), labels=y.cuda())
     assert rel(got.logits, want.logits) < FP32_TOL
+
+
+@pytest.mark.parametrize('reduction', ['mean', 'none'])
+def test_loss_weight_matches_reference_formula(reduction):
+    """ecg_vit.py:144-147: BCEWithLogitsLoss(weight=tensor(loss_weight)[labels.long()], reduction)"""
+    oracle, model, x, y = make_pair(GOLDEN_CFG, 'fp32', 4)
+    lw = [0.25, 4.0]
+    model.loss_weight = lw
+    model.loss_reduction = reduction
+    out = model(sample_values=x.cuda(), labels=y.cuda())
+    with torch.no_grad():
+        logits = oracle(sample_values=x).logits
+    want = nn.BCEWithLogitsLoss(weight=torch.tensor(lw)[y.long()], reduction=reduction)(input=logits, target=y)
+    assert rel(out.loss, want) < FP32_TOL
+    if reduction == 'mean':
+        out.loss.backward()
+        oracle.zero_grad()
+        lo = oracle(sample_values=x).logits
+        nn.BCEWithLogitsLoss(weight=torch.tensor(lw)[y.long()])(input=lo, target=y).backward()
+        for (k, p), (_, q) in zip(model.named_parameters(), oracle.named_parameters()):
+            assert rel(p.grad, q.grad) < 2e-4 and cosine(p.grad, q.grad) > 0.999999, k
+        # the fused trainer picks the table up too (and re-captures when it changes)
+        tr = FusedTrainer(model, use_cuda_graph=True, data_parallel=False)
+        l1, _ = tr.step(x.cuda(), y.cuda())
+        assert rel(l1, want) < FP32_TOL
+        model.loss_weight = None
+        l2, _ = tr.step(x.cuda(), y.cuda())
+        assert float(l2) != float(l1)
