@@ -37,6 +37,10 @@ SIGNATURES = {
     'ecgvit_last_error': [],
     'ecgvit_device_ok': [],
     'ecgvit_patchify': [c_void_p, c_void_p, c_int, c_int, c_int64, c_int, c_int, c_int, c_void_p],
+    'ecgvit_patchify_leads': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_int, c_int, c_int,
+                              c_int, c_int, c_void_p],
+    'ecgvit_pad_cols': [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p],
+    'ecgvit_unpad_add_f32': [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p],
     'ecgvit_patchify_transform': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_int, c_int,
                                   c_int, c_int, c_void_p],
     'ecgvit_embed_assemble': [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int, c_void_p,
@@ -57,8 +61,9 @@ SIGNATURES = {
     'ecgvit_eval_metrics': [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p],
     'ecgvit_attention_fwd': [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float, c_int,
                              c_void_p, c_int, c_void_p],
-    'ecgvit_attention_bwd': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float,
-                             c_float, c_int, c_void_p, c_int, c_void_p],
+    'ecgvit_attention_bwd_scratch_floats': [c_int, c_int, c_int, c_int, c_int],
+    'ecgvit_attention_bwd': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                             c_float, c_float, c_int, c_void_p, c_int, c_void_p],
     'ecgvit_head_fwd': [c_void_p] * 7 + [c_int] + [c_void_p] * 5 + [c_int, c_int, c_int, c_int, c_int, c_float, c_int,
                                                                      c_void_p],
     'ecgvit_head_bwd': [c_void_p] * 5 + [c_int] + [c_void_p] * 11 + [c_int, c_int, c_int, c_int, c_int, c_float, c_int,
@@ -70,7 +75,7 @@ SIGNATURES = {
     'ecgvit_cast_f32_to_bf16': [c_void_p, c_void_p, c_int64, c_void_p],
 }
 _RESTYPES = {'ecgvit_last_error': c_char_p, 'ecgvit_layernorm_bwd_scratch_floats': c_int64,
-             'ecgvit_eval_metrics_scratch_bytes': c_int64}
+             'ecgvit_eval_metrics_scratch_bytes': c_int64, 'ecgvit_attention_bwd_scratch_floats': c_int64}
 
 _lib = None
 
@@ -98,7 +103,7 @@ def last_error():
 
 
 # kernels launched per successful entry-point call (memsets are not kernels); feeds bench.py's `gpu_launches`
-KERNELS_PER_CALL = {'head_fwd': 2, 'head_bwd': 3, 'layernorm_bwd': 2, 'grad_sumsq': 2, 'eval_metrics': 3}
+KERNELS_PER_CALL = {'attention_bwd_flash': 3, 'head_fwd': 2, 'head_bwd': 3, 'layernorm_bwd': 2, 'grad_sumsq': 2, 'eval_metrics': 3}
 launch_counter = [0]
 
 

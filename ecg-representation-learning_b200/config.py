@@ -24,7 +24,7 @@ class EcgVitConfig(PretrainedConfig):
                  hidden_size: int = 512, num_hidden_layers: int = 8, num_attention_heads: int = 8,
                  intermediate_size: int = 2048, hidden_dropout_prob: float = 0.1,
                  attention_probs_dropout_prob: float = 0.1, num_class: int = 71,
-                 compute_dtype: str = 'bf16', **kwargs):
+                 compute_dtype: str = 'bf16', per_lead_tokens: bool = False, **kwargs):
         self.max_signal_length = max_signal_length
         self.patch_size = patch_size
         self.num_channels = num_channels
@@ -38,6 +38,10 @@ class EcgVitConfig(PretrainedConfig):
         # B200 knob: 'bf16' = tcgen05 contractions with fp32 accumulation/statistics (performance mode);
         #            'fp32' = FFMA contractions (parity mode, <= 1e-5 relative to the reference CPU model)
         self.compute_dtype = compute_dtype
+        # False = the reference wrapper (one token per time window, all leads inside it: ecg_vit.py:102-104).
+        # True  = BASELINE.json configs[3]: every lead is tokenised on its own (vit_pytorch ViT(image_size=(C, L),
+        #         patch_size=(1, P), channels=1)), N = C * L / P + 1 -- not constructible through the reference wrapper
+        self.per_lead_tokens = per_lead_tokens
         super().__init__(**kwargs)
         self.size = None
 

@@ -11,6 +11,18 @@ int attention_fwd_mma(const void *qkv, void *o, float *lse, int B, int N, int H,
 int attention_bwd_mma(const void *qkv, const void *o, const void *d_o, const float *lse, void *dqkv, int B, int N,
                       int H, int dh, float scale, DropoutParams drop, cudaStream_t stream);
 bool attention_mma_supported(int N, int dh);
+// attention_flash.cu: tiled kernels for N > 64 (bf16)
+int attention_fwd_flash(const void *qkv, void *o, float *lse, int B, int N, int H, int dh, float scale,
+                        DropoutParams drop, cudaStream_t stream);
+int attention_bwd_flash(const void *qkv, const void *o, const void *d_o, const float *lse, void *dqkv, float *dscratch,
+                        int B, int N, int H, int dh, float scale, DropoutParams drop, cudaStream_t stream);
+bool attention_flash_supported(int N, int dh);
+
+// the dropout counter of the attention probabilities is a 32-bit element index ((b*H + h) * Np + i) * Np + j
+static bool dropout_index_fits(int B, int N, int H) {
+    const int64_t Np = (N + 63) / 64 * 64;
+    return (int64_t)B * H * Np * Np <= ((int64_t)1 << 32);
+}
 }  // namespace ecgvit
 
 namespace ecgvit {
@@ -93,20 +105,34 @@ int ecgvit_attention_fwd(const void *qkv, void *o, float *lse, int B, int N, int
     ECGVIT_REQUIRE(qkv && o && lse && B > 0 && N > 0 && H > 0, "attention_fwd: bad arguments");
     ECGVIT_REQUIRE(dh % 8 == 0, "attention_fwd: head dim %d must be a multiple of 8", dh);
     ECGVIT_REQUIRE(dtype == ECGVIT_F32 || dtype == ECGVIT_BF16, "attention_fwd: unknown dtype %d", dtype);
+    ECGVIT_REQUIRE(drop.threshold == 0 || dropout_index_fits(B, N, H),
+                   "attention_fwd: B*H*Np*Np = %d*%d*Np^2 overflows the 32-bit dropout counter (N=%d)", B, H, N);
     if (dtype == ECGVIT_BF16 && attention_mma_supported(N, dh))
         return attention_fwd_mma(qkv, o, lse, B, N, H, dh, scale, drop, as_stream(stream));
+    if (dtype == ECGVIT_BF16 && attention_flash_supported(N, dh))
+        return attention_fwd_flash(qkv, o, lse, B, N, H, dh, scale, drop, as_stream(stream));
     return attention_fwd_simt(qkv, o, lse, B, N, H, dh, scale, dtype, drop, as_stream(stream));
 }
 
-int ecgvit_attention_bwd(const void *qkv, const void *o, const void *d_o, const float *lse, void *dqkv, int B,
-                         int N, int H, int dh, float scale, float dropout_p, int dropout_stream,
+int64_t ecgvit_attention_bwd_scratch_floats(int B, int N, int H, int dh, int dtype) {
+    return (dtype == ECGVIT_BF16 && attention_flash_supported(N, dh)) ? (int64_t)B * H * N : 0;
+}
+
+int ecgvit_attention_bwd(const void *qkv, const void *o, const void *d_o, const float *lse, void *dqkv, float *scratch,
+                         int B, int N, int H, int dh, float scale, float dropout_p, int dropout_stream,
                          const uint32_t *dropout_seed, int dtype, void *stream) {
     const DropoutParams drop = make_dropout(dropout_p, dropout_stream, dropout_seed);
     ECGVIT_REQUIRE(qkv && o && d_o && lse && dqkv && B > 0 && N > 0 && H > 0, "attention_bwd: bad arguments");
     ECGVIT_REQUIRE(dh % 8 == 0, "attention_bwd: head dim %d must be a multiple of 8", dh);
     ECGVIT_REQUIRE(dtype == ECGVIT_F32 || dtype == ECGVIT_BF16, "attention_bwd: unknown dtype %d", dtype);
+    ECGVIT_REQUIRE(drop.threshold == 0 || dropout_index_fits(B, N, H),
+                   "attention_bwd: B*H*Np*Np = %d*%d*Np^2 overflows the 32-bit dropout counter (N=%d)", B, H, N);
     if (dtype == ECGVIT_BF16 && attention_mma_supported(N, dh))
         return attention_bwd_mma(qkv, o, d_o, lse, dqkv, B, N, H, dh, scale, drop, as_stream(stream));
+    if (dtype == ECGVIT_BF16 && attention_flash_supported(N, dh)) {
+        ECGVIT_REQUIRE(scratch != nullptr, "attention_bwd: N=%d needs the scratch of ecgvit_attention_bwd_scratch_floats", N);
+        return attention_bwd_flash(qkv, o, d_o, lse, dqkv, scratch, B, N, H, dh, scale, drop, as_stream(stream));
+    }
     return attention_bwd_simt(qkv, o, d_o, lse, dqkv, B, N, H, dh, scale, dtype, drop, as_stream(stream));
 }
 

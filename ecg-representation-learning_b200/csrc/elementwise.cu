@@ -59,6 +59,60 @@ __global__ void patchify_transform_kernel(const float *__restrict__ x, const flo
     for (int i = threadIdx.x; i < PC; i += blockDim.x) out[i] = from_f32<T>(tile[i]);
 }
 
+// per-lead tokens (BASELINE.json configs[3]: vit_pytorch ViT(image_size=(C, L), patch_size=(1, P), channels=1) fed
+// [B, 1, C, L]): token (c, w) of record b holds the P samples x[b, c, w*P : (w+1)*P]; rows are padded with zeros to Kp
+// features (a multiple of 8) so the embedding GEMM's operand rows stay 16-byte aligned.  Same optional transforms as
+// patchify_transform_kernel.  One thread per output element.
+template <typename T>
+__global__ void patchify_leads_kernel(const float *__restrict__ x, const float *__restrict__ mean,
+                                      const float *__restrict__ stdev, const int *__restrict__ spans,
+                                      T *__restrict__ a, int64_t total, int C, int64_t x_ld, int L_valid, int n_w, int P,
+                                      int Kp) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int t = (int)(i % Kp);
+        const int64_t tok = i / Kp;  // (b * C + c) * n_w + w
+        const int w = (int)(tok % n_w);
+        const int64_t bc = tok / n_w;
+        const int c = (int)(bc % C);
+        const int64_t b = bc / C;
+        const int pos = w * P + t;
+        float v = 0.f;
+        if (t < P && pos < L_valid) {
+            bool cut = false;
+            if (spans != nullptr) {
+                const int s0 = spans[2 * b];
+                cut = pos >= s0 && pos < s0 + spans[2 * b + 1];
+            }
+            if (!cut) {
+                v = x[bc * x_ld + pos];
+                if (mean != nullptr) v = __fdiv_rn(__fsub_rn(v, mean[c]), stdev[c]);
+            }
+        }
+        a[i] = from_f32<T>(v);
+    }
+}
+
+// dst[r, 0:cols_padded] = src[r, 0:cols] followed by zeros
+template <typename T>
+__global__ void pad_cols_kernel(const T *__restrict__ src, T *__restrict__ dst, int64_t rows, int cols, int cols_padded) {
+    const int64_t total = rows * cols_padded;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % cols_padded);
+        const int64_t r = i / cols_padded;
+        dst[i] = c < cols ? src[r * cols + c] : from_f32<T>(0.f);
+    }
+}
+// dst[r, c] += src[r, c] for c < cols (src rows are cols_padded long)
+__global__ void unpad_add_kernel(const float *__restrict__ src, float *__restrict__ dst, int64_t rows, int cols,
+                                 int cols_padded) {
+    const int64_t total = rows * cols;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % cols);
+        const int64_t r = i / cols;
+        dst[i] += src[r * cols_padded + c];
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // tok[b,0,:] = cls + pos[0];  tok[b,1+w,:] = e[b*n+w,:] + pos[1+w,:]
 template <typename T>
@@ -546,6 +600,40 @@ int ecgvit_patchify_transform(const float *x, const float *mean, const float *st
         patchify_transform_kernel<float><<<grid, 256, smem, as_stream(stream)>>>(x, mean, stdev, spans, (float *)a, C, x_ld, L_valid, n_patch, P);
     else return fail(-1, "patchify_transform: unknown dtype %d", dtype);
     return check_launch("patchify_transform");
+}
+
+int ecgvit_patchify_leads(const float *x, const float *mean, const float *stdev, const int *spans, void *a, int B, int C,
+                          int64_t x_ld, int L_valid, int n_w, int P, int Kp, int dtype, void *stream) {
+    ECGVIT_REQUIRE(x && a && B > 0 && C > 0 && n_w > 0 && P > 0, "patchify_leads: bad arguments");
+    ECGVIT_REQUIRE((mean == nullptr) == (stdev == nullptr), "patchify_leads: mean and std come together");
+    ECGVIT_REQUIRE(Kp >= P && Kp % 8 == 0, "patchify_leads: padded row length %d must be a multiple of 8 >= P=%d", Kp, P);
+    ECGVIT_REQUIRE(L_valid > 0 && L_valid <= x_ld && (int64_t)n_w * P >= L_valid,
+                   "patchify_leads: L_valid=%d must fit x_ld=%lld and n_w*P=%d", L_valid, (long long)x_ld, n_w * P);
+    const int64_t total = (int64_t)B * C * n_w * Kp;
+    const int grid = grid_for(total, 256);
+    if (dtype == ECGVIT_BF16)
+        patchify_leads_kernel<bf16><<<grid, 256, 0, as_stream(stream)>>>(x, mean, stdev, spans, (bf16 *)a, total, C, x_ld, L_valid, n_w, P, Kp);
+    else if (dtype == ECGVIT_F32)
+        patchify_leads_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(x, mean, stdev, spans, (float *)a, total, C, x_ld, L_valid, n_w, P, Kp);
+    else return fail(-1, "patchify_leads: unknown dtype %d", dtype);
+    return check_launch("patchify_leads");
+}
+
+int ecgvit_pad_cols(const void *src, void *dst, int64_t rows, int cols, int cols_padded, int dtype, void *stream) {
+    ECGVIT_REQUIRE(src && dst && rows > 0 && cols > 0 && cols_padded >= cols, "pad_cols: bad arguments");
+    const int grid = grid_for(rows * cols_padded, 256);
+    if (dtype == ECGVIT_BF16)
+        pad_cols_kernel<bf16><<<grid, 256, 0, as_stream(stream)>>>((const bf16 *)src, (bf16 *)dst, rows, cols, cols_padded);
+    else if (dtype == ECGVIT_F32)
+        pad_cols_kernel<float><<<grid, 256, 0, as_stream(stream)>>>((const float *)src, (float *)dst, rows, cols, cols_padded);
+    else return fail(-1, "pad_cols: unknown dtype %d", dtype);
+    return check_launch("pad_cols");
+}
+
+int ecgvit_unpad_add_f32(const float *src, float *dst, int64_t rows, int cols, int cols_padded, void *stream) {
+    ECGVIT_REQUIRE(src && dst && rows > 0 && cols > 0 && cols_padded >= cols, "unpad_add: bad arguments");
+    unpad_add_kernel<<<grid_for(rows * cols, 256), 256, 0, as_stream(stream)>>>(src, dst, rows, cols, cols_padded);
+    return check_launch("unpad_add");
 }
 
 int ecgvit_embed_assemble(const void *e, const float *cls, const float *pos, void *tok, int B, int n_patch, int d,

@@ -93,7 +93,10 @@ class StepEngine:
         H = c.num_attention_heads
         inner = d  # dim_head = d // heads (ecg_vit.py:100)
         assert L % P == 0, f'signal length {L} must be a multiple of patch_size {P}'
-        n = L // P
+        per_lead = bool(getattr(c, 'per_lead_tokens', False))
+        n = L // P * (C if per_lead else 1)
+        K = P if per_lead else P * C            # features of one patch
+        Kp = (K + 7) // 8 * 8 if per_lead else K  # row length of the patch matrix (16-byte aligned rows for TMA)
         assert n + 1 <= m.vit.pos_embedding.shape[1], \
             f'{n} patches exceed the positional table ({m.vit.pos_embedding.shape[1] - 1})'
         N = n + 1
@@ -101,11 +104,15 @@ class StepEngine:
         depth = c.num_hidden_layers
         w = _Workspace()
         w.B, w.L, w.n, w.N, w.M = B, L, n, N, M
+        w.per_lead, w.K, w.Kp = per_lead, K, Kp
 
         def buf(*shape, dtype=T):
             return torch.empty(*shape, device=dev, dtype=dtype)
 
-        w.a_patch = buf(B * n, P * C)
+        w.a_patch = buf(B * n, Kp)
+        # per-lead tokens with P % 8 != 0: zero-padded copies of the embedding weight and of its gradient
+        w.embed_wpad = buf(d, Kp) if Kp != K else None
+        w.embed_gpad = buf(d, Kp, dtype=torch.float32) if Kp != K else None
         w.e = buf(B * n, d)
         w.x = [buf(M, d) for _ in range(depth + 1)]  # x[l] = input of block l; x[depth] = encoder output
         w.ln1 = [buf(M, d) for _ in range(depth)]
@@ -137,6 +144,8 @@ class StepEngine:
         # dropout-masked copies of the residual-stream gradients (only used when p > 0): one per site of a block
         w.dzm = [buf(M, d), buf(M, d)]
         w.ln_scratch = buf(int(self.lib.ecgvit_layernorm_bwd_scratch_floats(d)), dtype=torch.float32)
+        n_attn = int(self.lib.ecgvit_attention_bwd_scratch_floats(B, N, H, d // H, m._dtype_code))
+        w.attn_scratch = buf(n_attn, dtype=torch.float32) if n_attn > 0 else None
         self.ws[key] = w
         return w
 
@@ -164,19 +173,29 @@ class StepEngine:
         wt = m._weights()  # GEMM operand views (bf16 shadow or fp32 master)
         pf = m._params_f32()  # fp32 master views (biases, LayerNorm, cls, pos, head)
 
-        if pipe is None:
-            _lib.check(lib.ecgvit_patchify(x.data_ptr(), w.a_patch.data_ptr(), B, C, x.stride(1), n, P, dt, st),
-                       'patchify')
-        else:
+        mean = std = spans = None
+        if pipe is not None:
             # raw records in: Normalize -> TimeEndPad -> TimeOut (training only) fused into the gather
             mean, std = pipe.device_stats(x.device)
             spans = self.span_buffer(B) if (pipe.timeout is not None and m.training) else None
+        K, Kp = w.K, w.Kp
+        if w.per_lead:
+            _lib.check(lib.ecgvit_patchify_leads(x.data_ptr(), _lib.ptr(mean), _lib.ptr(std), _lib.ptr(spans),
+                                                 w.a_patch.data_ptr(), B, C, x.stride(1), L_in, L // P, P, Kp, dt, st),
+                       'patchify_leads')
+        elif pipe is None:
+            _lib.check(lib.ecgvit_patchify(x.data_ptr(), w.a_patch.data_ptr(), B, C, x.stride(1), n, P, dt, st),
+                       'patchify')
+        else:
             _lib.check(lib.ecgvit_patchify_transform(x.data_ptr(), _lib.ptr(mean), _lib.ptr(std), _lib.ptr(spans),
                                                      w.a_patch.data_ptr(), B, C, x.stride(1), L_in, n, P, dt, st),
                        'patchify_transform')
         # e = a_patch @ We^T + be
-        self._gemm(B * n, d, P * C, w.a_patch, P * C, 1, wt['embed.w'], P * C, 1, EPI_STORE, w.e, d,
-                   bias=pf['embed.b'])
+        w_embed = wt['embed.w']
+        if Kp != K:
+            _lib.check(lib.ecgvit_pad_cols(w_embed.data_ptr(), w.embed_wpad.data_ptr(), d, K, Kp, dt, st), 'pad_cols')
+            w_embed = w.embed_wpad
+        self._gemm(B * n, d, Kp, w.a_patch, Kp, 1, w_embed, Kp, 1, EPI_STORE, w.e, d, bias=pf['embed.b'])
         p_emb, p_blk = self._dropout_probs()
         w.p_emb, w.p_blk = p_emb, p_blk
         seed_ptr = self.rng.data_ptr()
@@ -339,8 +358,9 @@ class StepEngine:
             self._gemm(M, inner, d, dyl, d, 1, wt[p + 'out.w'], inner, 0, EPI_STORE, w.d_o, inner)
             before_overwrite(ev_qkv)   # dqkv
             _lib.check(lib.ecgvit_attention_bwd(w.qkv[l].data_ptr(), w.o[l].data_ptr(), w.d_o.data_ptr(),
-                                                w.lse[l].data_ptr(), w.dqkv.data_ptr(), B, N, H, dh, scale, p_blk, s_att,
-                                                blk_seed, dt, st), 'attention_bwd')
+                                                w.lse[l].data_ptr(), w.dqkv.data_ptr(), _lib.ptr(w.attn_scratch), B, N,
+                                                H, dh, scale, p_blk, s_att, blk_seed, dt, st),
+                       'attention_bwd' if w.attn_scratch is None else 'attention_bwd_flash')
             ev_qkv = wgrad(3 * inner, d, M, w.dqkv, 3 * inner, 0, w.ln1[l], d, 0, EPI_ATOMIC_F32, gr[p + 'qkv.w'], d,
                            split_k=0)
             self._gemm(M, d, 3 * inner, w.dqkv, 3 * inner, 1, wt[p + 'qkv.w'], d, 0, EPI_STORE, w.dln, d)
@@ -363,6 +383,12 @@ class StepEngine:
         _lib.check(lib.ecgvit_embed_assemble_bwd(dz.data_ptr(), w.de.data_ptr(), gr['cls'].data_ptr(),
                                                  gr['pos'].data_ptr(), gr['embed.b'].data_ptr(), B, n, d, p_emb, 0,
                                                  seed_ptr if p_emb > 0 else None, dt, st), 'embed_assemble_bwd')
-        self._gemm(d, P * C, B * n, w.de, d, 0, w.a_patch, P * C, 0, EPI_ATOMIC_F32, gr['embed.w'], P * C, split_k=0)
+        if w.Kp == w.K:
+            self._gemm(d, w.K, B * n, w.de, d, 0, w.a_patch, w.K, 0, EPI_ATOMIC_F32, gr['embed.w'], w.K, split_k=0)
+        else:
+            w.embed_gpad.zero_()
+            self._gemm(d, w.Kp, B * n, w.de, d, 0, w.a_patch, w.Kp, 0, EPI_ATOMIC_F32, w.embed_gpad, w.Kp, split_k=0)
+            _lib.check(lib.ecgvit_unpad_add_f32(w.embed_gpad.data_ptr(), gr['embed.w'].data_ptr(), d, w.K, w.Kp, st),
+                       'unpad_add')
         if m._after_layer_backward is not None:
             m._after_layer_backward(-1)

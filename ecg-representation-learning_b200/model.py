@@ -81,12 +81,13 @@ class ViT(nn.Module):
     """parameter container with vit_pytorch.ViT's attribute names / init distributions"""
 
     def __init__(self, *, signal_length, patch_size, num_classes, dim, depth, heads, mlp_dim, channels, dim_head,
-                 dropout, emb_dropout):
+                 dropout, emb_dropout, per_lead=False):
         super().__init__()
         assert signal_length % patch_size == 0, 'Image dimensions must be divisible by the patch size.'
-        n_patch = signal_length // patch_size
+        n_patch = signal_length // patch_size * (channels if per_lead else 1)
+        patch_dim = patch_size if per_lead else channels * patch_size
         self.to_patch_embedding = nn.Sequential(_Slot('Rearrange b c (w p) -> b w (p c) [fused]'),
-                                                nn.Linear(channels * patch_size, dim))
+                                                nn.Linear(patch_dim, dim))
         self.pos_embedding = nn.Parameter(torch.randn(1, n_patch + 1, dim))
         self.cls_token = nn.Parameter(torch.randn(1, 1, dim))
         self.dropout = _Slot(f'Dropout(p={emb_dropout})')
@@ -143,7 +144,8 @@ class EcgVit(nn.Module):
                        dim=hd_sz, depth=config.num_hidden_layers, heads=n_head, mlp_dim=config.intermediate_size,
                        channels=config.num_channels, dim_head=hd_sz // n_head,
                        dropout=config.hidden_dropout_prob,              # attention + feed-forward (ecg_vit.py:113)
-                       emb_dropout=config.attention_probs_dropout_prob)  # embedding (ecg_vit.py:114)
+                       emb_dropout=config.attention_probs_dropout_prob,  # embedding (ecg_vit.py:114)
+                       per_lead=bool(getattr(config, 'per_lead_tokens', False)))
         self.vit._owner = weakref.ref(self)  # lets `Recorder(model.vit)` reach the kernels (not a module: no cycle)
         self._loss_reduction = loss_reduction
         self.loss_weight = None

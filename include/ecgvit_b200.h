@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define ECGVIT_ABI_VERSION 3
+#define ECGVIT_ABI_VERSION 4
 
 enum { ECGVIT_F32 = 0, ECGVIT_BF16 = 1 };
 
@@ -62,6 +62,17 @@ int ecgvit_patchify(const float *x, void *a, int B, int C, int64_t x_ld, int n_p
 int ecgvit_patchify_transform(const float *x, const float *mean, const float *stdev, const int *spans, void *a,
                               int B, int C, int64_t x_ld, int L_valid, int n_patch, int P, int dtype,
                               void *stream);
+
+/* ---- per-lead tokens (BASELINE.json configs[3]; the oracle is vit_pytorch's ViT(image_size=(C, L),
+ *      patch_size=(1, P), channels=1) on [B, 1, C, L]): a[((b*C + c)*n_w + w), t] = x[b, c, w*P + t] for t < P and
+ *      0 for P <= t < Kp (Kp = P rounded up to 8: the embedding GEMM reads 16-byte aligned rows).  mean / std / spans
+ *      as in ecgvit_patchify_transform (all optional). */
+int ecgvit_patchify_leads(const float *x, const float *mean, const float *stdev, const int *spans, void *a, int B,
+                          int C, int64_t x_ld, int L_valid, int n_w, int P, int Kp, int dtype, void *stream);
+/* helpers of that mode: zero-padded copy of a [rows, cols] matrix to [rows, cols_padded] (the embedding weight),
+ * and dst[rows, cols] += src[rows, 0:cols] of a padded fp32 matrix (its gradient) */
+int ecgvit_pad_cols(const void *src, void *dst, int64_t rows, int cols, int cols_padded, int dtype, void *stream);
+int ecgvit_unpad_add_f32(const float *src, float *dst, int64_t rows, int cols, int cols_padded, void *stream);
 
 /* ---- CLS concat + positional add: replaces torch.cat(cls, x); x += pos_embedding[:, :n+1]
  *      tok[b,0,:] = cls + pos[0];  tok[b,1+w,:] = e[b*n_patch+w,:] + pos[1+w]  (e already holds the bias) */
@@ -124,9 +135,12 @@ int ecgvit_gemm(const ecgvit_gemm_args *g, void *stream);
 int ecgvit_attention_fwd(const void *qkv, void *o, float *lse, int B, int N, int H, int dh, float scale,
                          float dropout_p, int dropout_stream, const uint32_t *dropout_seed, int dtype,
                          void *stream);
+/* scratch: fp32 workspace of ecgvit_attention_bwd_scratch_floats(...) elements (rowsum(dO * O) of the tiled kernels
+ * that serve N > 64 in bf16; 0 -> may be NULL) */
+int64_t ecgvit_attention_bwd_scratch_floats(int B, int N, int H, int dh, int dtype);
 int ecgvit_attention_bwd(const void *qkv, const void *o, const void *d_o, const float *lse, void *dqkv,
-                         int B, int N, int H, int dh, float scale, float dropout_p, int dropout_stream,
-                         const uint32_t *dropout_seed, int dtype, void *stream);
+                         float *scratch, int B, int N, int H, int dh, float scale, float dropout_p,
+                         int dropout_stream, const uint32_t *dropout_seed, int dtype, void *stream);
 
 /* slow path for vit_pytorch's Recorder / the reference's EcgVitVisualizer (ecg_vit.py:176-193): the softmax
  * probabilities of one layer, fp32, probs[b * batch_stride + (h * N + i) * N + j] (no dropout: Recorder hooks

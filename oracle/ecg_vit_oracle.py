@@ -42,7 +42,7 @@ class OracleConfig:
 
     def __init__(self, max_signal_length=2560, patch_size=64, num_channels=12, hidden_size=512,
                  num_hidden_layers=8, num_attention_heads=8, intermediate_size=2048,
-                 hidden_dropout_prob=0.1, attention_probs_dropout_prob=0.1, num_class=71):
+                 hidden_dropout_prob=0.1, attention_probs_dropout_prob=0.1, num_class=71, per_lead_tokens=False):
         self.max_signal_length = max_signal_length
         self.patch_size = patch_size
         self.num_channels = num_channels
@@ -53,6 +53,9 @@ class OracleConfig:
         self.hidden_dropout_prob = hidden_dropout_prob
         self.attention_probs_dropout_prob = attention_probs_dropout_prob
         self.num_class = num_class
+        # BASELINE.json configs[3] ("per-lead tokens"): not constructible through the reference wrapper;
+        # its oracle is vit_pytorch's ViT(image_size=(C, L), patch_size=(1, P), channels=1) on [B, 1, C, L]
+        self.per_lead_tokens = per_lead_tokens
         self.size = None
 
     @classmethod
@@ -74,15 +77,20 @@ class OracleEcgVit(nn.Module):
         d, h = config.hidden_size, config.num_attention_heads
         assert d % h == 0  # ecg_vit.py:99
         self.config = config
+        self.per_lead = bool(getattr(config, 'per_lead_tokens', False))
         self.vit = ViT(  # ecg_vit.py:102-116; note the dropout wiring quirk (:113-114)
-            image_size=(1, config.max_signal_length), patch_size=(1, config.patch_size), num_classes=num_class,
+            image_size=(config.num_channels if self.per_lead else 1, config.max_signal_length),
+            patch_size=(1, config.patch_size), num_classes=num_class,
             dim=d, depth=config.num_hidden_layers, heads=h, mlp_dim=config.intermediate_size, pool='cls',
-            channels=config.num_channels, dim_head=d // h, dropout=config.hidden_dropout_prob,
-            emb_dropout=config.attention_probs_dropout_prob)
+            channels=1 if self.per_lead else config.num_channels, dim_head=d // h,
+            dropout=config.hidden_dropout_prob, emb_dropout=config.attention_probs_dropout_prob)
         self.loss_reduction = loss_reduction
 
     def forward(self, sample_values, labels=None):
-        logits = self.vit(sample_values.unsqueeze(-2))  # ecg_vit.py:141
+        if self.per_lead:
+            logits = self.vit(sample_values.unsqueeze(1))   # [B, 1, C, L]: leads are image rows, one channel
+        else:
+            logits = self.vit(sample_values.unsqueeze(-2))  # ecg_vit.py:141
         loss = None
         if labels is not None:
             loss = nn.functional.binary_cross_entropy_with_logits(logits, labels, reduction=self.loss_reduction)

@@ -366,8 +366,8 @@ def test_loss_weight_matches_reference_formula(reduction):
             assert rel(p.grad, q.grad) < 2e-4 and cosine(p.grad, q.grad) > 0.999999, k
         # the fused trainer picks the table up too (and re-captures when it changes)
         tr = FusedTrainer(model, use_cuda_graph=True, data_parallel=False)
-        l1, _ = tr.step(x.cuda(), y.cuda())
-        assert rel(l1, want) < FP32_TOL
+        l1 = float(tr.step(x.cuda(), y.cuda())[0])   # the returned tensors are views of workspace buffers
+        assert abs(l1 - float(want)) < FP32_TOL * float(want)
         model.loss_weight = None
-        l2, _ = tr.step(x.cuda(), y.cuda())
-        assert float(l2) != float(l1)
+        l2 = float(tr.step(x.cuda(), y.cuda())[0])
+        assert abs(l2 - l1) > 0.1 * l1
