@@ -165,3 +165,30 @@ def adamw_hyper(lr, beta1, beta2, eps, weight_decay, step, max_norm, grad_scale)
     vals = [lr, beta1, beta2, eps, weight_decay, bc1, bc2, max_norm, grad_scale,
             1.0 - beta1, 1.0 - beta2, 1.0 - lr * weight_decay, lr / bc1, bc2 ** 0.5]
     return vals + [0.0] * (16 - len(vals))
+
+
+class PinnedRing:
+    """Asynchronous upload of a few host scalars per step.  `dst.copy_(torch.tensor(values))` from pageable memory makes
+    the host wait for everything queued on the stream (i.e. the previous step), which exposes the whole host-side
+    launch cost between two graph replays; a ring of pinned staging slots lets the copy be truly asynchronous, and a
+    slot is rewritten only after the copy that read it has completed (its event), so the host can run several steps
+    ahead of the device."""
+
+    def __init__(self, numel, dtype, slots=8):
+        import torch
+        self.bufs = [torch.empty(numel, dtype=dtype).pin_memory() for _ in range(slots)]
+        self.events = [None] * slots
+        self.i = 0
+
+    def upload(self, dst, values):
+        import torch
+        i = self.i
+        self.i = (i + 1) % len(self.bufs)
+        if self.events[i] is not None:
+            self.events[i].synchronize()  # normally long complete
+        buf = self.bufs[i]
+        buf.copy_(torch.tensor(values, dtype=buf.dtype))
+        dst.copy_(buf, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self.events[i] = ev

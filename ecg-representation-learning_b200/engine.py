@@ -47,6 +47,7 @@ class StepEngine:
         self.side_stream = torch.cuda.Stream(device=model._flat_p.device) \
             if os.environ.get('ECGVIT_WGRAD_STREAM', '1') != '0' else None
         self._seed_counter = 0
+        self._seed_ring = None
         self.base_seed = 0x5EED
 
     def new_dropout_seed(self, seed=None):
@@ -54,7 +55,9 @@ class StepEngine:
         self._seed_counter += 1
         if seed is None:
             seed = (self.base_seed * 0x9E3779B1 + self._seed_counter * 0x85EBCA6B) & 0x7FFFFFFF
-        self.rng.copy_(torch.tensor([seed, self._seed_counter & 0x7FFFFFFF], dtype=torch.int32))
+        if self._seed_ring is None:
+            self._seed_ring = _lib.PinnedRing(2, torch.int32)
+        self._seed_ring.upload(self.rng, [seed, self._seed_counter & 0x7FFFFFFF])  # asynchronous: no host stall
         return seed
 
     def _dropout_probs(self):

@@ -64,6 +64,7 @@ class FusedTrainer:
         self.use_cuda_graph = use_cuda_graph
         self._state_ready = False
         self._graph = None
+        self._hyper_ring = None
         self._reducer = None
         self.launches_per_step = None
         self._step_done = collections.deque(maxlen=2)
@@ -93,8 +94,9 @@ class FusedTrainer:
         b1, b2 = self.betas
         vals = _lib.adamw_hyper(self.current_lr(), b1, b2, self.eps, self.wd, t,
                                 self.max_grad_norm if self.max_grad_norm is not None else 0.0, 1.0 / self.world)
-        # pageable source: staged by the driver before the call returns, so no host buffer is ever live across steps
-        self.hyper.copy_(torch.tensor(vals, dtype=torch.float32))
+        if self._hyper_ring is None:
+            self._hyper_ring = _lib.PinnedRing(len(vals), torch.float32)
+        self._hyper_ring.upload(self.hyper, vals)  # asynchronous: the host keeps queueing steps ahead of the device
 
     # ---- the step ----------------------------------------------------------------------------------
     def _device_step(self, sample_values, labels):
