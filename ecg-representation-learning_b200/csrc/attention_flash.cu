@@ -87,11 +87,16 @@ __global__ void __launch_bounds__(128) flash_fwd_kernel(const bf16 *__restrict__
         rows_times_transposed<DH, 4>(s, sQ, sKb, m0, lane);
         const int k0 = kt * TILE;
         float tmx0 = mx0, tmx1 = mx1;
+        if (k0 + TILE > N) {  // only the last key tile has columns past the sequence (block-uniform)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int c = k0 + 8 * j + 2 * t;
+                if (c >= N) { s[j][0] = -INFINITY; s[j][2] = -INFINITY; }
+                if (c + 1 >= N) { s[j][1] = -INFINITY; s[j][3] = -INFINITY; }
+            }
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const int c = k0 + 8 * j + 2 * t;
-            if (c >= N) { s[j][0] = -INFINITY; s[j][2] = -INFINITY; }
-            if (c + 1 >= N) { s[j][1] = -INFINITY; s[j][3] = -INFINITY; }
             tmx0 = fmaxf(tmx0, fmaxf(s[j][0], s[j][1]));
             tmx1 = fmaxf(tmx1, fmaxf(s[j][2], s[j][3]));
         }
@@ -101,11 +106,12 @@ __global__ void __launch_bounds__(128) flash_fwd_kernel(const bf16 *__restrict__
         const float alpha0 = ex2_approx((mx0 - tmx0) * sl2), alpha1 = ex2_approx((mx1 - tmx1) * sl2);
         mx0 = tmx0;
         mx1 = tmx1;
+        const float nm0 = -mx0 * sl2, nm1 = -mx1 * sl2;  // exp2(s * sl2 - max * sl2): one FFMA per element
         float ts0 = 0.f, ts1 = 0.f;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            s[j][0] = ex2_approx((s[j][0] - mx0) * sl2); s[j][1] = ex2_approx((s[j][1] - mx0) * sl2);
-            s[j][2] = ex2_approx((s[j][2] - mx1) * sl2); s[j][3] = ex2_approx((s[j][3] - mx1) * sl2);
+            s[j][0] = ex2_approx(fmaf(s[j][0], sl2, nm0)); s[j][1] = ex2_approx(fmaf(s[j][1], sl2, nm0));
+            s[j][2] = ex2_approx(fmaf(s[j][2], sl2, nm1)); s[j][3] = ex2_approx(fmaf(s[j][3], sl2, nm1));
             ts0 += s[j][0] + s[j][1];
             ts1 += s[j][2] + s[j][3];
         }
@@ -228,6 +234,10 @@ __global__ void __launch_bounds__(128) flash_bwd_dq_kernel(const bf16 *__restric
         const uint32_t e0 = (static_cast<uint32_t>(bh) * Np + r0) * Np + k0 + 2 * t;
         const uint32_t e1 = e0 + 8u * Np;
         uint32_t dsa[4][4];
+        // padded keys (last key tile) and padded queries (last query tile) must contribute nothing; everywhere else
+        // the validity test is skipped (block-uniform branch)
+        const bool tail = (k0 + TILE > N) || (q0 + TILE > N);
+        const float nl0 = -l0, nl1 = -l1;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int c = k0 + 8 * j + 2 * t;
@@ -238,8 +248,8 @@ __global__ void __launch_bounds__(128) flash_bwd_dq_kernel(const bf16 *__restric
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const bool valid = (c + (i & 1) < N) && ((i < 2 ? r0 : r1) < N);
-                const float pu = valid ? ex2_approx(s[j][i] * sl2 - (i < 2 ? l0 : l1)) : 0.f;
+                float pu = ex2_approx(fmaf(s[j][i], sl2, i < 2 ? nl0 : nl1));
+                if (tail && !((c + (i & 1) < N) && ((i < 2 ? r0 : r1) < N))) pu = 0.f;
                 ds[i] = pu * (dp[j][i] * mk[i] - (i < 2 ? D0 : D1)) * scale;
             }
             dsa[j >> 1][(j & 1) * 2] = pack_bf16x2(ds[0], ds[1]);
@@ -312,6 +322,7 @@ __global__ void __launch_bounds__(128) flash_bwd_dkv_kernel(const bf16 *__restri
         const int q0 = qt * TILE;
         const float *L = sL + buf * TILE, *Dq = sD + buf * TILE;
         uint32_t pa[4][4], dsa[4][4];
+        const bool tail = (k0 + TILE > N) || (q0 + TILE > N);  // block-uniform: only edge tiles test validity
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int c = 8 * j + 2 * t;  // query column inside the tile
@@ -320,8 +331,8 @@ __global__ void __launch_bounds__(128) flash_bwd_dkv_kernel(const bf16 *__restri
             for (int i = 0; i < 4; ++i) {
                 const int qi = q0 + c + (i & 1);       // global query
                 const int kj = (i < 2) ? r0 : r1;      // global key
-                const bool valid = qi < N && kj < N;
-                const float pu = valid ? ex2_approx(st[j][i] * sl2 - L[c + (i & 1)]) : 0.f;
+                float pu = ex2_approx(fmaf(st[j][i], sl2, -L[c + (i & 1)]));
+                if (tail && !(qi < N && kj < N)) pu = 0.f;
                 float mk = 1.f;
                 if (dropping) mk = dropout_one(drop, seed, (static_cast<uint32_t>(bh) * Np + qi) * Np + kj);
                 ds[i] = pu * (dpt[j][i] * mk - Dq[c + (i & 1)]) * scale;

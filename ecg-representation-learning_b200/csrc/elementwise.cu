@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const T *__restri
                                                                 float *__restrict__ dgamma, float *__restrict__ dbeta,
                                                                 float *__restrict__ dcolsum, float *__restrict__ partial,
                                                                 int M, int d, T *__restrict__ dxm, DropoutParams drop) {
-    extern __shared__ float red[];  // [warps][3][d] column partials, then [d] gamma
+    extern __shared__ float red[];  // [warps][3][d] column partials, then [NV * 256] permuted gamma
     pdl_launch_dependents();
     pdl_wait();
     float *sgamma = red + (blockDim.x >> 5) * 3 * d;
@@ -340,8 +340,15 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const T *__restri
     for (int i = 0; i < NV; ++i)
 #pragma unroll
         for (int k = 0; k < 4; ++k) { acc_g[i][k] = 0ull; acc_b[i][k] = 0ull; acc_c[i][k] = 0ull; }
-    for (int i = threadIdx.x; i < d; i += blockDim.x) sgamma[i] = gamma[i];
+    // gamma is staged PERMUTED: pair k (0..3) of vector i of lane l sits at ((i * 4 + k) * 32 + l) * 2, so the LDS.64 a
+    // warp issues for one (i, k) reads 256 consecutive bytes (the natural layout strides lanes by 32 bytes: 2-way
+    // bank conflicts on every read, 24 reads per row)
+    for (int c = threadIdx.x; c < d; c += blockDim.x) {
+        const int i = c >> 8, l = (c >> 3) & 31, k = (c >> 1) & 3;
+        sgamma[((i * 4 + k) * 32 + l) * 2 + (c & 1)] = gamma[c];
+    }
     __syncthreads();
+    const uint64_t *sg2 = reinterpret_cast<const uint64_t *>(sgamma) + lane;  // + (i * 4 + k) * 32
 
     for (int64_t row = (int64_t)blockIdx.x * warps_per_block + warp; row < M;
          row += (int64_t)gridDim.x * warps_per_block) {
@@ -365,11 +372,10 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const T *__restri
                 uint64_t dy2[4], x2[4];
                 unpack_pairs(pdy[i], dy2);
                 unpack_pairs(px[i], x2);
-                const uint64_t *gm2 = reinterpret_cast<const uint64_t *>(sgamma + c);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const uint64_t xh = fma2(x2[k], rstd2, nmr2);
-                    const uint64_t g = mul2(dy2[k], gm2[k]);
+                    const uint64_t g = mul2(dy2[k], sg2[(i * 4 + k) * 32]);
                     s1_2 = add2(s1_2, g);
                     s2_2 = fma2(g, xh, s2_2);
                     acc_g[i][k] = fma2(dy2[k], xh, acc_g[i][k]);
@@ -387,9 +393,9 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const T *__restri
                 uint64_t dy2[4], x2[4], o2[4];
                 unpack_pairs(pdy[i], dy2);
                 unpack_pairs(px[i], x2);
-                const uint64_t *gm2 = reinterpret_cast<const uint64_t *>(sgamma + c);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) o2[k] = fma2(dy2[k], mul2(gm2[k], rstd2), fma2(x2[k], B2, C2));
+                for (int k = 0; k < 4; ++k)
+                    o2[k] = fma2(dy2[k], mul2(sg2[(i * 4 + k) * 32], rstd2), fma2(x2[k], B2, C2));
                 if (dres != nullptr) {
                     uint64_t r2[4];
                     unpack_pairs(pres[i], r2);
@@ -709,8 +715,8 @@ int ecgvit_layernorm_bwd(const void *dy, const void *x, const float *gamma, cons
     const bool dropping = drop.threshold != 0 && dxm != nullptr;
     int grid = grid_for((int64_t)M * 32, 256, 2);
     if (grid > LN_BWD_MAX_BLOCKS) grid = LN_BWD_MAX_BLOCKS;
-    const size_t smem = (8 * 3 + 1) * (size_t)d * sizeof(float);
     const int nv = (d + 255) / 256;
+    const size_t smem = (8 * 3 * (size_t)d + (size_t)nv * 256) * sizeof(float);  // warp slabs + permuted gamma
     cudaStream_t st = as_stream(stream);
 #define ECGVIT_LN_BWD2(TT, NVV, DROP)                                                                                  \
     do {                                                                                                               \
