@@ -7,11 +7,11 @@ through the shim at the repo root.
 """
 from .config import EcgVitConfig
 from .model import EcgVit, ModelOutput, Recorder
-from .trainer import FusedTrainer, get_train_args, lr_multiplier
+from .trainer import FusedTrainer, fused_train_step, get_train_args, lr_multiplier
 from .optim import FusedAdamW, clip_grad_norm_
 from .transform import InputPipeline
 from .metrics import get_accuracy, evaluate
 from . import _lib
 
-__all__ = ['EcgVitConfig', 'EcgVit', 'ModelOutput', 'FusedTrainer', 'FusedAdamW', 'clip_grad_norm_',
+__all__ = ['EcgVitConfig', 'EcgVit', 'ModelOutput', 'FusedTrainer', 'fused_train_step', 'FusedAdamW', 'clip_grad_norm_',
            'get_train_args', 'lr_multiplier', 'InputPipeline', 'Recorder', 'get_accuracy', 'evaluate']

@@ -24,11 +24,30 @@ constexpr int TILE = NMAX;  // 64 rows per tile
 // rows [row0, row0 + 64) of an [N x DH] head matrix (row stride ld) -> smem tile, zero-filling rows >= N
 template <int DH>
 __device__ __forceinline__ void load_rows(bf16 (*dst)[DH + 8], const bf16 *src, int64_t ld, int row0, int N) {
+    // 128 threads: thread t owns 16-byte chunk (t % VPR) of tile rows t / VPR + k * (128 / VPR); constant pointer steps
     constexpr int VPR = DH / 8;
-    for (int i = threadIdx.x; i < TILE * VPR; i += blockDim.x) {
-        const int r = i / VPR, c = (i % VPR) * 8;
-        if (row0 + r < N) cp_async16(&dst[r][c], src + (int64_t)(row0 + r) * ld + c);
-        else *reinterpret_cast<uint4 *>(&dst[r][c]) = make_uint4(0u, 0u, 0u, 0u);
+    constexpr int ROWS_PER_STEP = 128 / VPR;
+    const int c = (threadIdx.x % VPR) * 8;
+    int r = threadIdx.x / VPR;
+    const bf16 *p = src + (int64_t)(row0 + r) * ld + c;
+    bf16 *q = &dst[r][c];
+    const int64_t pstep = (int64_t)ROWS_PER_STEP * ld;
+    if (row0 + TILE <= N) {  // interior tile (block-uniform): no bounds tests
+#pragma unroll
+        for (int k = 0; k < TILE / ROWS_PER_STEP; ++k) {
+            cp_async16(q, p);
+            p += pstep;
+            q += ROWS_PER_STEP * (DH + 8);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < TILE / ROWS_PER_STEP; ++k) {
+            if (row0 + r < N) cp_async16(q, p);
+            else *reinterpret_cast<uint4 *>(q) = make_uint4(0u, 0u, 0u, 0u);
+            r += ROWS_PER_STEP;
+            p += pstep;
+            q += ROWS_PER_STEP * (DH + 8);
+        }
     }
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
@@ -234,9 +253,8 @@ __global__ void __launch_bounds__(128) flash_bwd_dq_kernel(const bf16 *__restric
         const uint32_t e0 = (static_cast<uint32_t>(bh) * Np + r0) * Np + k0 + 2 * t;
         const uint32_t e1 = e0 + 8u * Np;
         uint32_t dsa[4][4];
-        // padded keys (last key tile) and padded queries (last query tile) must contribute nothing; everywhere else
-        // the validity test is skipped (block-uniform branch)
-        const bool tail = (k0 + TILE > N) || (q0 + TILE > N);
+        // No validity tests: padded Q / K / V / dO rows are zero in shared memory, so what P and dS hold for padded
+        // queries or keys only ever multiplies zero rows or lands in rows that are never stored.
         const float nl0 = -l0, nl1 = -l1;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -248,8 +266,7 @@ __global__ void __launch_bounds__(128) flash_bwd_dq_kernel(const bf16 *__restric
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                float pu = ex2_approx(fmaf(s[j][i], sl2, i < 2 ? nl0 : nl1));
-                if (tail && !((c + (i & 1) < N) && ((i < 2 ? r0 : r1) < N))) pu = 0.f;
+                const float pu = ex2_approx(fmaf(s[j][i], sl2, i < 2 ? nl0 : nl1));
                 ds[i] = pu * (dp[j][i] * mk[i] - (i < 2 ? D0 : D1)) * scale;
             }
             dsa[j >> 1][(j & 1) * 2] = pack_bf16x2(ds[0], ds[1]);
@@ -322,7 +339,7 @@ __global__ void __launch_bounds__(128) flash_bwd_dkv_kernel(const bf16 *__restri
         const int q0 = qt * TILE;
         const float *L = sL + buf * TILE, *Dq = sD + buf * TILE;
         uint32_t pa[4][4], dsa[4][4];
-        const bool tail = (k0 + TILE > N) || (q0 + TILE > N);  // block-uniform: only edge tiles test validity
+        // no validity tests (see flash_bwd_dq_kernel): padded rows are zero in shared memory
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int c = 8 * j + 2 * t;  // query column inside the tile
@@ -331,8 +348,7 @@ __global__ void __launch_bounds__(128) flash_bwd_dkv_kernel(const bf16 *__restri
             for (int i = 0; i < 4; ++i) {
                 const int qi = q0 + c + (i & 1);       // global query
                 const int kj = (i < 2) ? r0 : r1;      // global key
-                float pu = ex2_approx(fmaf(st[j][i], sl2, -L[c + (i & 1)]));
-                if (tail && !(qi < N && kj < N)) pu = 0.f;
+                const float pu = ex2_approx(fmaf(st[j][i], sl2, -L[c + (i & 1)]));
                 float mk = 1.f;
                 if (dropping) mk = dropout_one(drop, seed, (static_cast<uint32_t>(bh) * Np + qi) * Np + kj);
                 ds[i] = pu * (dpt[j][i] * mk - Dq[c + (i & 1)]) * scale;

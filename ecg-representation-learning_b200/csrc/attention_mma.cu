@@ -44,19 +44,22 @@ __global__ void __launch_bounds__(128) attention_fwd_mma_kernel(const bf16 *__re
     float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
     for (int j = 0; j < 2 * NT; ++j) {
-        const int c = 8 * j + 2 * t;
-        if (c >= N) { s[j][0] = -INFINITY; s[j][2] = -INFINITY; }
-        if (c + 1 >= N) { s[j][1] = -INFINITY; s[j][3] = -INFINITY; }
+        if (8 * j + 8 > N) {  // warp-uniform: only the last one or two 8-key groups reach past the sequence
+            const int c = 8 * j + 2 * t;
+            if (c >= N) { s[j][0] = -INFINITY; s[j][2] = -INFINITY; }
+            if (c + 1 >= N) { s[j][1] = -INFINITY; s[j][3] = -INFINITY; }
+        }
         mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
         mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
     }
     mx0 = quad_max(mx0);
     mx1 = quad_max(mx1);
+    const float nm0 = -mx0 * sl2, nm1 = -mx1 * sl2;  // exp2(s * sl2 - max * sl2): one FFMA per element
     float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
     for (int j = 0; j < 2 * NT; ++j) {
-        s[j][0] = ex2_approx((s[j][0] - mx0) * sl2); s[j][1] = ex2_approx((s[j][1] - mx0) * sl2);
-        s[j][2] = ex2_approx((s[j][2] - mx1) * sl2); s[j][3] = ex2_approx((s[j][3] - mx1) * sl2);
+        s[j][0] = ex2_approx(fmaf(s[j][0], sl2, nm0)); s[j][1] = ex2_approx(fmaf(s[j][1], sl2, nm0));
+        s[j][2] = ex2_approx(fmaf(s[j][2], sl2, nm1)); s[j][3] = ex2_approx(fmaf(s[j][3], sl2, nm1));
         sum0 += s[j][0] + s[j][1];
         sum1 += s[j][2] + s[j][3];
     }
@@ -169,7 +172,7 @@ __global__ void __launch_bounds__(128) attention_bwd_mma_kernel(const bf16 *__re
         const int r0 = m0 + g, r1 = r0 + 8;
         const float D0 = sD[r0], D1 = sD[r1];
         const float *l = lse + ((int64_t)b * H + h) * N;
-        const float l0 = r0 < N ? l[r0] * LOG2E : 0.f, l1 = r1 < N ? l[r1] * LOG2E : 0.f;
+        const float nl0 = r0 < N ? -l[r0] * LOG2E : 0.f, nl1 = r1 < N ? -l[r1] * LOG2E : 0.f;
 
         float s[2 * NT][4], dp[2 * NT][4];
         rows_times_transposed<DH, NT>(s, sQ, sK, m0, lane);    // S = Q K^T
@@ -187,12 +190,14 @@ __global__ void __launch_bounds__(128) attention_bwd_mma_kernel(const bf16 *__re
                 dropout_pair(drop, seed, base0 + 8 * j, mk[0], mk[1]);
                 dropout_pair(drop, seed, base0 + 8 * NMAX + 8 * j, mk[2], mk[3]);
             }
+            // No validity tests: padded Q / K / V / dO rows are zero in shared memory, so whatever P and dS hold for
+            // padded queries or keys multiplies zero rows in dQ = dS K, dK = dS^T Q, dV = P^T dO, or lands in rows that
+            // are never stored.
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const bool valid = (c + (i & 1) < N) && ((i < 2 ? r0 : r1) < N);
-                const float pu = valid ? ex2_approx(s[j][i] * sl2 - (i < 2 ? l0 : l1)) : 0.f;  // softmax probability
-                ds[i] = pu * (dp[j][i] * mk[i] - (i < 2 ? D0 : D1)) * scale;                  // dS uses the undropped P
-                p[i] = pu * mk[i];                                                            // dV uses the dropped P
+                const float pu = ex2_approx(fmaf(s[j][i], sl2, i < 2 ? nl0 : nl1));  // softmax probability
+                ds[i] = pu * (dp[j][i] * mk[i] - (i < 2 ? D0 : D1)) * scale;        // dS uses the undropped P
+                p[i] = pu * mk[i];                                                  // dV uses the dropped P
             }
             const uint32_t p01 = pack_bf16x2(p[0], p[1]), p23 = pack_bf16x2(p[2], p[3]);
             const uint32_t d01 = pack_bf16x2(ds[0], ds[1]), d23 = pack_bf16x2(ds[2], ds[3]);

@@ -48,11 +48,22 @@ __device__ __forceinline__ void cp_async_wait_all() {
 // zero-filling rows >= N; the caller waits with cp_async_wait_all() + __syncthreads()
 template <int DH>
 __device__ __forceinline__ void load_tile(bf16 (*dst)[DH + 8], const bf16 *src, int ld, int N) {
+    // 128 threads: thread t owns 16-byte chunk (t % VPR) of rows t / VPR + k * (128 / VPR); pointers advance by a
+    // constant per step (the generic i / VPR, i % VPR form cost ~30 integer instructions per cp.async)
     constexpr int VPR = DH / 8;
-    for (int i = threadIdx.x; i < NMAX * VPR; i += blockDim.x) {
-        const int r = i / VPR, c = (i % VPR) * 8;
-        if (r < N) cp_async16(&dst[r][c], src + r * ld + c);
-        else *reinterpret_cast<uint4 *>(&dst[r][c]) = make_uint4(0u, 0u, 0u, 0u);
+    constexpr int ROWS_PER_STEP = 128 / VPR;
+    const int c = (threadIdx.x % VPR) * 8;
+    int r = threadIdx.x / VPR;
+    const bf16 *p = src + static_cast<int64_t>(r) * ld + c;
+    bf16 *q = &dst[r][c];
+    const int64_t pstep = static_cast<int64_t>(ROWS_PER_STEP) * ld;
+#pragma unroll
+    for (int k = 0; k < NMAX / ROWS_PER_STEP; ++k) {
+        if (r < N) cp_async16(q, p);
+        else *reinterpret_cast<uint4 *>(q) = make_uint4(0u, 0u, 0u, 0u);
+        r += ROWS_PER_STEP;
+        p += pstep;
+        q += ROWS_PER_STEP * (DH + 8);
     }
 }
 

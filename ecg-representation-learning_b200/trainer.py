@@ -213,11 +213,34 @@ class FusedTrainer:
                 '(the fused step skipped this update)')
 
     def state_dict(self):
-        """optimizer + schedule state for a true resume (the reference never saves it)"""
-        return {'step': self.step_count, 'exp_avg': self.exp_avg.clone(), 'exp_avg_sq': self.exp_avg_sq.clone()}
+        """optimizer + schedule (+ dropout stream) state for a true resume; the reference saves the model only
+        (train.py:297-300), so a restarted run there silently restarts AdamW's moments and the LR schedule"""
+        self._ensure_state(next(self.model.parameters()).device)
+        eng = self.model._engine
+        return {'step': self.step_count, 'exp_avg': self.exp_avg.clone(), 'exp_avg_sq': self.exp_avg_sq.clone(),
+                'dropout_counter': eng._seed_counter, 'dropout_base_seed': eng.base_seed}
 
     def load_state_dict(self, sd):
-        self._ensure_state(self.model._flat_p.device)
+        self._ensure_state(next(self.model.parameters()).device)
         self.step_count = sd['step']
         self.exp_avg.copy_(sd['exp_avg'])
         self.exp_avg_sq.copy_(sd['exp_avg_sq'])
+        eng = self.model._engine
+        eng._seed_counter = sd.get('dropout_counter', eng._seed_counter)
+        eng.base_seed = sd.get('dropout_base_seed', eng.base_seed)
+
+
+_TRAINERS = {}
+
+
+def fused_train_step(model, batch, lr=3e-4, **trainer_kwargs):
+    """One `zero_grad -> forward -> backward -> clip -> AdamW -> scheduler` step (train.py:271-283) on a batch dict as
+    the reference's DataLoader yields it (`sample_values`, `labels`); the `FusedTrainer` behind it is created on first
+    use and kept per model.  Returns `ModelOutput(loss, logits)` (device tensors, valid until the next step)."""
+    from .model import ModelOutput
+    tr = _TRAINERS.get(id(model))
+    if tr is None or tr.model is not model:
+        tr = _TRAINERS[id(model)] = FusedTrainer(model, learning_rate=lr, **trainer_kwargs)
+    tr.lr = lr
+    loss, logits = tr.step(batch['sample_values'].cuda(non_blocking=True), batch['labels'].cuda(non_blocking=True))
+    return ModelOutput(loss=loss, logits=logits)

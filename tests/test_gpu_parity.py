@@ -371,3 +371,43 @@ def test_loss_weight_matches_reference_formula(reduction):
         model.loss_weight = None
         l2 = float(tr.step(x.cuda(), y.cuda())[0])
         assert abs(l2 - l1) > 0.1 * l1
+
+
+def test_resume_from_saved_optimizer_state_and_fused_train_step():
+    """model + FusedTrainer state saved after 2 steps, loaded into fresh objects, 2 more steps ==
+    4 uninterrupted steps (cosine schedule with warm-up and dropout on, so step counter, moments and the dropout
+    stream all matter)"""
+    cfg = dict(GOLDEN_CFG, hidden_dropout_prob=0.1, attention_probs_dropout_prob=0.1)
+    kw = dict(learning_rate=1e-3, weight_decay=1e-2, schedule='cosine', n_warmup=2, n_step=8, use_cuda_graph=True,
+              data_parallel=False)
+    _, m_ref, x, y = make_pair(cfg, 'fp32', 4)
+    _, m_a, _, _ = make_pair(cfg, 'fp32', 4)
+    xs, ys = x.cuda(), y.cuda()
+    t_ref, t_a = FusedTrainer(m_ref, **kw), FusedTrainer(m_a, **kw)
+    for _ in range(4):
+        t_ref.step(xs, ys)
+    for _ in range(2):
+        t_a.step(xs, ys)
+    saved = {'model': {k: v.cpu() for k, v in m_a.state_dict().items()},
+             'trainer': {k: (v.cpu() if torch.is_tensor(v) else v) for k, v in t_a.state_dict().items()}}
+    m_b = EcgVit(config=EcgVitConfig(compute_dtype='fp32', **cfg))
+    m_b.load_state_dict(saved['model'], strict=True)
+    m_b.cuda().train()
+    t_b = FusedTrainer(m_b, **kw)
+    t_b.load_state_dict(saved['trainer'])
+    for _ in range(2):
+        t_b.step(xs, ys)
+    assert t_b.step_count == 4
+    assert rel(m_b._flat_p, m_ref._flat_p) < 1e-5
+    assert rel(t_b.exp_avg_sq, t_ref.exp_avg_sq) < 1e-4
+    # without the optimizer state the run diverges visibly (what the reference's model-only checkpoint gives)
+    m_c = EcgVit(config=EcgVitConfig(compute_dtype='fp32', **cfg))
+    m_c.load_state_dict(saved['model'], strict=True)
+    m_c.cuda().train()
+    t_c = FusedTrainer(m_c, **kw)
+    for _ in range(2):
+        t_c.step(xs, ys)
+    assert rel(m_c._flat_p, m_ref._flat_p) > 10 * rel(m_b._flat_p, m_ref._flat_p)
+    # the functional entry point of SURVEY 8b
+    out = ecg_b200.fused_train_step(m_c, dict(sample_values=x, labels=y), lr=1e-3)
+    assert isinstance(out, ecg_b200.ModelOutput) and out.logits.shape == (4, 71) and float(out.loss) > 0
