@@ -342,23 +342,41 @@ def main():
         step_ms_eager = sum(v[1] for v in agg.values())
         kernels = {k: {'calls': v[0], 'ms': round(v[1], 4), 'share': round(v[1] / step_ms_eager, 4)} for k, v in agg.items()}
         # The dominant kernel family, timed on its own: every distinct GEMM of the step (shape, operand majors, epilogue)
-        # is re-launched back to back with CUDA events around the batch, rotating over the step's own instances of
-        # that call (different layers -> different weights and activation buffers), and weighted by its launches per
-        # step.  (The per-call event deltas above include host launch gaps, so they only give SHARES.)
+        # is re-launched back to back (as a replayed CUDA graph of >= 12 launches) with CUDA events around the batch,
+        # rotating over the step's own instances of that call (different layers -> different weights and activation
+        # buffers), and weighted by its launches per step.  (The per-call event deltas above include host launch gaps,
+        # so they only give SHARES.)
         import ctypes
         lib = _lib.load()
         st = torch.cuda.current_stream().cuda_stream
         gemm_rows, gemm_flops, gemm_ms = [], 0.0, 0.0
         for key, instances in gemm_calls.items():
             M_, N_, K_, epi, a_k, b_k = key
-            reps = max(10, len(instances))
-            for i in range(3):
-                _lib.check(lib.ecgvit_gemm(ctypes.byref(instances[i % len(instances)]), st), 'gemm')
+            reps = max(12, len(instances))
+
+            def batch():
+                for i in range(reps):
+                    _lib.check(lib.ecgvit_gemm(ctypes.byref(instances[i % len(instances)]), st), 'gemm')
+
+            # the batch is captured into a CUDA graph and the REPLAY is timed: launched from Python one call at a time
+            # the host (tensor-map encoding + ctypes, ~20 us per call) cannot keep a 20 us kernel's queue full, and the
+            # idle gaps would be charged to the kernel
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                st = side.cuda_stream
+                batch()  # warm-up (sets function attributes) outside capture
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                st = torch.cuda.current_stream().cuda_stream
+                batch()
+            g.replay()
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            for i in range(reps):
-                _lib.check(lib.ecgvit_gemm(ctypes.byref(instances[i % len(instances)]), st), 'gemm')
+            g.replay()
             e1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / reps
