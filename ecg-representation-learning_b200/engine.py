@@ -378,8 +378,18 @@ class StepEngine:
                 blk_seed if drop_below else None, M, d, dt, st), 'layernorm_bwd')
             dzl = w.dzm[0] if drop_below else dz
             if m._after_layer_backward is not None:
-                before_overwrite(ev_qkv)  # the bucket of layer l is complete only when its side-stream wgrads are
-                m._after_layer_backward(l)
+                # the gradient bucket of layer l is complete once its side-stream wgrads AND everything the main stream
+                # has issued so far (LayerNorm / bias gradients) are done.  The collective is therefore issued from the
+                # side stream after it has waited for the main stream's current point: c10d orders the NCCL kernel
+                # after the issuing stream, and the main chain never waits for the weight-gradient GEMMs.
+                if side is None:
+                    m._after_layer_backward(l)
+                else:
+                    here = torch.cuda.Event()
+                    here.record(main)
+                    side.wait_event(here)
+                    with torch.cuda.stream(side):
+                        m._after_layer_backward(l)
         for ev in (ev_ff2, ev_ff1, ev_out, ev_qkv):
             before_overwrite(ev)  # join the side stream
         # ---- embedding: tok = [cls | a_patch We^T + be] + pos

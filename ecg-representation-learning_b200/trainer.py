@@ -102,10 +102,24 @@ class FusedTrainer:
     def _device_step(self, sample_values, labels):
         m, st = self.model, torch.cuda.current_stream().cuda_stream
         eng = m._engine
+        side = eng.side_stream
+        if side is not None:
+            # the 342 MB gradient memset does not depend on the forward pass: on the side stream it becomes a parallel
+            # branch of the step graph and disappears behind the (tensor-bound) forward kernels
+            main = torch.cuda.current_stream()
+            fork = torch.cuda.Event()
+            fork.record(main)
+            side.wait_event(fork)  # after the previous step's AdamW / all-reduce, which read the gradients
+            with torch.cuda.stream(side):
+                m._flat_g.zero_()
+                zeroed = torch.cuda.Event()
+                zeroed.record(side)
         loss, logits = eng.forward(sample_values, labels, m.loss_reduction)
+        if side is not None:
+            main.wait_event(zeroed)
         if self._reducer is not None:
             self._reducer.begin()
-        eng.backward(grad_scale=1.0, zero_grads=True)
+        eng.backward(grad_scale=1.0, zero_grads=side is None)
         if self._reducer is not None:
             self._reducer.finish()
         n = m._flat_g.numel()
