@@ -346,7 +346,17 @@ class StepEngine:
             before_overwrite(ev_ff1)   # du
             self._gemm(M, mlp, d, dzl, d, 1, wt[p + 'ff2.w'], mlp, 0, EPI_DGELU, w.du, mlp, aux=w.u[l],
                        drop=(p_blk, s_act))
-            _lib.check(lib.ecgvit_colsum(w.du.data_ptr(), gr[p + 'ff1.b'].data_ptr(), M, mlp, mlp, dt, st), 'colsum')
+            # FF1's bias gradient (column sums of du) feeds nothing in the chain: it rides on the side stream in front of
+            # FF1's weight gradient (same operand, so the event that guards `du` covers both)
+            if side is None:
+                _lib.check(lib.ecgvit_colsum(w.du.data_ptr(), gr[p + 'ff1.b'].data_ptr(), M, mlp, mlp, dt, st), 'colsum')
+            else:
+                ready = torch.cuda.Event()
+                ready.record(main)
+                side.wait_event(ready)
+                with torch.cuda.stream(side):
+                    _lib.check(lib.ecgvit_colsum(w.du.data_ptr(), gr[p + 'ff1.b'].data_ptr(), M, mlp, mlp, dt,
+                                                 side.cuda_stream), 'colsum')
             ev_ff1 = wgrad(mlp, d, M, w.du, mlp, 0, w.ln2[l], d, 0, EPI_ATOMIC_F32, gr[p + 'ff1.w'], d, split_k=0)
             self._gemm(M, d, mlp, w.du, mlp, 1, wt[p + 'ff1.w'], d, 0, EPI_STORE, w.dln, d)
             before_overwrite(ev_out)   # dy / dzm[1] were read by the previous layer's out-proj wgrad
