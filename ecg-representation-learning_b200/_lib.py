@@ -53,8 +53,9 @@ SIGNATURES = {
                              c_int, c_void_p],
     'ecgvit_layernorm_bwd_scratch_floats': [c_int],
     'ecgvit_layernorm_bwd': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                             c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_void_p, c_int, c_int, c_int,
+                             c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_void_p, c_int, c_int, c_int, c_int,
                              c_void_p],
+    'ecgvit_layernorm_bwd_finalize': [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p],
     'ecgvit_gemm': [POINTER(GemmArgs), c_void_p],
     'ecgvit_attention_probs': [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_int64, c_int, c_void_p],
     'ecgvit_eval_metrics_scratch_bytes': [c_int],
@@ -103,7 +104,7 @@ def last_error():
 
 
 # kernels launched per successful entry-point call (memsets are not kernels); feeds bench.py's `gpu_launches`
-KERNELS_PER_CALL = {'attention_bwd_flash': 3, 'head_fwd': 2, 'head_bwd': 3, 'layernorm_bwd': 2, 'grad_sumsq': 2, 'eval_metrics': 3}
+KERNELS_PER_CALL = {'attention_bwd_flash': 3, 'head_fwd': 2, 'head_bwd': 3, 'layernorm_bwd': 2, 'layernorm_bwd_partial': 1, 'grad_sumsq': 2, 'eval_metrics': 3}
 launch_counter = [0]
 
 

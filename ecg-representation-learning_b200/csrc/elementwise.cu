@@ -707,18 +707,30 @@ int ecgvit_layernorm_fwd(const void *x, const float *gamma, const float *beta, v
 
 int64_t ecgvit_layernorm_bwd_scratch_floats(int d) { return (int64_t)LN_BWD_MAX_BLOCKS * 3 * d; }
 
+static int ln_bwd_blocks(int M) {
+    int grid = grid_for((int64_t)M * 32, 256, 2);
+    return grid > LN_BWD_MAX_BLOCKS ? LN_BWD_MAX_BLOCKS : grid;
+}
+
+int ecgvit_layernorm_bwd_finalize(const float *scratch, float *dgamma, float *dbeta, float *dcolsum, int M, int d,
+                                  void *stream) {
+    ECGVIT_REQUIRE(scratch && dgamma && dbeta && M > 0 && d > 0, "layernorm_bwd_finalize: bad arguments");
+    launch_pdl(layernorm_bwd_finalize_kernel, dim3((3 * d + 31) / 32), dim3(256), 0, as_stream(stream), scratch,
+               ln_bwd_blocks(M), dgamma, dbeta, dcolsum, d);
+    return check_launch("layernorm_bwd_finalize");
+}
+
 int ecgvit_layernorm_bwd(const void *dy, const void *x, const float *gamma, const float *mean, const float *rstd,
                          const void *dres, void *dx, float *dgamma, float *dbeta, float *dcolsum, float *scratch,
                          void *dxm, float dropout_p, int dropout_stream, const uint32_t *dropout_seed, int M, int d,
-                         int dtype, void *stream) {
+                         int defer_finalize, int dtype, void *stream) {
     ECGVIT_REQUIRE(dy && x && gamma && mean && rstd && dx && dgamma && dbeta && scratch && M > 0,
                    "layernorm_bwd: bad arguments");
     ECGVIT_REQUIRE(d % 8 == 0 && d <= 8 * 32 * LN_MAXV, "layernorm_bwd: d=%d must be a multiple of 8 and <= %d", d,
                    8 * 32 * LN_MAXV);
     const DropoutParams drop = make_dropout(dropout_p, dropout_stream, dropout_seed);
     const bool dropping = drop.threshold != 0 && dxm != nullptr;
-    int grid = grid_for((int64_t)M * 32, 256, 2);
-    if (grid > LN_BWD_MAX_BLOCKS) grid = LN_BWD_MAX_BLOCKS;
+    const int grid = ln_bwd_blocks(M);
     const int nv = (d + 255) / 256;
     const size_t smem = (8 * 3 * (size_t)d + (size_t)nv * 256) * sizeof(float);  // warp slabs + permuted gamma
     cudaStream_t st = as_stream(stream);
@@ -753,10 +765,8 @@ int ecgvit_layernorm_bwd(const void *dy, const void *x, const float *gamma, cons
 #undef ECGVIT_LN_BWD
 #undef ECGVIT_LN_BWD2
     int rc = check_launch("layernorm_bwd");
-    if (rc) return rc;
-    launch_pdl(layernorm_bwd_finalize_kernel, dim3((3 * d + 31) / 32), dim3(256), 0, st, (const float *)scratch, grid,
-               dgamma, dbeta, dcolsum, d);
-    return check_launch("layernorm_bwd_finalize");
+    if (rc || defer_finalize) return rc;
+    return ecgvit_layernorm_bwd_finalize(scratch, dgamma, dbeta, dcolsum, M, d, stream);
 }
 
 int ecgvit_colsum(const void *x, float *out, int M, int N, int64_t ld, int dtype, void *stream) {

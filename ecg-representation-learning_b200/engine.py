@@ -146,7 +146,8 @@ class StepEngine:
         w.de = buf(B * n, d)
         # dropout-masked copies of the residual-stream gradients (only used when p > 0): one per site of a block
         w.dzm = [buf(M, d), buf(M, d)]
-        w.ln_scratch = buf(int(self.lib.ecgvit_layernorm_bwd_scratch_floats(d)), dtype=torch.float32)
+        # two partial-row scratch buffers (one per LayerNorm of a block): their fold runs off the critical chain
+        w.ln_scratch = [buf(int(self.lib.ecgvit_layernorm_bwd_scratch_floats(d)), dtype=torch.float32) for _ in range(2)]
         n_attn = int(self.lib.ecgvit_attention_bwd_scratch_floats(B, N, H, d // H, m._dtype_code))
         w.attn_scratch = buf(n_attn, dtype=torch.float32) if n_attn > 0 else None
         self.ws[key] = w
@@ -335,6 +336,30 @@ class StepEngine:
             if ev is not None:
                 main.wait_event(ev)
 
+        ev_fold = [None, None]
+
+        def layernorm_bwd(which, dln, x_in, gamma, stat, dres, dx, dgamma, dbeta, dcol, dxm, p_drop, site):
+            """dx = dres + LN'(dln) (+ the dropout-masked copy dxm) on the main stream; the fold of the per-CTA partial rows
+            into dgamma / dbeta / dcol feeds nothing in the chain and runs on the side stream"""
+            scr = w.ln_scratch[which]
+            before_overwrite(ev_fold[which])  # the fold of this scratch's previous user
+            seed = blk_seed if (dxm is not None and p_drop > 0) else None
+            _lib.check(lib.ecgvit_layernorm_bwd(
+                dln.data_ptr(), x_in.data_ptr(), gamma.data_ptr(), stat[0].data_ptr(), stat[1].data_ptr(),
+                dres.data_ptr(), dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), _lib.ptr(dcol), scr.data_ptr(),
+                _lib.ptr(dxm), p_drop, site, seed, M, d, 0 if side is None else 1, dt, st),
+                'layernorm_bwd' if side is None else 'layernorm_bwd_partial')
+            if side is not None:
+                ready = torch.cuda.Event()
+                ready.record(main)
+                side.wait_event(ready)
+                with torch.cuda.stream(side):
+                    _lib.check(lib.ecgvit_layernorm_bwd_finalize(scr.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(),
+                                                                 _lib.ptr(dcol), M, d, side.cuda_stream),
+                               'layernorm_bwd_finalize')
+                    ev_fold[which] = torch.cuda.Event()
+                    ev_fold[which].record(side)
+
         ev_ff2 = ev_ff1 = ev_out = ev_qkv = None
         for l in range(depth - 1, -1, -1):
             p = f'l{l}.'
@@ -361,11 +386,8 @@ class StepEngine:
             self._gemm(M, d, mlp, w.du, mlp, 1, wt[p + 'ff1.w'], d, 0, EPI_STORE, w.dln, d)
             before_overwrite(ev_out)   # dy / dzm[1] were read by the previous layer's out-proj wgrad
             dyl = w.dzm[1] if p_blk > 0 else dy
-            _lib.check(lib.ecgvit_layernorm_bwd(
-                w.dln.data_ptr(), w.y[l].data_ptr(), pf[p + 'ln2.w'].data_ptr(), w.stat2[l][0].data_ptr(),
-                w.stat2[l][1].data_ptr(), dz.data_ptr(), dy.data_ptr(), gr[p + 'ln2.w'].data_ptr(),
-                gr[p + 'ln2.b'].data_ptr(), gr[p + 'out.b'].data_ptr(), w.ln_scratch.data_ptr(),
-                dyl.data_ptr() if p_blk > 0 else None, p_blk, s_out, blk_seed, M, d, dt, st), 'layernorm_bwd')
+            layernorm_bwd(0, w.dln, w.y[l], pf[p + 'ln2.w'], w.stat2[l], dz, dy, gr[p + 'ln2.w'], gr[p + 'ln2.b'],
+                          gr[p + 'out.b'], dyl if p_blk > 0 else None, p_blk, s_out)
             # ---- attention branch: y = x + drop(Wo attn(Wqkv ln1(x)) + bo); dyl = mask * dy / (1 - p)
             ev_out = wgrad(d, inner, M, dyl, d, 0, w.o[l], inner, 0, EPI_ATOMIC_F32, gr[p + 'out.w'], inner, split_k=0)
             self._gemm(M, inner, d, dyl, d, 1, wt[p + 'out.w'], inner, 0, EPI_STORE, w.d_o, inner)
@@ -380,12 +402,8 @@ class StepEngine:
             below_bias = gr[f'l{l - 1}.ff2.b'] if l > 0 else None
             drop_below = p_blk > 0 and l > 0
             before_overwrite(ev_ff2)   # this layer's ff2 wgrad reads dz (p = 0) / dzm[0], which LayerNorm' now rewrites
-            _lib.check(lib.ecgvit_layernorm_bwd(
-                w.dln.data_ptr(), w.x[l].data_ptr(), pf[p + 'ln1.w'].data_ptr(), w.stat1[l][0].data_ptr(),
-                w.stat1[l][1].data_ptr(), dy.data_ptr(), dz.data_ptr(), gr[p + 'ln1.w'].data_ptr(),
-                gr[p + 'ln1.b'].data_ptr(), _lib.ptr(below_bias), w.ln_scratch.data_ptr(),
-                w.dzm[0].data_ptr() if drop_below else None, p_blk if drop_below else 0.0, s_ff2 - 4,
-                blk_seed if drop_below else None, M, d, dt, st), 'layernorm_bwd')
+            layernorm_bwd(1, w.dln, w.x[l], pf[p + 'ln1.w'], w.stat1[l], dy, dz, gr[p + 'ln1.w'], gr[p + 'ln1.b'],
+                          below_bias, w.dzm[0] if drop_below else None, p_blk if drop_below else 0.0, s_ff2 - 4)
             dzl = w.dzm[0] if drop_below else dz
             if m._after_layer_backward is not None:
                 # the gradient bucket of layer l is complete once its side-stream wgrads AND everything the main stream
@@ -400,7 +418,7 @@ class StepEngine:
                     side.wait_event(here)
                     with torch.cuda.stream(side):
                         m._after_layer_backward(l)
-        for ev in (ev_ff2, ev_ff1, ev_out, ev_qkv):
+        for ev in (ev_ff2, ev_ff1, ev_out, ev_qkv, ev_fold[0], ev_fold[1]):
             before_overwrite(ev)  # join the side stream
         # ---- embedding: tok = [cls | a_patch We^T + be] + pos
         _lib.check(lib.ecgvit_embed_assemble_bwd(dz.data_ptr(), w.de.data_ptr(), gr['cls'].data_ptr(),

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define ECGVIT_ABI_VERSION 4
+#define ECGVIT_ABI_VERSION 5
 
 enum { ECGVIT_F32 = 0, ECGVIT_BF16 = 1 };
 
@@ -94,10 +94,15 @@ int ecgvit_layernorm_fwd(const void *x, const float *gamma, const float *beta, v
  * well and dcolsum += colsum(dxm).
  * scratch: fp32 workspace of ecgvit_layernorm_bwd_scratch_floats(d) elements (per-CTA column partials) */
 int64_t ecgvit_layernorm_bwd_scratch_floats(int d);
+/* defer_finalize != 0: only the per-CTA partial rows are written to `scratch`; the caller folds them into dgamma /
+ * dbeta / dcolsum later with ecgvit_layernorm_bwd_finalize (e.g. on another stream, off the critical chain) and must
+ * not reuse `scratch` before that has run. */
 int ecgvit_layernorm_bwd(const void *dy, const void *x, const float *gamma, const float *mean,
                          const float *rstd, const void *dres, void *dx, float *dgamma, float *dbeta,
                          float *dcolsum, float *scratch, void *dxm, float dropout_p, int dropout_stream,
-                         const uint32_t *dropout_seed, int M, int d, int dtype, void *stream);
+                         const uint32_t *dropout_seed, int M, int d, int defer_finalize, int dtype, void *stream);
+int ecgvit_layernorm_bwd_finalize(const float *scratch, float *dgamma, float *dbeta, float *dcolsum, int M, int d,
+                                  void *stream);
 
 /* ---- dense contraction  C[m,n] = sum_k A(m,k) * B(n,k)  with fused epilogue.
  *      Replaces nn.Linear forward / its autograd dgrad / wgrad (vit_pytorch Attention.to_qkv, to_out[0],
