@@ -49,3 +49,34 @@ def test_argument_validation_returns_error_without_touching_the_gpu():
     assert 'null' in ecg_b200._lib.last_error()
     with pytest.raises(RuntimeError):
         ecg_b200._lib.check(lib.ecgvit_patchify(None, None, 0, 0, 0, 0, 0, 0, None), 'patchify')
+
+
+def _declared_prototypes():
+    """{name: [C parameter types]} parsed from the header (comments stripped)"""
+    src = re.sub(r'/\*.*?\*/', '', open(HEADER).read(), flags=re.S)
+    out = {}
+    for m in re.finditer(r'\b(?:int|int64_t|const char \*)\s*\*?\s*(ecgvit_[a-z0-9_]+)\s*\(([^)]*)\)\s*;', src):
+        params = [p.strip() for p in m.group(2).replace('\n', ' ').split(',')]
+        out[m.group(1)] = [] if params == ['void'] else params
+    return out
+
+
+def test_ctypes_signatures_match_the_header_prototypes():
+    """argument count and C type class (pointer / int / int64 / float) of every entry point: the binding in _lib.py is
+    what every caller goes through, and a drifted signature corrupts the stack silently"""
+    import ecg_b200
+    kinds = {ctypes.c_void_p: 'ptr', ctypes.c_char_p: 'ptr', ctypes.c_int: 'int', ctypes.c_int64: 'i64',
+             ctypes.c_float: 'f32'}
+
+    def kind_of_c(decl):
+        if '*' in decl:
+            return 'ptr'
+        t = decl.rsplit(' ', 1)[0].replace('const ', '').strip()
+        return {'int': 'int', 'int64_t': 'i64', 'float': 'f32'}[t]
+
+    protos = _declared_prototypes()
+    assert set(protos) == set(ecg_b200._lib.SIGNATURES)
+    for name, params in protos.items():
+        sig = ecg_b200._lib.SIGNATURES[name]
+        got = ['ptr' if (isinstance(t, type) and issubclass(t, ctypes._Pointer)) else kinds[t] for t in sig]
+        assert got == [kind_of_c(p) for p in params], (name, got, params)
