@@ -161,3 +161,22 @@ def test_metrics_oracle_matches_reference_vectors(case):
     assert np.array_equal(np.isnan(per_class), np.isnan(want))
     assert np.allclose(per_class[~np.isnan(want)], want[~np.isnan(want)], rtol=1e-12, atol=0)
     assert np.isnan(per_class[5]) and np.isnan(per_class[9])      # single-label classes are filtered (util/train.py:29)
+
+
+def test_oracle_fp64_tie_breaker(golden):
+    """an fp64 run of the oracle is the referee when fp32 CPU and fp32 GPU disagree near 1e-5.  It also
+    measures the fp32 noise floor of the golden vectors themselves: well below the 1e-5 bar the GPU tests apply."""
+    m = OracleEcgVit(config=OracleConfig(**GOLDEN_CFG))
+    _load_state(m, golden, 'init/')
+    m = m.double().train()
+    x, y = torch.from_numpy(golden['x']).double(), torch.from_numpy(golden['y']).double()
+    out = m(sample_values=x, labels=y)
+    out.loss.backward()
+    want = torch.from_numpy(golden['logits']).double()
+    rel = float((out.logits.detach() - want).norm() / want.norm())
+    assert rel < 1e-6, rel
+    assert abs(out.loss.item() - float(golden['loss'])) < 1e-6 * float(golden['loss'])
+    worst = max(float((p.grad - torch.from_numpy(golden['grad/' + k]).double()).norm() /
+                      torch.from_numpy(golden['grad/' + k]).double().norm().clamp_min(1e-30))
+                for k, p in m.named_parameters())
+    assert worst < 1e-5, worst
