@@ -180,3 +180,56 @@ def test_oracle_fp64_tie_breaker(golden):
                       torch.from_numpy(golden['grad/' + k]).double().norm().clamp_min(1e-30))
                 for k, p in m.named_parameters())
     assert worst < 1e-5, worst
+
+
+@pytest.mark.parametrize('seed', range(6))
+def test_metrics_oracle_matches_sklearn_on_random_cases(seed):
+    """oracle/metrics.py against scikit-learn itself (the third-party code the reference calls, util/train.py:33-52) on
+    random sizes, class balances and tie structures, with the reference's argument order for classification_report"""
+    sk = pytest.importorskip('sklearn.metrics')
+    from oracle import metrics
+    rng = np.random.default_rng(seed)
+    n, k = int(rng.integers(2, 400)), int(rng.integers(1, 12))
+    quant = [None, 2, 8][seed % 3]
+    logits = rng.standard_normal((n, k)) * 2
+    if quant:
+        logits = np.round(logits * quant) / quant
+    preds = (1 / (1 + np.exp(-logits))).astype(np.float32)
+    labels = (rng.random((n, k)) < rng.uniform(0.05, 0.6)).astype(np.float32)
+    scalars, per_class = metrics.get_accuracy(preds, labels)
+    two = np.any(labels != labels[0], axis=0)
+    for c in range(k):
+        if two[c]:
+            assert abs(per_class[c] - sk.roc_auc_score(labels[:, c], preds[:, c])) < 1e-12
+        else:
+            assert np.isnan(per_class[c])
+    pb, y = (preds >= 0.5).astype(np.float32).flatten(), labels.flatten()
+    assert abs(scalars[0] - sk.accuracy_score(y, pb)) < 1e-12
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        assert abs(scalars[1] - sk.balanced_accuracy_score(y, pb)) < 1e-12
+        rep = sk.classification_report(pb, y, labels=[0, 1], target_names=['neg', 'pos'], output_dict=True,
+                                       zero_division=0)
+    rec_pos, rec_neg = [rep[t]['recall'] for t in ['neg', 'pos']]            # util/train.py:50, names as swapped there
+    assert abs(scalars[2] - rec_neg) < 1e-12 and abs(scalars[3] - rec_pos) < 1e-12
+
+
+@pytest.mark.parametrize('seed', range(4))
+def test_transform_oracle_random_shapes_against_numpy_semantics(seed):
+    """TimeEndPad's length rule and TimeOut's span on random lengths; Normalize in fp32 like numpy broadcasting"""
+    from oracle import transforms
+    rng = np.random.default_rng(100 + seed)
+    C, L, k = int(rng.integers(1, 13)), int(rng.integers(10, 700)), int(rng.integers(2, 90))
+    rec = rng.standard_normal((2, C, L)).astype(np.float32)
+    mean, std = rng.standard_normal(C), rng.random(C) + 0.1
+    Lp = L + (k - L % k)
+    spans = [(int(rng.integers(0, Lp // 2)), int(rng.integers(0, Lp // 2))) for _ in range(2)]
+    out = transforms.pipeline(rec, mean, std, pad=k, spans=spans)
+    assert out.shape == (2, C, Lp) and out.dtype == np.float32 and Lp % k == 0 and Lp > L
+    want = (rec - mean.astype(np.float32)[None, :, None]) / std.astype(np.float32)[None, :, None]
+    for b, (s, l) in enumerate(spans):
+        keep = np.ones(Lp, bool)
+        keep[s:s + l] = False
+        assert np.array_equal(out[b][:, :L][:, keep[:L]], want[b][:, keep[:L]])
+        assert not out[b][:, ~keep].any() and not out[b][:, L:].any()
