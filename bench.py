@@ -227,7 +227,7 @@ def main():
     import torch.distributed as dist
     import ecg_b200
     from ecg_b200 import _lib
-    from oracle.ecg_vit_oracle import synthetic_batch  # only the seeded input generator
+    from ecg_b200 import synthetic_batch  # seeded input generator; nothing of oracle/ on this arm
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))

@@ -11,7 +11,8 @@ from .trainer import FusedTrainer, fused_train_step, get_train_args, lr_multipli
 from .optim import FusedAdamW, clip_grad_norm_
 from .transform import InputPipeline
 from .metrics import get_accuracy, evaluate
+from .synthetic import synthetic_batch
 from . import _lib
 
 __all__ = ['EcgVitConfig', 'EcgVit', 'ModelOutput', 'FusedTrainer', 'fused_train_step', 'FusedAdamW', 'clip_grad_norm_',
-           'get_train_args', 'lr_multiplier', 'InputPipeline', 'Recorder', 'get_accuracy', 'evaluate']
+           'get_train_args', 'lr_multiplier', 'InputPipeline', 'Recorder', 'get_accuracy', 'evaluate', 'synthetic_batch']

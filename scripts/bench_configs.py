@@ -9,7 +9,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import ecg_b200
-from oracle.ecg_vit_oracle import synthetic_batch
+from ecg_b200 import synthetic_batch
 
 CASES = {
     'base_p0': ('ecg-vit-base', 'bf16', 256, 0.0), 'base_p01': ('ecg-vit-base', 'bf16', 256, 0.1),

@@ -14,7 +14,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import ecg_b200
 from bench import BASE_CFG
-from oracle.ecg_vit_oracle import synthetic_batch
+from ecg_b200 import synthetic_batch
 
 p = float(sys.argv[1]) if len(sys.argv) > 1 else 0.1
 cfg = dict(BASE_CFG, hidden_dropout_prob=p, attention_probs_dropout_prob=p)
