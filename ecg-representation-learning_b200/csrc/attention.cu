@@ -17,6 +17,10 @@ int attention_fwd_flash(const void *qkv, void *o, float *lse, int B, int N, int 
 int attention_bwd_flash(const void *qkv, const void *o, const void *d_o, const float *lse, void *dqkv, float *dscratch,
                         int B, int N, int H, int dh, float scale, DropoutParams drop, cudaStream_t stream);
 bool attention_flash_supported(int N, int dh);
+// attention_tc.cu: tcgen05 / TMEM / TMA kernels (bf16, head dim 64, any N)
+int attention_fwd_tc(const void *qkv, void *o, float *lse, int B, int N, int H, int dh, float scale, DropoutParams drop,
+                     cudaStream_t stream);
+bool attention_tc_supported(int N, int dh);
 
 // the dropout counter of the attention probabilities is a 32-bit element index ((b*H + h) * Np + i) * Np + j
 static bool dropout_index_fits(int B, int N, int H) {
@@ -107,6 +111,8 @@ int ecgvit_attention_fwd(const void *qkv, void *o, float *lse, int B, int N, int
     ECGVIT_REQUIRE(dtype == ECGVIT_F32 || dtype == ECGVIT_BF16, "attention_fwd: unknown dtype %d", dtype);
     ECGVIT_REQUIRE(drop.threshold == 0 || dropout_index_fits(B, N, H),
                    "attention_fwd: B*H*Np*Np = %d*%d*Np^2 overflows the 32-bit dropout counter (N=%d)", B, H, N);
+    if (dtype == ECGVIT_BF16 && attention_tc_supported(N, dh))
+        return attention_fwd_tc(qkv, o, lse, B, N, H, dh, scale, drop, as_stream(stream));
     if (dtype == ECGVIT_BF16 && attention_mma_supported(N, dh))
         return attention_fwd_mma(qkv, o, lse, B, N, H, dh, scale, drop, as_stream(stream));
     if (dtype == ECGVIT_BF16 && attention_flash_supported(N, dh))
