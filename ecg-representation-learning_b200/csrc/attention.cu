@@ -20,6 +20,9 @@ bool attention_flash_supported(int N, int dh);
 // attention_tc.cu: tcgen05 / TMEM / TMA kernels (bf16, head dim 64, any N)
 int attention_fwd_tc(const void *qkv, void *o, float *lse, int B, int N, int H, int dh, float scale, DropoutParams drop,
                      cudaStream_t stream);
+int attention_bwd_tc(const void *qkv, const void *o, const void *d_o, const float *lse, void *dqkv, float *scratch, int B,
+                     int N, int H, int dh, float scale, DropoutParams drop, cudaStream_t stream);
+int64_t attention_bwd_tc_scratch_floats(int B, int N, int H);
 bool attention_tc_supported(int N, int dh);
 
 // the dropout counter of the attention probabilities is a 32-bit element index ((b*H + h) * Np + i) * Np + j
@@ -121,6 +124,7 @@ int ecgvit_attention_fwd(const void *qkv, void *o, float *lse, int B, int N, int
 }
 
 int64_t ecgvit_attention_bwd_scratch_floats(int B, int N, int H, int dh, int dtype) {
+    if (dtype == ECGVIT_BF16 && attention_tc_supported(N, dh)) return attention_bwd_tc_scratch_floats(B, N, H);
     return (dtype == ECGVIT_BF16 && attention_flash_supported(N, dh)) ? (int64_t)B * H * N : 0;
 }
 
@@ -133,6 +137,8 @@ int ecgvit_attention_bwd(const void *qkv, const void *o, const void *d_o, const 
     ECGVIT_REQUIRE(dtype == ECGVIT_F32 || dtype == ECGVIT_BF16, "attention_bwd: unknown dtype %d", dtype);
     ECGVIT_REQUIRE(drop.threshold == 0 || dropout_index_fits(B, N, H),
                    "attention_bwd: B*H*Np*Np = %d*%d*Np^2 overflows the 32-bit dropout counter (N=%d)", B, H, N);
+    if (dtype == ECGVIT_BF16 && attention_tc_supported(N, dh))
+        return attention_bwd_tc(qkv, o, d_o, lse, dqkv, scratch, B, N, H, dh, scale, drop, as_stream(stream));
     if (dtype == ECGVIT_BF16 && attention_mma_supported(N, dh))
         return attention_bwd_mma(qkv, o, d_o, lse, dqkv, B, N, H, dh, scale, drop, as_stream(stream));
     if (dtype == ECGVIT_BF16 && attention_flash_supported(N, dh)) {

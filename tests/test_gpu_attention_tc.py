@@ -101,3 +101,49 @@ def test_attention_tc_forward_large_scores_are_stable():
     want, want_lse, _ = reference(qkv, B, N, H, dh, dh ** -0.5)
     assert torch.isfinite(o.float()).all()
     assert rel(o, want) < 8e-3 and rel(lse, want_lse) < 1e-5
+
+
+def run_bwd(lib, qkv, o, lse, d_o, B, N, H, dh, p=0.0, site=0, seed_t=None):
+    dqkv = torch.full_like(qkv, float('nan'))
+    n_scr = int(lib.ecgvit_attention_bwd_scratch_floats(B, N, H, dh, BF16))
+    scr = torch.empty(max(n_scr, 1), device='cuda')
+    L.check(lib.ecgvit_attention_bwd(qkv.data_ptr(), o.data_ptr(), d_o.data_ptr(), lse.data_ptr(), dqkv.data_ptr(),
+                                     scr.data_ptr() if n_scr else None, B, N, H, dh, dh ** -0.5, p, site,
+                                     None if seed_t is None else seed_t.data_ptr(), BF16, stream()), 'attn_bwd')
+    torch.cuda.synchronize()
+    return dqkv
+
+
+def parts(t, H, dh):
+    return t.float().chunk(3, dim=-1)
+
+
+@pytest.mark.parametrize('B,N,H', CASES)
+def test_attention_tc_backward(B, N, H):
+    lib = L.load()
+    dh = 64
+    g = torch.Generator(device='cuda').manual_seed(B * 1000 + N + 1)
+    qkv = torch.randn(B * N, 3 * H * dh, device='cuda', generator=g).bfloat16()
+    d_o = torch.randn(B * N, H * dh, device='cuda', generator=g).bfloat16()
+    o, lse = run_fwd(lib, qkv, B, N, H, dh)
+    dqkv = run_bwd(lib, qkv, o, lse, d_o, B, N, H, dh)
+    want, _, leaf = reference(qkv, B, N, H, dh, dh ** -0.5)
+    want.backward(d_o.float())
+    assert torch.isfinite(dqkv.float()).all()
+    for name, got, ref in zip('qkv', parts(dqkv, H, dh), parts(leaf.grad, H, dh)):
+        assert rel(got, ref) < 1.5e-2, (name, rel(got, ref))
+
+
+@pytest.mark.parametrize('B,N,H', [(3, 51, 4), (1, 200, 2), (1, 300, 1)])
+def test_attention_tc_backward_dropout_masks_match_host_replica(B, N, H):
+    lib = L.load()
+    dh, p, site, seed = 64, 0.2, 5, 77
+    qkv = torch.randn(B * N, 3 * H * dh, device='cuda').bfloat16()
+    d_o = torch.randn(B * N, H * dh, device='cuda').bfloat16()
+    seed_t = torch.tensor([seed], dtype=torch.int32, device='cuda')
+    o, lse = run_fwd(lib, qkv, B, N, H, dh, p, site, seed_t)
+    dqkv = run_bwd(lib, qkv, o, lse, d_o, B, N, H, dh, p, site, seed_t)
+    want, _, leaf = reference(qkv, B, N, H, dh, dh ** -0.5, keep_mask(seed, site, p, B, N, H))
+    want.backward(d_o.float())
+    for name, got, ref in zip('qkv', parts(dqkv, H, dh), parts(leaf.grad, H, dh)):
+        assert rel(got, ref) < 1.5e-2, (name, rel(got, ref))
