@@ -530,14 +530,15 @@ PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
 }
 
 // bf16 [B][N][cols] view (row pitch `ld` elements, batch pitch N * ld) with a {64 features, box_rows tokens, 1} box
-int make_tmap3(CUtensorMap *tm, const void *base, int cols, int N, int B, int64_t ld, int box_rows) {
+int make_tmap3(CUtensorMap *tm, const void *base, int cols, int N, int B, int64_t ld, int box_rows, bool fp32 = false) {
     PFN_cuTensorMapEncodeTiled_v12000 enc = encode_fn();
     if (enc == nullptr) return fail(-2, "cuTensorMapEncodeTiled not available from the driver");
     cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)N, (cuuint64_t)B};
-    cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)N * (cuuint64_t)ld * 2};
-    cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
+    const cuuint64_t esz = fp32 ? 4 : 2;   // either way a box row is 128 bytes (64 bf16 / 32 fp32)
+    cuuint64_t strides[2] = {(cuuint64_t)ld * esz, (cuuint64_t)N * (cuuint64_t)ld * esz};
+    cuuint32_t box[3] = {fp32 ? 32u : 64u, (cuuint32_t)box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(base), dims, strides, box, estr,
+    CUresult r = enc(tm, fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(-3, "cuTensorMapEncodeTiled(3d) failed with CUresult %d", (int)r);
@@ -604,25 +605,33 @@ int launch_fwd(const void *qkv, void *o, float *lse, int B, int N, int H, float 
 // core is never waiting for the exponentials of the step it just finished.
 // D = rowsum(dO * O): packed rows are whole in one tile, so D = sum_j Pd_ij dP_ij is formed in the kernel (the two
 // threads of a row swap partial sums through shared memory); long rows take it from a small pre-pass over O and dO.
-// shared-memory map (packed: 2 Q/dO stages + the D exchange; long: 3 Q/dO stages, D comes from the pre-pass)
+// shared-memory map.  Pd_s / dS_s are two [128 query x 64 key] chunks each; in the packed geometry only the diagonal
+// quarters are ever non-zero, so the chunks overlap on one shared 8 KB block of zeros (chunk stride 8 KB instead of 16):
+//   [rows 0..63 of chunk 0 | zeros = rows 64..127 of chunk 0 = rows 0..63 of chunk 1 | rows 64..127 of chunk 1]
+// OUT is the staging area the results leave through (TMA store / reduce-add issued by warp 3):
+//   packed: dQ | dK | dV tiles (bf16);  long: dQ as two fp32 [128 x 32] sub-tiles, reused for dK | dV at the item's end
 template <bool kPacked> struct BwdMap {
-    static constexpr int QD_STAGES = kPacked ? 2 : 3;
+    static constexpr int QD_STAGES = 2;
+    static constexpr int CHUNK = kPacked ? TILE_BYTES / 2 : TILE_BYTES;   // byte distance between the two key chunks
+    static constexpr int PD_BYTES = CHUNK + TILE_BYTES;
     static constexpr int KV_OFF = 0;                                      // [slot 2] K tile | V tile
     static constexpr int QD_OFF = KV_OFF + 2 * 2 * TILE_BYTES;            // [stage] Q tile | dO tile
-    static constexpr int PD_OFF = QD_OFF + QD_STAGES * 2 * TILE_BYTES;    // Pd_s: two [128 q x 64 keys] chunks
-    static constexpr int DS_OFF = PD_OFF + 2 * TILE_BYTES;                // dS_s: same
-    static constexpr int DX_OFF = DS_OFF + 2 * TILE_BYTES;                // float [parity 2][half 2][128] (packed only)
+    static constexpr int PD_OFF = QD_OFF + QD_STAGES * 2 * TILE_BYTES;
+    static constexpr int DS_OFF = PD_OFF + PD_BYTES;
+    static constexpr int OUT_OFF = DS_OFF + PD_BYTES;
+    static constexpr int OUT_BYTES = kPacked ? 3 * TILE_BYTES : 2 * TILE_BYTES;
+    static constexpr int DX_OFF = OUT_OFF + OUT_BYTES;                    // float [parity 2][half 2][128] (packed only)
     static constexpr int BAR_OFF = DX_OFF + (kPacked ? 2048 : 0);
-    static constexpr int SMEM_BYTES = BAR_OFF + 256 + 1024;
+    static constexpr int SMEM_BYTES = BAR_OFF + 256;                      // the dynamic array is declared 1024-aligned
     static_assert(SMEM_BYTES <= 232448, "backward shared memory");
 };
-constexpr int G_QD_MAX_STAGES = 3;
+constexpr int G_QD_MAX_STAGES = 2;
 constexpr uint32_t G_TM_S = 0, G_TM_DP = 128, G_TM_DV = 256, G_TM_DK = 320, G_TM_DQ = 384;
 
 struct BwdBars {
     uint64_t kv_full[2], kv_empty[2];
     uint64_t qd_full[G_QD_MAX_STAGES], qd_empty[G_QD_MAX_STAGES];
-    uint64_t sdp_full, sdp_free, pds_full, mma2_done;
+    uint64_t sdp_full, sdp_free, pds_full, mma2_done, out_full, out_free;
     uint32_t tmem_ptr;
 };
 static_assert(sizeof(BwdBars) <= 256, "barrier block");
@@ -651,13 +660,14 @@ __device__ __forceinline__ void bwd_decode(int kk, int B, int N, int H, BwdItem<
 template <bool kPacked>
 __global__ void __launch_bounds__(384, 1)
 attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
-                   const float *__restrict__ lse, const float *__restrict__ Drow, bf16 *__restrict__ dqkv,
-                   float *__restrict__ dq_acc, int B, int N, int H, float scale, DropoutParams drop) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+                   const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_acc,
+                   const float *__restrict__ lse, const float *__restrict__ Drow, int B, int N, int H, float scale,
+                   DropoutParams drop) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((ptx::smem_u32(smem) & 1023u) != 0) asm volatile("trap;");   // SWIZZLE_128B tiles need the declared alignment
     using Map = BwdMap<kPacked>;
     constexpr int G_KV_OFF = Map::KV_OFF, G_QD_OFF = Map::QD_OFF, G_PD_OFF = Map::PD_OFF, G_DS_OFF = Map::DS_OFF,
-                  G_DX_OFF = Map::DX_OFF, G_QD_STAGES = Map::QD_STAGES;
+                  G_DX_OFF = Map::DX_OFF, G_QD_STAGES = Map::QD_STAGES, G_OUT_OFF = Map::OUT_OFF, G_CHUNK = Map::CHUNK;
     BwdBars *bars = reinterpret_cast<BwdBars *>(smem + Map::BAR_OFF);
 
     pdl_launch_dependents();
@@ -668,8 +678,12 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&tm_qkv);
         ptx::prefetch_tensormap(&tm_do);
+        ptx::prefetch_tensormap(&tm_out);
+        if (!kPacked) ptx::prefetch_tensormap(&tm_acc);
     }
     if (warp == 1 && lane == 0) {
+        ptx::mbar_init(&bars->out_full, 8);
+        ptx::mbar_init(&bars->out_free, 1);
         for (int s = 0; s < 2; ++s) {
             ptx::mbar_init(&bars->kv_full[s], 1);
             ptx::mbar_init(&bars->kv_empty[s], 1);
@@ -686,13 +700,11 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     }
     if (warp == 2) ptx::tmem_alloc(&bars->tmem_ptr, 512);
     if (kPacked && warp >= 4) {
-        // the off-diagonal quarters of Pd_s / dS_s are never written in the packed geometry: clear them once.
-        // chunk 0 (keys 0..63) rows 64..127 and chunk 1 (keys 64..127) rows 0..63 of both matrices: 4 x 8 KB
+        // the shared block of zeros of Pd_s and of dS_s (never written afterwards)
         const int tid = threadIdx.x - 128;
-        for (int i = tid; i < 4 * 512; i += 256) {
-            const int region = i >> 9, w = i & 511;   // 512 x 16 B per region
-            uint8_t *base = smem + (region < 2 ? G_PD_OFF : G_DS_OFF) + ((region & 1) ? TILE_BYTES : TILE_BYTES / 2);
-            *reinterpret_cast<uint4 *>(base + w * 16) = make_uint4(0u, 0u, 0u, 0u);
+        for (int i = tid; i < 2 * 512; i += 256) {
+            uint8_t *base = smem + ((i >> 9) ? G_DS_OFF : G_PD_OFF) + G_CHUNK;
+            *reinterpret_cast<uint4 *>(base + (i & 511) * 16) = make_uint4(0u, 0u, 0u, 0u);
         }
         ptx::fence_proxy_async_smem();
     }
@@ -787,8 +799,8 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
             if (ptx::elect_one()) {
                 const uint32_t kv = sb + G_KV_OFF + kvslot * 2 * TILE_BYTES, qd = sb + G_QD_OFF + st * 2 * TILE_BYTES;
                 // MN-major operands: 16 contraction rows (queries / keys) = 2048 B per UMMA_K; A spans two 64-wide chunks
-                const uint64_t a_pd = ptx::make_smem_desc(sb + G_PD_OFF, 2 * TILE_BYTES / 2, 1024);
-                const uint64_t a_ds = ptx::make_smem_desc(sb + G_DS_OFF, 2 * TILE_BYTES / 2, 1024);
+                const uint64_t a_pd = ptx::make_smem_desc(sb + G_PD_OFF, G_CHUNK, 1024);
+                const uint64_t a_ds = ptx::make_smem_desc(sb + G_DS_OFF, G_CHUNK, 1024);
                 const uint64_t b_do = ptx::make_smem_desc(qd + TILE_BYTES, 8192, 1024);
                 const uint64_t b_q = ptx::make_smem_desc(qd, 8192, 1024);
                 const uint64_t b_k = ptx::make_smem_desc(kv, 8192, 1024);
@@ -800,8 +812,8 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
                 for (int k = 0; k < TM / 16; ++k)
                     ptx::umma_bf16(tmem_base + G_TM_DK, a_ds + 128 * k, b_q + 128 * k, idesc_kv, (acc || k > 0) ? 1u : 0u);
 #pragma unroll
-                for (int k = 0; k < TN / 16; ++k)   // keys: chunk k / 4 (16 KB apart), 32 B per UMMA_K inside the chunk
-                    ptx::umma_bf16(tmem_base + G_TM_DQ, a_dsk + (k >> 2) * (TILE_BYTES >> 4) + 2 * (k & 3), b_k + 128 * k,
+                for (int k = 0; k < TN / 16; ++k)   // keys: chunk k / 4, 32 B per UMMA_K inside the chunk
+                    ptx::umma_bf16(tmem_base + G_TM_DQ, a_dsk + (k >> 2) * (G_CHUNK >> 4) + 2 * (k & 3), b_k + 128 * k,
                                    idesc_q, k > 0 ? 1u : 0u);
                 ptx::umma_commit(&bars->mma2_done);
                 ptx::umma_commit(&bars->qd_empty[st]);
@@ -850,6 +862,54 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
             }
             it = nxt;
         }
+    } else if (warp == 3) {
+        // ================================ result warp: TMA stores / reduce-adds out of the staging area ==
+        uint32_t oph = 0;
+        uint8_t *out = smem + G_OUT_OFF;
+        for (int kk = 0;; ++kk) {
+            BwdItem<kPacked> it;
+            bwd_decode<kPacked>(kk, B, N, H, it);
+            if (!it.valid) break;
+            for (int i = 0; i < nsteps; ++i) {
+                ptx::mbar_wait(&bars->out_full, oph);
+                oph ^= 1;
+                if (ptx::elect_one()) {
+                    if (kPacked) {
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            const int p = it.prob[j], c = (p % H) * DH, b = p / H;
+#pragma unroll
+                            for (int w = 0; w < 3; ++w)   // dQ, dK, dV
+                                ptx::tma_store_3d(&tm_out, out + w * TILE_BYTES + j * (TILE_BYTES / 2), w * inner + c, 0, b);
+                        }
+                    } else {
+                        const int p = it.prob[0], c = (p % H) * DH, b = p / H;
+#pragma unroll
+                        for (int hh = 0; hh < 2; ++hh)
+                            ptx::tma_reduce_add_3d(&tm_acc, out + hh * TILE_BYTES, c + 32 * hh, i * TM, b);
+                    }
+                    ptx::tma_store_commit();
+                    ptx::tma_store_wait_read<0>();
+                    ptx::mbar_arrive(&bars->out_free);
+                }
+                __syncwarp();
+                if (!kPacked && i + 1 == nsteps) {
+                    ptx::mbar_wait(&bars->out_full, oph);
+                    oph ^= 1;
+                    if (ptx::elect_one()) {
+                        const int p = it.prob[0], c = (p % H) * DH, b = p / H;
+                        ptx::tma_store_3d(&tm_out, out, inner + c, it.k0, b);
+                        ptx::tma_store_3d(&tm_out, out + TILE_BYTES, 2 * inner + c, it.k0, b);
+                        ptx::tma_store_commit();
+                        ptx::tma_store_wait_read<0>();
+                        ptx::mbar_arrive(&bars->out_free);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+        if (ptx::elect_one()) ptx::tma_store_wait_all<0>();
+        __syncwarp();
     }
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
@@ -868,70 +928,71 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
         const uint32_t thr = drop.threshold << 16;
         const float sd = drop.scale;
         const int Np = (N + 63) / 64 * 64;
-        const int64_t ld3 = 3 * static_cast<int64_t>(inner);
         float *dx = reinterpret_cast<float *>(smem + G_DX_OFF);
         // destination of this thread's Pd / dS values: chunk cbase / 64, 16-byte pieces (cbase % 64) / 8 ... of row r
-        uint8_t *pd_row = smem + G_PD_OFF + (cbase >> 6) * TILE_BYTES, *ds_row = smem + G_DS_OFF + (cbase >> 6) * TILE_BYTES;
+        uint8_t *pd_row = smem + G_PD_OFF + (cbase >> 6) * G_CHUNK, *ds_row = smem + G_DS_OFF + (cbase >> 6) * G_CHUNK;
         const int piece0 = (cbase & 63) >> 3;
 
         uint32_t sph = 0, dph = 0;
         int step = 0;
         // what the previous step left in TMEM for this thread to drain
         bool have_prev = false, prev_last = false;
-        int prev_prob = 0, prev_q = 0, prev_k = 0;
+        uint32_t oph = 0;
+        uint8_t *out = smem + G_OUT_OFF;
+        // 32 accumulator columns of this thread's row -> bf16 -> pieces 4 g .. 4 g + 3 of row r of a staged [128 x 64] tile
+        auto stage_bf16 = [&](uint32_t tmem_col, uint8_t *tile) {
+            uint32_t v[32];
+            ptx::tmem_ld_32x32(lane_addr + tmem_col + 32 * g, v);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                uint4 u;
+                u.x = pack_bf16x2(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]));
+                u.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
+                u.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
+                u.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
+                *reinterpret_cast<uint4 *>(tile + sw128_offset(r, 4 * g + j)) = u;
+            }
+        };
+        auto publish = [&]() {
+            ptx::tcgen05_fence_before();
+            ptx::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&bars->out_full);
+        };
+        auto wait_out_free = [&]() {
+            ptx::mbar_wait(&bars->out_free, oph ^ 1);   // the result warp's previous operations have read the staging area
+            oph ^= 1;
+        };
+        // the previous step's results leave TMEM through the staging area (warp 3 issues the TMA operations)
         auto drain = [&]() {
             ptx::mbar_wait(&bars->mma2_done, dph);
             dph ^= 1;
             ptx::tcgen05_fence_after();
-            const int pb = prev_prob / H, ph = prev_prob - pb * H;
-            {
-                uint32_t v[32];
-                ptx::tmem_ld_32x32(lane_addr + G_TM_DQ + 32 * g, v);
-                ptx::tmem_ld_wait();
-                if (prev_q < N && prev_prob < B * H) {
-                    if (kPacked) {
-                        bf16 *dst = dqkv + (static_cast<int64_t>(pb) * N + prev_q) * ld3 + ph * DH + 32 * g;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            uint4 u;
-                            u.x = pack_bf16x2(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]));
-                            u.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
-                            u.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
-                            u.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
-                            *reinterpret_cast<uint4 *>(dst + 8 * j) = u;
-                        }
-                    } else {
-                        float *dst = dq_acc + (static_cast<int64_t>(pb) * N + prev_q) * inner + ph * DH + 32 * g;
-#pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * j),
-                                         "f"(__uint_as_float(v[4 * j])), "f"(__uint_as_float(v[4 * j + 1])),
-                                         "f"(__uint_as_float(v[4 * j + 2])), "f"(__uint_as_float(v[4 * j + 3]))
-                                         : "memory");
-                    }
-                }
-            }
-            if (prev_last) {
-#pragma unroll
-                for (int which = 0; which < 2; ++which) {   // dK, then dV
+            wait_out_free();
+            if (kPacked) {
+                stage_bf16(G_TM_DQ, out);
+                stage_bf16(G_TM_DK, out + TILE_BYTES);
+                stage_bf16(G_TM_DV, out + 2 * TILE_BYTES);
+                publish();
+            } else {
+                {   // dQ of the step, fp32: sub-tile g holds columns 32 g .. 32 g + 31 (128-byte rows)
                     uint32_t v[32];
-                    ptx::tmem_ld_32x32(lane_addr + (which ? G_TM_DV : G_TM_DK) + 32 * g, v);
+                    ptx::tmem_ld_32x32(lane_addr + G_TM_DQ + 32 * g, v);
                     ptx::tmem_ld_wait();
-                    if (prev_k < N && prev_prob < B * H) {
-                        bf16 *dst = dqkv + (static_cast<int64_t>(pb) * N + prev_k) * ld3 + (1 + which) * inner + ph * DH + 32 * g;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            uint4 u;
-                            u.x = pack_bf16x2(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]));
-                            u.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
-                            u.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
-                            u.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
-                            *reinterpret_cast<uint4 *>(dst + 8 * j) = u;
-                        }
-                    }
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<uint4 *>(out + g * TILE_BYTES + sw128_offset(r, j)) =
+                            make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                }
+                publish();
+                if (prev_last) {
+                    wait_out_free();
+                    stage_bf16(G_TM_DK, out);
+                    stage_bf16(G_TM_DV, out + TILE_BYTES);
+                    publish();
                 }
             }
-            ptx::tcgen05_fence_before();
         };
 
         for (int kk = 0;; ++kk) {
@@ -1034,9 +1095,6 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
                 if (lane == 0) ptx::mbar_arrive(&bars->pds_full);
                 have_prev = true;
                 prev_last = i + 1 == nsteps;
-                prev_prob = prob;
-                prev_q = qrow;
-                prev_k = kPacked ? (r & 63) : it.k0 + r;
             }
         }
         if (have_prev) drain();
@@ -1088,10 +1146,13 @@ template <bool kPacked>
 int launch_bwd(const void *qkv, const void *d_o, const float *lse, const float *Drow, void *dqkv, float *dq_acc, int B,
                int N, int H, float scale, DropoutParams drop, cudaStream_t stream) {
     const int inner = H * DH;
-    CUtensorMap tq, td;
+    CUtensorMap tq, td, tout, tacc;
     int rc;
     if ((rc = make_tmap3(&tq, qkv, 3 * inner, N, B, 3 * (int64_t)inner, kPacked ? 64 : TM))) return rc;
     if ((rc = make_tmap3(&td, d_o, inner, N, B, inner, kPacked ? 64 : TM))) return rc;
+    if ((rc = make_tmap3(&tout, dqkv, 3 * inner, N, B, 3 * (int64_t)inner, kPacked ? 64 : TM))) return rc;
+    tacc = tout;
+    if (!kPacked && (rc = make_tmap3(&tacc, dq_acc, inner, N, B, inner, TM, /*fp32=*/true))) return rc;
     auto kern = attn_tc_bwd_kernel<kPacked>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -1101,8 +1162,8 @@ int launch_bwd(const void *qkv, const void *d_o, const float *lse, const float *
     }
     const int items = kPacked ? (B * H + 1) >> 1 : B * H * ((N + TN - 1) / TN);
     const int grid = items < sm_count() ? items : sm_count();
-    cudaError_t le = launch_pdl(kern, dim3(grid), dim3(384), BwdMap<kPacked>::SMEM_BYTES, stream, tq, td, lse, Drow,
-                                reinterpret_cast<bf16 *>(dqkv), dq_acc, B, N, H, scale, drop);
+    cudaError_t le = launch_pdl(kern, dim3(grid), dim3(384), BwdMap<kPacked>::SMEM_BYTES, stream, tq, td, tout, tacc, lse,
+                                Drow, B, N, H, scale, drop);
     if (le != cudaSuccess) return fail((int)le, "attn_tc_bwd launch: %s", cudaGetErrorString(le));
     return check_launch("attn_tc_bwd");
 }
