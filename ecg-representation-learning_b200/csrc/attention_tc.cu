@@ -128,7 +128,16 @@ __device__ __forceinline__ void chunk_exp(const uint32_t s[32], int lim, float s
         }
         sum2[(i >> 1) & 1] = add2(sum2[(i >> 1) & 1], pack2(p[i], p[i + 1]));
     }
-    if (drop.threshold != 0) dropout_apply<32>(drop, seed, e0, p);
+    if (drop.threshold != 0) {
+        // keep / drop only: the 1 / (1 - p) factor of the kept probabilities is applied once, to the finished row of O
+        const uint32_t thr = drop.threshold << 16;
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+            const uint32_t h = dropout_hash(seed, drop.stream, (e0 + i) >> 1);
+            p[i] = (h << 16) >= thr ? p[i] : 0.f;
+            p[i + 1] = h >= thr ? p[i + 1] : 0.f;
+        }
+    }
 #pragma unroll
     for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(p[2 * i], p[2 * i + 1]);
 }
@@ -467,7 +476,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
             if (q == 0 && lane == 0) ptx::tma_store_wait_read<0>();  // the previous store of this tile has read `ost`
             ptx::named_bar_sync(1 + t, 128);
             if (q == 0) stamp(1 + t, 7);
-            const float inv_l = 1.0f / l;
+            const float inv_l = drop.scale / l;   // drop.scale = 1 / (1 - p) of the attention dropout (1 when off)
 #pragma unroll 1
             for (int c = 0; c < DH / 32; ++c) {
                 uint32_t o[32];
@@ -545,6 +554,31 @@ int make_tmap3(CUtensorMap *tm, const void *base, int cols, int N, int B, int64_
     return 0;
 }
 
+// debug only: <env>=<file> dumps CTA 0's clock64() stamps (3 roles x 64 x (clock, tag)) after a synchronous copy
+long long *timeline_begin(const char *env) {
+    if (getenv(env) == nullptr) return nullptr;
+    long long *tl = nullptr;
+    cudaMalloc(&tl, 3 * 64 * 2 * sizeof(long long));
+    cudaMemset(tl, 0, 3 * 64 * 2 * sizeof(long long));
+    return tl;
+}
+void timeline_end(long long *tl, const char *env) {
+    if (tl == nullptr) return;
+    long long host[3 * 64 * 2];
+    cudaMemcpy(host, tl, sizeof(host), cudaMemcpyDeviceToHost);
+    cudaFree(tl);
+    long long t0 = 0;
+    for (int i = 0; i < 3 * 64; ++i)
+        if (host[2 * i + 1] != 0 && (t0 == 0 || host[2 * i] < t0)) t0 = host[2 * i];
+    if (FILE *f = fopen(getenv(env), "w")) {
+        for (int r = 0; r < 3; ++r)
+            for (int i = 0; i < 64; ++i)
+                if (host[(r * 64 + i) * 2 + 1] != 0)
+                    fprintf(f, "%d %d %lld %lld\n", r, i, host[(r * 64 + i) * 2] - t0, host[(r * 64 + i) * 2 + 1]);
+        fclose(f);
+    }
+}
+
 template <bool kPacked>
 int launch_fwd(const void *qkv, void *o, float *lse, int B, int N, int H, float scale, DropoutParams drop,
                cudaStream_t stream) {
@@ -564,27 +598,10 @@ int launch_fwd(const void *qkv, void *o, float *lse, int B, int N, int H, float 
     if (kPacked) items = (B * H + 1) >> 1;
     else items = B * H * ((((N + TM - 1) / TM) + 1) >> 1);
     const int grid = items < sm_count() ? items : sm_count();
-    // debug only: ECGVIT_ATTN_TIMELINE=<file> dumps CTA 0's clock64() stamps (3 roles x 64 x (clock, tag)), synchronously
-    const char *tl_path = getenv("ECGVIT_ATTN_TIMELINE");
-    long long *tl = nullptr;
-    if (tl_path != nullptr) {
-        cudaMalloc(&tl, 3 * 64 * 2 * sizeof(long long));
-        cudaMemset(tl, 0, 3 * 64 * 2 * sizeof(long long));
-    }
+    long long *tl = timeline_begin("ECGVIT_ATTN_TIMELINE");
     cudaError_t le = launch_pdl(kern, dim3(grid), dim3(384), F_SMEM_BYTES, stream, tq, to, lse, B, N, H, scale, drop, tl);
     if (le != cudaSuccess) return fail((int)le, "attn_tc_fwd launch: %s", cudaGetErrorString(le));
-    if (tl != nullptr) {
-        long long host[3 * 64 * 2];
-        cudaMemcpy(host, tl, sizeof(host), cudaMemcpyDeviceToHost);
-        cudaFree(tl);
-        if (FILE *f = fopen(tl_path, "w")) {
-            for (int r = 0; r < 3; ++r)
-                for (int i = 0; i < 64; ++i)
-                    if (host[(r * 64 + i) * 2 + 1] != 0)
-                        fprintf(f, "%d %d %lld %lld\n", r, i, host[(r * 64 + i) * 2] - host[0], host[(r * 64 + i) * 2 + 1]);
-            fclose(f);
-        }
-    }
+    timeline_end(tl, "ECGVIT_ATTN_TIMELINE");
     return check_launch("attn_tc_fwd");
 }
 
@@ -662,8 +679,16 @@ __global__ void __launch_bounds__(384, 1)
 attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
                    const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_acc,
                    const float *__restrict__ lse, const float *__restrict__ Drow, int B, int N, int H, float scale,
-                   DropoutParams drop) {
+                   DropoutParams drop, long long *__restrict__ timeline) {
     extern __shared__ __align__(1024) uint8_t smem[];
+    int tl_n = 0;   // debug timeline (ECGVIT_ATTN_TIMELINE), see the forward kernel
+    auto stamp = [&](int role, int tag) {
+        if (timeline != nullptr && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && tl_n < 64) {
+            timeline[(role * 64 + tl_n) * 2] = clock64();
+            timeline[(role * 64 + tl_n) * 2 + 1] = tag;
+            ++tl_n;
+        }
+    };
     if ((ptx::smem_u32(smem) & 1023u) != 0) asm volatile("trap;");   // SWIZZLE_128B tiles need the declared alignment
     using Map = BwdMap<kPacked>;
     constexpr int G_KV_OFF = Map::KV_OFF, G_QD_OFF = Map::QD_OFF, G_PD_OFF = Map::PD_OFF, G_DS_OFF = Map::DS_OFF,
@@ -848,15 +873,20 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
                 const bool last = i + 1 == nsteps;
                 int kv_next = kv_cur, st_next = 0;
                 if (!last || nxt.valid) {
+                    stamp(0, 10);
                     ptx::mbar_wait(&bars->sdp_free, fph);   // S and dP are in the compute warps' registers
                     fph ^= 1;
+                    stamp(0, 11);
                     if (last) kv_next = wait_kv();
                     st_next = wait_qd();
                     mma1(kv_next, st_next);
                 }
+                stamp(0, 12);
                 ptx::mbar_wait(&bars->pds_full, pph);       // Pd_s / dS_s written, previous outputs drained
                 pph ^= 1;
+                stamp(0, 13);
                 mma2(kv_cur, st_cur, i > 0, last);
+                stamp(0, 14);
                 kv_cur = kv_next;
                 st_cur = st_next;
             }
@@ -873,6 +903,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
             for (int i = 0; i < nsteps; ++i) {
                 ptx::mbar_wait(&bars->out_full, oph);
                 oph ^= 1;
+                stamp(2, 30);
                 if (ptx::elect_one()) {
                     if (kPacked) {
 #pragma unroll
@@ -893,6 +924,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
                     ptx::mbar_arrive(&bars->out_free);
                 }
                 __syncwarp();
+                stamp(2, 31);
                 if (!kPacked && i + 1 == nsteps) {
                     ptx::mbar_wait(&bars->out_full, oph);
                     oph ^= 1;
@@ -940,17 +972,17 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
         uint32_t oph = 0;
         uint8_t *out = smem + G_OUT_OFF;
         // 32 accumulator columns of this thread's row -> bf16 -> pieces 4 g .. 4 g + 3 of row r of a staged [128 x 64] tile
-        auto stage_bf16 = [&](uint32_t tmem_col, uint8_t *tile) {
+        auto stage_bf16 = [&](uint32_t tmem_col, uint8_t *tile, float mul) {
             uint32_t v[32];
             ptx::tmem_ld_32x32(lane_addr + tmem_col + 32 * g, v);
             ptx::tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 uint4 u;
-                u.x = pack_bf16x2(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]));
-                u.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
-                u.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
-                u.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
+                u.x = pack_bf16x2(__uint_as_float(v[8 * j + 0]) * mul, __uint_as_float(v[8 * j + 1]) * mul);
+                u.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]) * mul, __uint_as_float(v[8 * j + 3]) * mul);
+                u.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]) * mul, __uint_as_float(v[8 * j + 5]) * mul);
+                u.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]) * mul, __uint_as_float(v[8 * j + 7]) * mul);
                 *reinterpret_cast<uint4 *>(tile + sw128_offset(r, 4 * g + j)) = u;
             }
         };
@@ -969,11 +1001,13 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
             ptx::mbar_wait(&bars->mma2_done, dph);
             dph ^= 1;
             ptx::tcgen05_fence_after();
+            if (warp == 4) stamp(1, 7);
             wait_out_free();
+            if (warp == 4) stamp(1, 8);
             if (kPacked) {
-                stage_bf16(G_TM_DQ, out);
-                stage_bf16(G_TM_DK, out + TILE_BYTES);
-                stage_bf16(G_TM_DV, out + 2 * TILE_BYTES);
+                stage_bf16(G_TM_DQ, out, scale);
+                stage_bf16(G_TM_DK, out + TILE_BYTES, scale);
+                stage_bf16(G_TM_DV, out + 2 * TILE_BYTES, 1.0f);
                 publish();
             } else {
                 {   // dQ of the step, fp32: sub-tile g holds columns 32 g .. 32 g + 31 (128-byte rows)
@@ -988,8 +1022,8 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
                 publish();
                 if (prev_last) {
                     wait_out_free();
-                    stage_bf16(G_TM_DK, out);
-                    stage_bf16(G_TM_DV, out + TILE_BYTES);
+                    stage_bf16(G_TM_DK, out, scale);
+                    stage_bf16(G_TM_DV, out + TILE_BYTES, 1.0f);
                     publish();
                 }
             }
@@ -1007,9 +1041,11 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
                 const float lse_r = row_ok ? __ldg(lse + static_cast<int64_t>(prob) * N + qrow) : INFINITY;
                 float D = 0.f;
                 if (!kPacked && row_ok) D = __ldg(Drow + static_cast<int64_t>(prob) * N + qrow);
+                if (warp == 4) stamp(1, 1);
                 ptx::mbar_wait(&bars->sdp_full, sph);
                 sph ^= 1;
                 ptx::tcgen05_fence_after();
+                if (warp == 4) stamp(1, 2);
                 uint32_t s[NCH][32], dp[NCH][32];
 #pragma unroll
                 for (int c = 0; c < NCH; ++c) ptx::tmem_ld_32x32(lane_addr + G_TM_S + cbase + 32 * c, s[c]);
@@ -1023,61 +1059,82 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
                 ptx::tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(&bars->sdp_free);
-                // ---- P = exp2(S sl2 - lse log2e) (in place), t = dP * mask (in place)
+                if (warp == 4) stamp(1, 3);
+                // ---- P = exp2(S sl2 - lse log2e), t = dP * mask, Pd = P * mask, dS' = P (t - D)   (packed fp32x2 math;
+                //      the softmax scale of dS is applied when dQ / dK leave TMEM)
                 const float nl2 = -lse_r * LOG2E_F;   // -inf for rows that do not exist: P = 0
                 const uint32_t e_row = (static_cast<uint32_t>(prob) * Np + static_cast<uint32_t>(qrow)) * Np +
                                        static_cast<uint32_t>(it.k0 + kcol);
-                float part = 0.f;
+                const uint64_t sl2_2 = splat2(sl2), nl2_2 = splat2(nl2);
+                uint32_t pdk[NCH][16], dsk[NCH][16];
+                if (!kPacked) {
+                    // D is known (pre-pass): one sweep
+                    const uint64_t nD2 = splat2(-D);
 #pragma unroll
-                for (int c = 0; c < NCH; ++c) {
-                    const uint64_t sl2_2 = splat2(sl2), nl2_2 = splat2(nl2);
+                    for (int c = 0; c < NCH; ++c)
+#pragma unroll
+                        for (int j = 0; j < 32; j += 2) {
+                            float x0, x1;
+                            unpack2(fma2(pack2(__uint_as_float(s[c][j]), __uint_as_float(s[c][j + 1])), sl2_2, nl2_2), x0, x1);
+                            float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+                            float t0 = __uint_as_float(dp[c][j]), t1 = __uint_as_float(dp[c][j + 1]);
+                            float d0 = p0, d1 = p1;
+                            if (dropping) {
+                                const uint32_t h = dropout_hash(seed, drop.stream, (e_row + 32 * c + j) >> 1);
+                                const bool k0 = (h << 16) >= thr, k1 = h >= thr;
+                                t0 = k0 ? t0 * sd : 0.f;
+                                t1 = k1 ? t1 * sd : 0.f;
+                                d0 = k0 ? p0 * sd : 0.f;
+                                d1 = k1 ? p1 * sd : 0.f;
+                            }
+                            float g0, g1;
+                            unpack2(mul2(pack2(p0, p1), add2(pack2(t0, t1), nD2)), g0, g1);
+                            pdk[c][j >> 1] = pack_bf16x2(d0, d1);
+                            dsk[c][j >> 1] = pack_bf16x2(g0, g1);
+                        }
+                } else {
+                    // D = sum over the row's 64 keys of Pd * dP: first sweep keeps P and t in place and packs Pd, then the
+                    // two threads of a row swap partial sums through shared memory, then dS'
+                    uint64_t part2 = 0ull;
 #pragma unroll
                     for (int j = 0; j < 32; j += 2) {
                         float x0, x1;
-                        unpack2(fma2(pack2(__uint_as_float(s[c][j]), __uint_as_float(s[c][j + 1])), sl2_2, nl2_2), x0, x1);
+                        unpack2(fma2(pack2(__uint_as_float(s[0][j]), __uint_as_float(s[0][j + 1])), sl2_2, nl2_2), x0, x1);
                         const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
-                        float t0 = __uint_as_float(dp[c][j]), t1 = __uint_as_float(dp[c][j + 1]);
+                        float t0 = __uint_as_float(dp[0][j]), t1 = __uint_as_float(dp[0][j + 1]);
+                        float d0 = p0, d1 = p1;
                         if (dropping) {
-                            const uint32_t h = dropout_hash(seed, drop.stream, (e_row + 32 * c + j) >> 1);
-                            t0 = (h << 16) >= thr ? t0 * sd : 0.f;
-                            t1 = h >= thr ? t1 * sd : 0.f;
+                            const uint32_t h = dropout_hash(seed, drop.stream, (e_row + j) >> 1);
+                            const bool k0 = (h << 16) >= thr, k1 = h >= thr;
+                            t0 = k0 ? t0 * sd : 0.f;
+                            t1 = k1 ? t1 * sd : 0.f;
+                            d0 = k0 ? p0 * sd : 0.f;
+                            d1 = k1 ? p1 * sd : 0.f;
                         }
-                        if (kPacked) part = fmaf(p0, t0, fmaf(p1, t1, part));
-                        s[c][j] = __float_as_uint(p0);
-                        s[c][j + 1] = __float_as_uint(p1);
-                        dp[c][j] = __float_as_uint(t0);
-                        dp[c][j + 1] = __float_as_uint(t1);
+                        part2 = fma2(pack2(p0, p1), pack2(t0, t1), part2);
+                        pdk[0][j >> 1] = pack_bf16x2(d0, d1);
+                        s[0][j] = __float_as_uint(p0);
+                        s[0][j + 1] = __float_as_uint(p1);
+                        dp[0][j] = __float_as_uint(t0);
+                        dp[0][j + 1] = __float_as_uint(t1);
                     }
-                }
-                if (kPacked) {
-                    // D = sum over the row's 64 keys of Pd * dP: swap partial sums with the thread holding the other half
+                    const float part = pair_sum2(part2);
                     float *slot = dx + (step & 1) * 256;
                     slot[g * 128 + r] = part;
                     ptx::named_bar_sync(3, 256);
-                    D = part + slot[(g ^ 1) * 128 + r];
-                }
-                // ---- Pd = P * mask, dS = P (t - D) scale  -> bf16 pairs
-                uint32_t pdk[NCH][16], dsk[NCH][16];
-#pragma unroll
-                for (int c = 0; c < NCH; ++c) {
+                    const uint64_t nD2 = splat2(-(part + slot[(g ^ 1) * 128 + r]));
 #pragma unroll
                     for (int j = 0; j < 32; j += 2) {
-                        const float p0 = __uint_as_float(s[c][j]), p1 = __uint_as_float(s[c][j + 1]);
-                        const float t0 = __uint_as_float(dp[c][j]), t1 = __uint_as_float(dp[c][j + 1]);
-                        float d0 = p0 * sd, d1 = p1 * sd;   // sd = 1 without dropout
-                        if (dropping) {
-                            // a dropped element has t == 0 exactly unless dP itself is 0, in which case Pd is irrelevant
-                            // to dS but not to dV: recompute the keep bits instead of inferring them
-                            const uint32_t h = dropout_hash(seed, drop.stream, (e_row + 32 * c + j) >> 1);
-                            d0 = (h << 16) >= thr ? d0 : 0.f;
-                            d1 = h >= thr ? d1 : 0.f;
-                        }
-                        pdk[c][j >> 1] = pack_bf16x2(d0, d1);
-                        dsk[c][j >> 1] = pack_bf16x2(p0 * (t0 - D) * scale, p1 * (t1 - D) * scale);
+                        float g0, g1;
+                        unpack2(mul2(pack2(__uint_as_float(s[0][j]), __uint_as_float(s[0][j + 1])),
+                                     add2(pack2(__uint_as_float(dp[0][j]), __uint_as_float(dp[0][j + 1])), nD2)), g0, g1);
+                        dsk[0][j >> 1] = pack_bf16x2(g0, g1);
                     }
                 }
                 // ---- the previous step's outputs leave TMEM before the tensor core may overwrite them
+                if (warp == 4) stamp(1, 4);
                 if (have_prev) drain();
+                if (warp == 4) stamp(1, 5);
                 // ---- Pd_s / dS_s rows (swizzled 16-byte pieces), then hand over to the tensor core
 #pragma unroll
                 for (int c = 0; c < NCH; ++c)
@@ -1093,6 +1150,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
                 ptx::tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(&bars->pds_full);
+                if (warp == 4) stamp(1, 6);
                 have_prev = true;
                 prev_last = i + 1 == nsteps;
             }
@@ -1126,9 +1184,9 @@ __global__ void __launch_bounds__(256) attn_tc_dot_kernel(const bf16 *__restrict
     if (lane == 0) D[((row / N) * H + h) * N + row % N] = part;
 }
 
-// dqkv[:, 0 : inner] = bf16(dq_acc)   (long geometry: dQ was accumulated in fp32 across the key blocks)
+// dqkv[:, 0 : inner] = bf16(scale * dq_acc)   (long geometry: dS K was accumulated in fp32 across the key blocks)
 __global__ void __launch_bounds__(256) attn_tc_dq_convert_kernel(const float *__restrict__ acc, bf16 *__restrict__ dqkv,
-                                                                  int64_t rows, int inner) {
+                                                                  int64_t rows, int inner, float mul) {
     pdl_launch_dependents();
     pdl_wait();
     const int64_t n8 = rows * (inner / 8);
@@ -1138,6 +1196,8 @@ __global__ void __launch_bounds__(256) attn_tc_dq_convert_kernel(const float *__
         const int c = static_cast<int>(i - row * (inner / 8)) * 8;
         float v[8];
         load8(acc + row * inner + c, v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] *= mul;
         store8(dqkv + row * 3 * static_cast<int64_t>(inner) + c, v);
     }
 }
@@ -1162,9 +1222,11 @@ int launch_bwd(const void *qkv, const void *d_o, const float *lse, const float *
     }
     const int items = kPacked ? (B * H + 1) >> 1 : B * H * ((N + TN - 1) / TN);
     const int grid = items < sm_count() ? items : sm_count();
+    long long *tl = timeline_begin("ECGVIT_ATTN_TIMELINE_BWD");
     cudaError_t le = launch_pdl(kern, dim3(grid), dim3(384), BwdMap<kPacked>::SMEM_BYTES, stream, tq, td, tout, tacc, lse,
-                                Drow, B, N, H, scale, drop);
+                                Drow, B, N, H, scale, drop, tl);
     if (le != cudaSuccess) return fail((int)le, "attn_tc_bwd launch: %s", cudaGetErrorString(le));
+    timeline_end(tl, "ECGVIT_ATTN_TIMELINE_BWD");
     return check_launch("attn_tc_bwd");
 }
 
@@ -1218,7 +1280,7 @@ int attention_bwd_tc(const void *qkv, const void *o, const void *d_o, const floa
     int rc = launch_bwd<false>(qkv, d_o, lse, Drow, dqkv, dq_acc, B, N, H, scale, drop, stream);
     if (rc) return rc;
     e = launch_pdl(attn_tc_dq_convert_kernel, dim3(sm_count() * 4), dim3(256), 0, stream,
-                   static_cast<const float *>(dq_acc), reinterpret_cast<bf16 *>(dqkv), rows, (int)inner);
+                   static_cast<const float *>(dq_acc), reinterpret_cast<bf16 *>(dqkv), rows, (int)inner, scale);
     if (e != cudaSuccess) return fail((int)e, "attn_tc_dq_convert launch: %s", cudaGetErrorString(e));
     return check_launch("attn_tc_dq_convert");
 }
