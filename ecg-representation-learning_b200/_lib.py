@@ -11,9 +11,9 @@ from ctypes import c_int, c_int64, c_float, c_void_p, c_char_p, POINTER, Structu
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, 'libecgvit_b200.so')
 
-F32, BF16 = 0, 1
+F32, BF16, BF16_RES32 = 0, 1, 2  # BF16_RES32: bf16 mode whose residual-stream operand is fp32 (ecgvit_b200.h)
 STATS_FLOATS = 2052  # ECGVIT_STATS_FLOATS
-EPI_STORE, EPI_BIAS_RES, EPI_BIAS_GELU, EPI_DGELU, EPI_ATOMIC_F32 = 0, 1, 2, 3, 4
+EPI_STORE, EPI_BIAS_RES, EPI_BIAS_GELU, EPI_DGELU, EPI_ATOMIC_F32, EPI_BIAS_RES_F32 = 0, 1, 2, 3, 4, 5
 REDUCTION = {'mean': 0, 'sum': 1, 'none': 2}
 
 

@@ -24,7 +24,7 @@ class EcgVitConfig(PretrainedConfig):
                  hidden_size: int = 512, num_hidden_layers: int = 8, num_attention_heads: int = 8,
                  intermediate_size: int = 2048, hidden_dropout_prob: float = 0.1,
                  attention_probs_dropout_prob: float = 0.1, num_class: int = 71,
-                 compute_dtype: str = 'bf16', per_lead_tokens: bool = False, **kwargs):
+                 compute_dtype: str = 'bf16', per_lead_tokens: bool = False, residual_dtype: str = 'auto', **kwargs):
         self.max_signal_length = max_signal_length
         self.patch_size = patch_size
         self.num_channels = num_channels
@@ -42,6 +42,10 @@ class EcgVitConfig(PretrainedConfig):
         # True  = BASELINE.json configs[3]: every lead is tokenised on its own (vit_pytorch ViT(image_size=(C, L),
         #         patch_size=(1, P), channels=1)), N = C * L / P + 1 -- not constructible through the reference wrapper
         self.per_lead_tokens = per_lead_tokens
+        # storage type of the residual stream (the running sum through the blocks) in bf16 mode: 'bf16', 'fp32', or 'auto'
+        # = fp32 for models deeper than 12 layers.  bf16 rounding of the stream random-walks with depth: the 24-layer
+        # 'large' model needs fp32 here to stay within 1e-2 of the fp32 reference; up to 12 layers bf16 is inside the bar
+        self.residual_dtype = residual_dtype
         super().__init__(**kwargs)
         self.size = None
 

@@ -54,6 +54,8 @@ int ecgvit_gemm(const ecgvit_gemm_args *g, void *stream) {
     if (g->epilogue == ECGVIT_EPI_BIAS_GELU && g->out2 == nullptr) return ecgvit::fail(-1, "gemm: BIAS_GELU needs out2");
     if ((g->epilogue == ECGVIT_EPI_BIAS_RES || g->epilogue == ECGVIT_EPI_DGELU) && g->aux == nullptr)
         return ecgvit::fail(-1, "gemm: epilogue %d needs aux", g->epilogue);
+    if (g->epilogue == ECGVIT_EPI_BIAS_RES_F32 && g->dtype != ECGVIT_BF16)
+        return ecgvit::fail(-1, "gemm: the fp32-residual epilogue belongs to bf16 mode (fp32 mode uses BIAS_RES)");
     if (g->dtype == ECGVIT_BF16) return ecgvit::gemm_bf16_tc(g, ecgvit::as_stream(stream));
     if (g->dtype == ECGVIT_F32) return ecgvit::gemm_f32_ffma(g, ecgvit::as_stream(stream));
     return ecgvit::fail(-1, "gemm: unknown dtype %d", g->dtype);

@@ -117,9 +117,9 @@ __global__ void unpad_add_kernel(const float *__restrict__ src, float *__restric
 
 // ---------------------------------------------------------------------------------------------------
 // tok[b,0,:] = cls + pos[0];  tok[b,1+w,:] = e[b*n+w,:] + pos[1+w,:]
-template <typename T>
+template <typename T, typename TO>
 __global__ void embed_assemble_kernel(const T *__restrict__ e, const float *__restrict__ cls,
-                                      const float *__restrict__ pos, T *__restrict__ tok, int B, int n_patch, int d,
+                                      const float *__restrict__ pos, TO *__restrict__ tok, int B, int n_patch, int d,
                                       DropoutParams drop) {
     const bool dropping = drop.threshold != 0;
     const uint32_t seed = dropping ? __ldg(drop.seed) : 0u;
@@ -237,8 +237,8 @@ __device__ __forceinline__ float pair_sum(uint64_t v) {
 // LayerNorm forward: one warp per row, NV 8-element vectors per lane (d <= 256 * NV), packed fp32x2 math,
 // two-pass statistics (mean, then centred sum of squares) like ATen.  R rows are in flight per warp and MINB CTAs per
 // SM are requested from ptxas; the launcher picks R = 1, MINB = 5 (see the measurements there).
-template <typename T, int NV, int R, int MINB>
-__global__ void __launch_bounds__(256, MINB) layernorm_fwd_kernel(const T *__restrict__ x, const float *__restrict__ gamma,
+template <typename T, int NV, int R, int MINB, typename TX = T>
+__global__ void __launch_bounds__(256, MINB) layernorm_fwd_kernel(const TX *__restrict__ x, const float *__restrict__ gamma,
                                                              const float *__restrict__ beta, T *__restrict__ y,
                                                              float *__restrict__ mean_out, float *__restrict__ rstd_out,
                                                              int M, int d, float eps) {
@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(256, MINB) layernorm_fwd_kernel(const T *__res
             for (int i = 0; i < NV; ++i) {
                 const int c = (i * 32 + lane) * 8;
                 if (live[r] && c < d) {
-                    Packed8<T> p;
+                    Packed8<TX> p;
                     ld_packed(p, x + row * d + c);
                     unpack_pairs(p, v[r][i]);
                 } else {
@@ -319,8 +319,8 @@ __global__ void __launch_bounds__(256, MINB) layernorm_fwd_kernel(const T *__res
 //   with s1 = mean_c(dy * gamma), s2 = mean_c(dy * gamma * xhat)
 // kDrop: dx feeds a Linear through a dropout (to_out[1] / net[4] of the block below): additionally write
 // dxm = mask * dx / (1 - p) (that Linear's dgrad / wgrad operand) and make the column sums those of dxm (its bias grad).
-template <typename T, int NV, bool kDrop>
-__global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const T *__restrict__ dy, const T *__restrict__ x,
+template <typename T, int NV, bool kDrop, typename TX = T>
+__global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const T *__restrict__ dy, const TX *__restrict__ x,
                                                                 const float *__restrict__ gamma,
                                                                 const float *__restrict__ mean_in,
                                                                 const float *__restrict__ rstd_in, const T *dres, T *dx,
@@ -353,7 +353,8 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const T *__restri
 
     for (int64_t row = (int64_t)blockIdx.x * warps_per_block + warp; row < M;
          row += (int64_t)gridDim.x * warps_per_block) {
-        Packed8<T> pdy[NV], px[NV], pres[NV];
+        Packed8<T> pdy[NV], pres[NV];
+        Packed8<TX> px[NV];
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
             const int c = (i * 32 + lane) * 8;
@@ -651,9 +652,11 @@ int ecgvit_embed_assemble(const void *e, const float *cls, const float *pos, voi
     const int64_t total = (int64_t)B * (n_patch + 1) * (d / 8);
     const int grid = grid_for(total, 256);
     if (dtype == ECGVIT_BF16)
-        embed_assemble_kernel<bf16><<<grid, 256, 0, as_stream(stream)>>>((const bf16 *)e, cls, pos, (bf16 *)tok, B, n_patch, d, drop);
+        embed_assemble_kernel<bf16, bf16><<<grid, 256, 0, as_stream(stream)>>>((const bf16 *)e, cls, pos, (bf16 *)tok, B, n_patch, d, drop);
+    else if (dtype == ECGVIT_BF16_RES32)
+        embed_assemble_kernel<bf16, float><<<grid, 256, 0, as_stream(stream)>>>((const bf16 *)e, cls, pos, (float *)tok, B, n_patch, d, drop);
     else if (dtype == ECGVIT_F32)
-        embed_assemble_kernel<float><<<grid, 256, 0, as_stream(stream)>>>((const float *)e, cls, pos, (float *)tok, B, n_patch, d, drop);
+        embed_assemble_kernel<float, float><<<grid, 256, 0, as_stream(stream)>>>((const float *)e, cls, pos, (float *)tok, B, n_patch, d, drop);
     else return fail(-1, "embed_assemble: unknown dtype %d", dtype);
     return check_launch("embed_assemble");
 }
@@ -693,6 +696,17 @@ int ecgvit_layernorm_fwd(const void *x, const float *gamma, const float *beta, v
             case 3: ECGVIT_LN_FWD(bf16, 3); break;
             default: ECGVIT_LN_FWD(bf16, 4); break;
         }
+    } else if (dtype == ECGVIT_BF16_RES32) {   // fp32 residual stream in, bf16 operand out
+#define ECGVIT_LN_FWD_R(NVV)                                                                                            \
+    launch_pdl(layernorm_fwd_kernel<bf16, NVV, 1, 4, float>, dim3(grid), dim3(256), 0, st, (const float *)x, gamma, beta, \
+               (bf16 *)y, mean, rstd, M, d, eps)
+        switch (nv) {
+            case 1: ECGVIT_LN_FWD_R(1); break;
+            case 2: ECGVIT_LN_FWD_R(2); break;
+            case 3: ECGVIT_LN_FWD_R(3); break;
+            default: ECGVIT_LN_FWD_R(4); break;
+        }
+#undef ECGVIT_LN_FWD_R
     } else if (dtype == ECGVIT_F32) {
         switch (nv) {
             case 1: ECGVIT_LN_FWD(float, 1); break;
@@ -734,25 +748,33 @@ int ecgvit_layernorm_bwd(const void *dy, const void *x, const float *gamma, cons
     const int nv = (d + 255) / 256;
     const size_t smem = (8 * 3 * (size_t)d + (size_t)nv * 256) * sizeof(float);  // warp slabs + permuted gamma
     cudaStream_t st = as_stream(stream);
-#define ECGVIT_LN_BWD2(TT, NVV, DROP)                                                                                  \
+#define ECGVIT_LN_BWD2(TT, NVV, DROP, TXX)                                                                             \
     do {                                                                                                               \
         static bool attr_set = false;                                                                                  \
         if (!attr_set) {                                                                                               \
-            cudaFuncSetAttribute(layernorm_bwd_kernel<TT, NVV, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+            cudaFuncSetAttribute(layernorm_bwd_kernel<TT, NVV, DROP, TXX>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                  25 * 1024 * 4);                                                                       \
             attr_set = true;                                                                                           \
         }                                                                                                              \
-        launch_pdl(layernorm_bwd_kernel<TT, NVV, DROP>, dim3(grid), dim3(256), smem, st, (const TT *)dy,              \
-                   (const TT *)x, gamma, mean, rstd, (const TT *)dres, (TT *)dx, dgamma, dbeta, dcolsum, scratch, M, d, \
+        launch_pdl(layernorm_bwd_kernel<TT, NVV, DROP, TXX>, dim3(grid), dim3(256), smem, st, (const TT *)dy,         \
+                   (const TXX *)x, gamma, mean, rstd, (const TT *)dres, (TT *)dx, dgamma, dbeta, dcolsum, scratch, M, d, \
                    (TT *)dxm, drop);                                                                                   \
     } while (0)
-#define ECGVIT_LN_BWD(TT, NVV) do { if (dropping) ECGVIT_LN_BWD2(TT, NVV, true); else ECGVIT_LN_BWD2(TT, NVV, false); } while (0)
+#define ECGVIT_LN_BWD(TT, NVV) do { if (dropping) ECGVIT_LN_BWD2(TT, NVV, true, TT); else ECGVIT_LN_BWD2(TT, NVV, false, TT); } while (0)
+#define ECGVIT_LN_BWD_R(NVV) do { if (dropping) ECGVIT_LN_BWD2(bf16, NVV, true, float); else ECGVIT_LN_BWD2(bf16, NVV, false, float); } while (0)
     if (dtype == ECGVIT_BF16) {
         switch (nv) {
             case 1: ECGVIT_LN_BWD(bf16, 1); break;
             case 2: ECGVIT_LN_BWD(bf16, 2); break;
             case 3: ECGVIT_LN_BWD(bf16, 3); break;
             default: ECGVIT_LN_BWD(bf16, 4); break;
+        }
+    } else if (dtype == ECGVIT_BF16_RES32) {   // x (the residual stream) is fp32, gradients stay bf16
+        switch (nv) {
+            case 1: ECGVIT_LN_BWD_R(1); break;
+            case 2: ECGVIT_LN_BWD_R(2); break;
+            case 3: ECGVIT_LN_BWD_R(3); break;
+            default: ECGVIT_LN_BWD_R(4); break;
         }
     } else if (dtype == ECGVIT_F32) {
         switch (nv) {
@@ -763,6 +785,7 @@ int ecgvit_layernorm_bwd(const void *dy, const void *x, const float *gamma, cons
         }
     } else return fail(-1, "layernorm_bwd: unknown dtype %d", dtype);
 #undef ECGVIT_LN_BWD
+#undef ECGVIT_LN_BWD_R
 #undef ECGVIT_LN_BWD2
     int rc = check_launch("layernorm_bwd");
     if (rc || defer_finalize) return rc;

@@ -14,7 +14,7 @@
 //   tmem_empty[a]  on the LEADER : 8 epilogue warps x 2 CTAs arrive (remote arrive from the peer)
 #pragma once
 
-template <int BN, bool B_MN> struct PairCfg {
+template <int BN, bool B_MN, bool WIDE = false> struct PairCfg {
     static constexpr int B_HALF = BN / 2;                                      // B rows (N values) per CTA
     // MN-major B is staged in 64-wide chunks; at BN = 192 the second chunk is only half used (over-fetch)
     static constexpr int B_LOAD_ROWS = B_MN ? ((B_HALF + 63) / 64) * 64 : B_HALF;
@@ -26,8 +26,9 @@ template <int BN, bool B_MN> struct PairCfg {
     static constexpr int EPI_WARPS = BN / 16;
     static constexpr int THREADS = 128 + 32 * EPI_WARPS;
     static constexpr int UNITS_PER_WARP = 2;                                   // 32-column units per epilogue warp
-    // staging: every epilogue warp owns two 32-row x 64-byte (32 bf16, SWIZZLE_64B) tiles
-    static constexpr int EPI_TILE_BYTES = 32 * 64;
+    // staging: every epilogue warp owns two 32-row x 32-column tiles: 64-byte rows of bf16 (SWIZZLE_64B), or 128-byte
+    // rows of fp32 (SWIZZLE_128B) for the fp32 residual stream (WIDE)
+    static constexpr int EPI_TILE_BYTES = WIDE ? 32 * 128 : 32 * 64;
     static constexpr int EPI_TILES_PER_WARP = 2;
     static constexpr int EPI_BYTES = EPI_WARPS * EPI_TILES_PER_WARP * EPI_TILE_BYTES;
     static constexpr int NUM_BARRIERS = 2 * 8 + 4 + EPI_WARPS * EPI_TILES_PER_WARP;
@@ -107,13 +108,41 @@ __device__ __forceinline__ void epilogue_half16(const EpiParams &ep, int64_t row
     }
 }
 
+// fp32 residual stream (ECGVIT_EPI_BIAS_RES_F32): out = drop(acc + bias) + aux with aux / out fp32.  The warp's staging
+// tile is 32 rows x 128 bytes (SWIZZLE_128B) and already holds the residual; 16 columns = four 16-byte pieces per call.
+__device__ __forceinline__ void epilogue_half16_f32(const EpiParams &ep, int64_t row, int col_base, int half,
+                                                    const uint32_t r[16], uint8_t *tile, int lane, float bias_lane) {
+    const bool drop = ep.drop.threshold != 0;  // kernel-uniform
+    const uint32_t seed = drop ? __ldg(ep.drop.seed) : 0u;
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+        const int jc = 4 * half + jj;  // 16-byte piece (4 floats) of the 32-column row
+        const int col = col_base + 4 * jc;
+        float v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[4 * jj + i]);
+        if (ep.bias != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[i] += __shfl_sync(0xffffffffu, bias_lane, 4 * jc + i);
+        }
+        if (drop) dropout_apply<4>(ep.drop, seed, static_cast<uint32_t>(row * ep.ldo + col), v);
+        float4 *p = reinterpret_cast<float4 *>(tile + static_cast<uint32_t>(lane) * 128u +
+                                               (static_cast<uint32_t>(jc ^ (lane & 7)) << 4));
+        float4 a = *p;
+        a.x += v[0]; a.y += v[1]; a.z += v[2]; a.w += v[3];
+        *p = a;
+    }
+}
+
 template <int BN, bool A_MN, bool B_MN, int MODE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairCfg<BN, B_MN>::THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1)
+__launch_bounds__(PairCfg<BN, B_MN, MODE == ECGVIT_EPI_BIAS_RES_F32>::THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                 const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_out2,
                 const __grid_constant__ CUtensorMap tmap_aux, int M, int N, int K, int split_k, EpiParams ep) {
-    using Cfg = PairCfg<BN, B_MN>;
-    constexpr bool kHasAux = (MODE == ECGVIT_EPI_BIAS_RES || MODE == ECGVIT_EPI_DGELU);
+    constexpr bool kWide = MODE == ECGVIT_EPI_BIAS_RES_F32;
+    using Cfg = PairCfg<BN, B_MN, kWide>;
+    constexpr bool kHasAux = (MODE == ECGVIT_EPI_BIAS_RES || MODE == ECGVIT_EPI_DGELU || kWide);
     constexpr int STAGES = Cfg::STAGES;
     constexpr int BM2 = 2 * BM;  // rows of the pair tile
 
@@ -339,10 +368,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                         if (lane == 0) ptx::tma_store_wait_read<0>();
                         __syncwarp();
                     }
-                    epilogue_half16<MODE>(ep, row, col_base, 0, ra, t0, t1, lane, bias_lane);
+                    if (kWide) epilogue_half16_f32(ep, row, col_base, 0, ra, t0, lane, bias_lane);
+                    else epilogue_half16<MODE>(ep, row, col_base, 0, ra, t0, t1, lane, bias_lane);
                     ptx::tmem_ld_wait_bind(rb);
                     if (i + 1 < n_units) ptx::tmem_ld_32x16(taddr0 + 32 * (i + 1), ra);
-                    epilogue_half16<MODE>(ep, row, col_base, 2, rb, t0, t1, lane, bias_lane);
+                    if (kWide) epilogue_half16_f32(ep, row, col_base, 1, rb, t0, lane, bias_lane);
+                    else epilogue_half16<MODE>(ep, row, col_base, 2, rb, t0, t1, lane, bias_lane);
                     ptx::fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
                     __syncwarp();
                     if (lane == 0) {

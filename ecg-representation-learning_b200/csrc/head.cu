@@ -111,8 +111,8 @@ __global__ void __launch_bounds__(1024) bce_loss_kernel(const float *__restrict_
 }
 
 // backward A: per sample, dlogits -> dxn = dlogits W -> LayerNorm' -> CLS row of dtok
-template <typename T>
-__global__ void __launch_bounds__(128) head_bwd_rows_kernel(const T *__restrict__ tok, const float *__restrict__ gamma,
+template <typename T, typename TX = T>
+__global__ void __launch_bounds__(128) head_bwd_rows_kernel(const TX *__restrict__ tok, const float *__restrict__ gamma,
                                                              const float *__restrict__ w,
                                                              const float *__restrict__ labels,
                                                              const float *__restrict__ mean_in,
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(128) head_bwd_rows_kernel(const T *__restrict_
         }
     }
     const float mean = mean_in[b], rstd = rstd_in[b];
-    const T *xr = tok + (int64_t)b * N * d;
+    const TX *xr = tok + (int64_t)b * N * d;
     float g[HEAD_MAXV][8], xh[HEAD_MAXV][8];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -183,8 +183,8 @@ __global__ void __launch_bounds__(128) head_bwd_rows_kernel(const T *__restrict_
 
 // backward B: per column k: dgamma, dbeta of the head LayerNorm and the column sum of the CLS-row gradients.
 // block = 32 columns x 8 sample groups, smem tree at the end
-template <typename T>
-__global__ void __launch_bounds__(256) head_bwd_cols_kernel(const T *__restrict__ tok, const T *__restrict__ dtok,
+template <typename T, typename TX = T>
+__global__ void __launch_bounds__(256) head_bwd_cols_kernel(const TX *__restrict__ tok, const T *__restrict__ dtok,
                                                              const float *__restrict__ dxn,
                                                              const float *__restrict__ mean_in,
                                                              const float *__restrict__ rstd_in,
@@ -263,7 +263,7 @@ int ecgvit_head_fwd(const void *tok, const float *gamma, const float *beta, cons
     const int grid = B;
     if (dtype == ECGVIT_BF16)
         head_fwd_kernel<bf16><<<grid, 128, 0, as_stream(stream)>>>((const bf16 *)tok, gamma, beta, w, b, xn, mean, rstd, logits, B, N, d, n_class, eps);
-    else if (dtype == ECGVIT_F32)
+    else if (dtype == ECGVIT_F32 || dtype == ECGVIT_BF16_RES32)   // fp32 tokens (parity mode / fp32 residual stream)
         head_fwd_kernel<float><<<grid, 128, 0, as_stream(stream)>>>((const float *)tok, gamma, beta, w, b, xn, mean, rstd, logits, B, N, d, n_class, eps);
     else return fail(-1, "head_fwd: unknown dtype %d", dtype);
     int rc = check_launch("head_fwd");
@@ -290,7 +290,7 @@ int ecgvit_head_bwd(const void *tok, const float *gamma, const float *w, const f
     ECGVIT_REQUIRE(d % 8 == 0 && d <= 8 * 32 * HEAD_MAXV, "head_bwd: d=%d must be a multiple of 8 and <= %d", d,
                    8 * 32 * HEAD_MAXV);
     cudaStream_t s = as_stream(stream);
-    const size_t esz = dtype == ECGVIT_BF16 ? 2 : 4;
+    const size_t esz = dtype == ECGVIT_F32 ? 4 : 2;   // dtok is bf16 in both bf16 modes
     cudaError_t e = cudaMemsetAsync(dtok, 0, (size_t)B * N * d * esz, s);
     if (e != cudaSuccess) return fail((int)e, "head_bwd: memset: %s", cudaGetErrorString(e));
     const float coef = grad_scale * (reduction == ECGVIT_REDUCTION_MEAN ? 1.0f / ((float)B * (float)n_class) : 1.0f);
@@ -299,6 +299,9 @@ int ecgvit_head_bwd(const void *tok, const float *gamma, const float *w, const f
     if (dtype == ECGVIT_BF16) {
         head_bwd_rows_kernel<bf16><<<grid, 128, 0, s>>>((const bf16 *)tok, gamma, w, labels, mean, rstd, logits, (bf16 *)dtok, dxn, dlog, B, N, d, n_class, coef, loss_weight, n_weight);
         head_bwd_cols_kernel<bf16><<<(d + 31) / 32, 256, 0, s>>>((const bf16 *)tok, (const bf16 *)dtok, dxn, mean, rstd, dgamma, dbeta, dcolsum, B, N, d);
+    } else if (dtype == ECGVIT_BF16_RES32) {
+        head_bwd_rows_kernel<bf16, float><<<grid, 128, 0, s>>>((const float *)tok, gamma, w, labels, mean, rstd, logits, (bf16 *)dtok, dxn, dlog, B, N, d, n_class, coef, loss_weight, n_weight);
+        head_bwd_cols_kernel<bf16, float><<<(d + 31) / 32, 256, 0, s>>>((const float *)tok, (const bf16 *)dtok, dxn, mean, rstd, dgamma, dbeta, dcolsum, B, N, d);
     } else if (dtype == ECGVIT_F32) {
         head_bwd_rows_kernel<float><<<grid, 128, 0, s>>>((const float *)tok, gamma, w, labels, mean, rstd, logits, (float *)dtok, dxn, dlog, B, N, d, n_class, coef, loss_weight, n_weight);
         head_bwd_cols_kernel<float><<<(d + 31) / 32, 256, 0, s>>>((const float *)tok, (const float *)dtok, dxn, mean, rstd, dgamma, dbeta, dcolsum, B, N, d);

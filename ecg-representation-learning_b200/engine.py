@@ -21,7 +21,8 @@ import os
 import torch
 
 from . import _lib
-from ._lib import GemmArgs, F32, BF16, EPI_STORE, EPI_BIAS_RES, EPI_BIAS_GELU, EPI_DGELU, EPI_ATOMIC_F32
+from ._lib import (GemmArgs, F32, BF16, EPI_STORE, EPI_BIAS_RES, EPI_BIAS_GELU, EPI_DGELU, EPI_ATOMIC_F32,
+                   EPI_BIAS_RES_F32)
 
 LN_EPS = 1e-5  # nn.LayerNorm default
 
@@ -117,7 +118,8 @@ class StepEngine:
         w.embed_wpad = buf(d, Kp) if Kp != K else None
         w.embed_gpad = buf(d, Kp, dtype=torch.float32) if Kp != K else None
         w.e = buf(B * n, d)
-        w.x = [buf(M, d) for _ in range(depth + 1)]  # x[l] = input of block l; x[depth] = encoder output
+        RT = m._res_dtype  # residual stream: fp32 for deep models in bf16 mode (config.residual_dtype)
+        w.x = [buf(M, d, dtype=RT) for _ in range(depth + 1)]  # x[l] = input of block l; x[depth] = encoder output
         w.ln1 = [buf(M, d) for _ in range(depth)]
         w.ln2 = [buf(M, d) for _ in range(depth)]
         w.stat1 = [buf(2, M, dtype=torch.float32) for _ in range(depth)]
@@ -125,7 +127,7 @@ class StepEngine:
         w.qkv = [buf(M, 3 * inner) for _ in range(depth)]
         w.lse = [buf(B, H, N, dtype=torch.float32) for _ in range(depth)]
         w.o = [buf(M, inner) for _ in range(depth)]
-        w.y = [buf(M, d) for _ in range(depth)]
+        w.y = [buf(M, d, dtype=RT) for _ in range(depth)]
         w.u = [buf(M, mlp) for _ in range(depth)]
         w.h = [buf(M, mlp) for _ in range(depth)]
         # head
@@ -161,6 +163,8 @@ class StepEngine:
         m, lib, st = self.model, self.lib, self._stream
         c = m.config
         dt = m._dtype_code
+        rdt = m._res_code                                        # dtype code of calls whose operand is the residual stream
+        epi_res = EPI_BIAS_RES_F32 if m._res_f32 else EPI_BIAS_RES
         x = sample_values
         assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 3, 'sample_values must be fp32 cuda [B, C, L]'
         assert x.shape[1] == c.num_channels
@@ -205,7 +209,7 @@ class StepEngine:
         seed_ptr = self.rng.data_ptr()
         _lib.check(lib.ecgvit_embed_assemble(w.e.data_ptr(), pf['cls'].data_ptr(), pf['pos'].data_ptr(),
                                              w.x[0].data_ptr(), B, n, d, p_emb, 0, seed_ptr if p_emb > 0 else None,
-                                             dt, st), 'embed_assemble')
+                                             rdt, st), 'embed_assemble')
         scale = float(dh) ** -0.5
         blk_seed = seed_ptr if p_blk > 0 else None
         for l in range(c.num_hidden_layers):
@@ -214,7 +218,7 @@ class StepEngine:
             s_att, s_out, s_act, s_ff2 = 1 + 4 * l, 2 + 4 * l, 3 + 4 * l, 4 + 4 * l
             _lib.check(lib.ecgvit_layernorm_fwd(w.x[l].data_ptr(), pf[p + 'ln1.w'].data_ptr(), pf[p + 'ln1.b'].data_ptr(),
                                                 w.ln1[l].data_ptr(), w.stat1[l][0].data_ptr(), w.stat1[l][1].data_ptr(),
-                                                M, d, LN_EPS, dt, st), 'layernorm_fwd')
+                                                M, d, LN_EPS, rdt, st), 'layernorm_fwd')
             self._gemm(M, 3 * inner, d, w.ln1[l], d, 1, wt[p + 'qkv.w'], d, 1, EPI_STORE, w.qkv[l], 3 * inner)
             if record_attention:
                 if l == 0:
@@ -225,14 +229,14 @@ class StepEngine:
                                                       rec.stride(0), dt, st), 'attention_probs')
             _lib.check(lib.ecgvit_attention_fwd(w.qkv[l].data_ptr(), w.o[l].data_ptr(), w.lse[l].data_ptr(), B, N, H, dh,
                                                 scale, p_blk, s_att, blk_seed, dt, st), 'attention_fwd')
-            self._gemm(M, d, inner, w.o[l], inner, 1, wt[p + 'out.w'], inner, 1, EPI_BIAS_RES, w.y[l], d,
+            self._gemm(M, d, inner, w.o[l], inner, 1, wt[p + 'out.w'], inner, 1, epi_res, w.y[l], d,
                        aux=w.x[l], bias=pf[p + 'out.b'], drop=(p_blk, s_out))
             _lib.check(lib.ecgvit_layernorm_fwd(w.y[l].data_ptr(), pf[p + 'ln2.w'].data_ptr(), pf[p + 'ln2.b'].data_ptr(),
                                                 w.ln2[l].data_ptr(), w.stat2[l][0].data_ptr(), w.stat2[l][1].data_ptr(),
-                                                M, d, LN_EPS, dt, st), 'layernorm_fwd')
+                                                M, d, LN_EPS, rdt, st), 'layernorm_fwd')
             self._gemm(M, mlp, d, w.ln2[l], d, 1, wt[p + 'ff1.w'], d, 1, EPI_BIAS_GELU, w.u[l], mlp,
                        out2=w.h[l], bias=pf[p + 'ff1.b'], drop=(p_blk, s_act))
-            self._gemm(M, d, mlp, w.h[l], mlp, 1, wt[p + 'ff2.w'], mlp, 1, EPI_BIAS_RES, w.x[l + 1], d,
+            self._gemm(M, d, mlp, w.h[l], mlp, 1, wt[p + 'ff2.w'], mlp, 1, epi_res, w.x[l + 1], d,
                        aux=w.y[l], bias=pf[p + 'ff2.b'], drop=(p_blk, s_ff2))
         red = _lib.REDUCTION[reduction]
         loss_buf = None
@@ -244,7 +248,7 @@ class StepEngine:
             w.x[c.num_hidden_layers].data_ptr(), pf['head.ln.w'].data_ptr(), pf['head.ln.b'].data_ptr(),
             pf['head.w'].data_ptr(), pf['head.b'].data_ptr(), w.labels.data_ptr() if labels is not None else None,
             *self._loss_weight_table(), w.xn.data_ptr(), w.hstat[0].data_ptr(), w.hstat[1].data_ptr(), w.logits.data_ptr(),
-            _lib.ptr(loss_buf), B, N, d, m.num_class, red, LN_EPS, dt, st), 'head_fwd')
+            _lib.ptr(loss_buf), B, N, d, m.num_class, red, LN_EPS, rdt, st), 'head_fwd')
         w.reduction = reduction
         loss = None
         if labels is not None:
@@ -281,6 +285,7 @@ class StepEngine:
         m, lib, st = self.model, self.lib, self._stream
         c = m.config
         dt = m._dtype_code
+        rdt = m._res_code
         w = self._cur
         assert w is not None, 'backward before forward'
         assert w.reduction in ('mean', 'sum'), "backward needs loss_reduction 'mean' or 'sum'"
@@ -303,7 +308,7 @@ class StepEngine:
             *self._loss_weight_table(), w.xn.data_ptr(), w.hstat[0].data_ptr(), w.hstat[1].data_ptr(), w.logits.data_ptr(), dz.data_ptr(),
             gr['head.w'].data_ptr(), gr['head.b'].data_ptr(), gr['head.ln.w'].data_ptr(), gr['head.ln.b'].data_ptr(),
             gr[last + 'ff2.b'].data_ptr() if p_blk == 0 else None, w.head_scratch.data_ptr(), B, N, d, m.num_class,
-            _lib.REDUCTION[w.reduction], float(grad_scale), dt, st), 'head_bwd')
+            _lib.REDUCTION[w.reduction], float(grad_scale), rdt, st), 'head_bwd')
         scale = float(dh) ** -0.5
 
         main, side = torch.cuda.current_stream(), self.side_stream
@@ -347,7 +352,7 @@ class StepEngine:
             _lib.check(lib.ecgvit_layernorm_bwd(
                 dln.data_ptr(), x_in.data_ptr(), gamma.data_ptr(), stat[0].data_ptr(), stat[1].data_ptr(),
                 dres.data_ptr(), dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), _lib.ptr(dcol), scr.data_ptr(),
-                _lib.ptr(dxm), p_drop, site, seed, M, d, 0 if side is None else 1, dt, st),
+                _lib.ptr(dxm), p_drop, site, seed, M, d, 0 if side is None else 1, rdt, st),
                 'layernorm_bwd' if side is None else 'layernorm_bwd_partial')
             if side is not None:
                 ready = torch.cuda.Event()

@@ -165,6 +165,13 @@ class EcgVit(nn.Module):
             raise ValueError(f"compute_dtype must be 'bf16' or 'fp32', got {dt!r}")
         self._dtype_code = _lib.BF16 if dt == 'bf16' else _lib.F32
         self._act_dtype = torch.bfloat16 if dt == 'bf16' else torch.float32
+        rd = getattr(config, 'residual_dtype', 'auto')
+        if rd not in ('auto', 'bf16', 'fp32'):
+            raise ValueError(f"residual_dtype must be 'auto', 'bf16' or 'fp32', got {rd!r}")
+        # fp32 residual stream in bf16 mode (config.py): the kernels that touch the stream get dtype code BF16_RES32
+        self._res_f32 = dt == 'bf16' and (rd == 'fp32' or (rd == 'auto' and config.num_hidden_layers > 12))
+        self._res_code = _lib.BF16_RES32 if self._res_f32 else self._dtype_code
+        self._res_dtype = torch.float32 if self._res_f32 else self._act_dtype
         self._flat_p = self._flat_g = self._shadow = None
         self._layout = None
         self._engine = None

@@ -25,9 +25,14 @@
 extern "C" {
 #endif
 
-#define ECGVIT_ABI_VERSION 5
+#define ECGVIT_ABI_VERSION 6
 
-enum { ECGVIT_F32 = 0, ECGVIT_BF16 = 1 };
+/* ECGVIT_BF16_RES32: bf16 mode with an fp32 RESIDUAL STREAM (the running sum x / y of the blocks, which deep models such
+ * as 'large' need to stay within 1e-2 of the fp32 reference).  Accepted by the entry points that touch the stream, which
+ * then take that one operand as fp32: ecgvit_embed_assemble (tok), ecgvit_layernorm_fwd (x), ecgvit_layernorm_bwd (x),
+ * ecgvit_head_fwd / ecgvit_head_bwd (tok); everything else they read or write stays bf16.  The Linear + residual GEMMs
+ * use ECGVIT_EPI_BIAS_RES_F32. */
+enum { ECGVIT_F32 = 0, ECGVIT_BF16 = 1, ECGVIT_BF16_RES32 = 2 };
 
 /* GEMM epilogues */
 enum {
@@ -35,7 +40,8 @@ enum {
     ECGVIT_EPI_BIAS_RES = 1,   /* out = acc + bias + aux          (Linear + residual add)         */
     ECGVIT_EPI_BIAS_GELU = 2,  /* out = acc + bias ; out2 = gelu_erf(out)                         */
     ECGVIT_EPI_DGELU = 3,      /* out = acc * gelu_erf'(aux)                                      */
-    ECGVIT_EPI_ATOMIC_F32 = 4  /* out(fp32) += acc                (weight gradients, split-K)     */
+    ECGVIT_EPI_ATOMIC_F32 = 4, /* out(fp32) += acc                (weight gradients, split-K)     */
+    ECGVIT_EPI_BIAS_RES_F32 = 5 /* out(fp32) = acc + bias + aux(fp32)  (bf16 GEMM, fp32 residual stream) */
 };
 
 enum { ECGVIT_REDUCTION_MEAN = 0, ECGVIT_REDUCTION_SUM = 1, ECGVIT_REDUCTION_NONE = 2 };

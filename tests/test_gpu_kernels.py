@@ -351,3 +351,85 @@ def test_cast_shadow(lib):
     dst = torch.empty(100003, device='cuda', dtype=torch.bfloat16)
     L.check(lib.ecgvit_cast_f32_to_bf16(src.data_ptr(), dst.data_ptr(), src.numel(), stream()), 'cast')
     assert torch.equal(dst, src.bfloat16())
+
+
+# ---- fp32 residual stream (ECGVIT_BF16_RES32 / ECGVIT_EPI_BIAS_RES_F32) -----------------------------------------------
+@pytest.mark.parametrize('shape', [(304, 256, 192), (1000, 768, 768), (2048, 1024, 4096), (333, 264, 600)])
+def test_gemm_fp32_residual_epilogue(lib, shape):
+    M, N, K = shape
+    A, B, acc = _operands(M, N, K, 1, 1, torch.bfloat16, seed=M + 1)
+    bias = torch.randn(N, device='cuda')
+    aux = torch.randn(M, N, device='cuda') * 30.0          # a stream much larger than the update: bf16 would lose it
+    out = torch.zeros(M, N, device='cuda')
+    gemm(lib, A, B, M, N, K, 1, 1, L.EPI_BIAS_RES_F32, out, L.BF16, aux=aux, bias=bias)
+    want = acc + bias + aux
+    assert rel(out, want) < 2e-5, rel(out, want)   # fp32 accumulation order over K; a bf16 stream would sit at 2e-3
+    assert float((out - want).abs().max()) < 1e-3 * float(acc.abs().max())
+    # in place (out == aux), as the engine never does but the ABI allows with distinct tiles per warp
+    with pytest.raises(RuntimeError):
+        gemm(lib, A.float(), B.float(), M, N, K, 1, 1, L.EPI_BIAS_RES_F32, out, L.F32, aux=aux, bias=bias)
+
+
+@pytest.mark.parametrize('d', [64, 256, 768, 1024])
+def test_layernorm_fp32_stream_in_bf16_out(lib, d):
+    M = 777
+    x = torch.randn(M, d, device='cuda') * 2 + 0.5
+    gamma, beta = torch.randn(d, device='cuda'), torch.randn(d, device='cuda')
+    y = torch.empty(M, d, device='cuda', dtype=torch.bfloat16)
+    mean, rstd = torch.empty(M, device='cuda'), torch.empty(M, device='cuda')
+    L.check(lib.ecgvit_layernorm_fwd(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), mean.data_ptr(),
+                                     rstd.data_ptr(), M, d, 1e-5, L.BF16_RES32, stream()), 'ln')
+    xr = x.clone().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    yr = torch.nn.functional.layer_norm(xr, (d,), gr, br, 1e-5)
+    assert rel(y, yr) < 4e-3 and rel(mean, xr.mean(-1)) < 1e-5
+    assert rel(rstd, 1.0 / torch.sqrt(xr.var(-1, unbiased=False) + 1e-5)) < 1e-5
+    dy = torch.randn(M, d, device='cuda').bfloat16()
+    dres = torch.randn(M, d, device='cuda').bfloat16()
+    yr.backward(dy.float())
+    dx = torch.empty(M, d, device='cuda', dtype=torch.bfloat16)
+    dg, db, dc = (torch.zeros(d, device='cuda') for _ in range(3))
+    scratch = torch.empty(int(lib.ecgvit_layernorm_bwd_scratch_floats(d)), device='cuda')
+    L.check(lib.ecgvit_layernorm_bwd(dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                     dres.data_ptr(), dx.data_ptr(), dg.data_ptr(), db.data_ptr(), dc.data_ptr(),
+                                     scratch.data_ptr(), None, 0.0, 0, None, M, d, 0, L.BF16_RES32, stream()), 'ln_bwd')
+    want_dx = xr.grad + dres.float()
+    assert rel(dx, want_dx) < 5e-3
+    assert rel(dg, gr.grad) < 1e-4 and rel(db, br.grad) < 1e-4 and rel(dc, want_dx.sum(0)) < 1e-3
+
+
+def test_embed_assemble_and_head_take_fp32_stream(lib):
+    B, n, d, C = 5, 10, 128, 71
+    e = torch.randn(B * n, d, device='cuda').bfloat16()
+    cls, pos = torch.randn(d, device='cuda'), torch.randn(n + 1, d, device='cuda')
+    tok = torch.empty(B * (n + 1), d, device='cuda')
+    L.check(lib.ecgvit_embed_assemble(e.data_ptr(), cls.data_ptr(), pos.data_ptr(), tok.data_ptr(), B, n, d, 0.0, 0, None,
+                                      L.BF16_RES32, stream()), 'assemble')
+    want = torch.cat([cls.expand(B, 1, d), e.float().reshape(B, n, d)], 1) + pos
+    assert rel(tok, want.reshape(-1, d)) < 1e-7
+    # head on fp32 tokens == the fp32-mode head; its token gradient comes back in bf16
+    gamma, beta = torch.randn(d, device='cuda'), torch.randn(d, device='cuda')
+    w, b = torch.randn(C, d, device='cuda') * 0.1, torch.randn(C, device='cuda')
+    labels = (torch.rand(B, C, device='cuda') < 0.1).float()
+    N = n + 1
+    outs = {}
+    for code, td in ((L.F32, torch.float32), (L.BF16_RES32, torch.bfloat16)):
+        xn, mean, rstd = torch.empty(B, d, device='cuda'), torch.empty(B, device='cuda'), torch.empty(B, device='cuda')
+        logits, loss = torch.empty(B, C, device='cuda'), torch.empty(1, device='cuda')
+        L.check(lib.ecgvit_head_fwd(tok.data_ptr(), gamma.data_ptr(), beta.data_ptr(), w.data_ptr(), b.data_ptr(),
+                                    labels.data_ptr(), None, 0, xn.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                    logits.data_ptr(), loss.data_ptr(), B, N, d, C, 0, 1e-5, code, stream()), 'head')
+        dtok = torch.full((B * N, d), 7.0, device='cuda').to(td)
+        grads = [torch.zeros_like(t) for t in (w, b, gamma, beta)]
+        dcol = torch.zeros(d, device='cuda')
+        scratch = torch.empty(B * d + B * C, device='cuda')
+        L.check(lib.ecgvit_head_bwd(tok.data_ptr(), gamma.data_ptr(), w.data_ptr(), labels.data_ptr(), None, 0,
+                                    xn.data_ptr(), mean.data_ptr(), rstd.data_ptr(), logits.data_ptr(), dtok.data_ptr(),
+                                    grads[0].data_ptr(), grads[1].data_ptr(), grads[2].data_ptr(), grads[3].data_ptr(),
+                                    dcol.data_ptr(), scratch.data_ptr(), B, N, d, C, 0, 1.0, code, stream()), 'head_bwd')
+        outs[code] = (logits, loss, dtok.float(), grads)
+    a, bb = outs[L.F32], outs[L.BF16_RES32]
+    assert torch.equal(a[0], bb[0]) and torch.equal(a[1], bb[1])
+    assert rel(bb[2], a[2]) < 4e-3
+    for ga, gb in zip(a[3], bb[3]):
+        assert rel(gb, ga) < 1e-3
