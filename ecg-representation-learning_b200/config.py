@@ -24,7 +24,8 @@ class EcgVitConfig(PretrainedConfig):
                  hidden_size: int = 512, num_hidden_layers: int = 8, num_attention_heads: int = 8,
                  intermediate_size: int = 2048, hidden_dropout_prob: float = 0.1,
                  attention_probs_dropout_prob: float = 0.1, num_class: int = 71,
-                 compute_dtype: str = 'bf16', per_lead_tokens: bool = False, residual_dtype: str = 'auto', **kwargs):
+                 compute_dtype: str = 'bf16', per_lead_tokens: bool = False, residual_dtype: str = 'auto',
+                 activation_checkpointing: bool = False, **kwargs):
         self.max_signal_length = max_signal_length
         self.patch_size = patch_size
         self.num_channels = num_channels
@@ -46,6 +47,10 @@ class EcgVitConfig(PretrainedConfig):
         # = fp32 for models deeper than 12 layers.  bf16 rounding of the stream random-walks with depth: the 24-layer
         # 'large' model needs fp32 here to stay within 1e-2 of the fp32 reference; up to 12 layers bf16 is inside the bar
         self.residual_dtype = residual_dtype
+        # True: keep only every block's input and recompute the block's activations in backward (BASELINE.json configs[4]).
+        # Costs one extra block forward per layer (minus the last Linear); 'large' at 512 records per GPU fits 180 GB
+        # without it (33.5 GB), so it is off by default
+        self.activation_checkpointing = activation_checkpointing
         super().__init__(**kwargs)
         self.size = None
 

@@ -291,6 +291,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             next_bias1 = (c + 32 < N) ? __ldg(ep.bias + c + 32) : 0.f;
         };
         if (has_bias && cluster_id < num_units) fetch_bias(cluster_id);
+        // phase of each aux barrier: it only advances on tiles where the unit lies inside the matrix (a partial last
+        // column tile skips the load), so it is tracked per barrier, not derived from the tile count
+        uint32_t aux_phase = 0;
         int it = 0;
         for (int u = cluster_id; u < num_units; u += num_clusters, ++it) {
             const float bias0 = next_bias0, bias1 = next_bias1;
@@ -360,7 +363,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                         t1 = tiles + Cfg::EPI_TILE_BYTES;
                     } else {
                         t0 = tiles + i * Cfg::EPI_TILE_BYTES;
-                        if (kHasAux) ptx::mbar_wait(&my_aux_bar[i], it & 1);
+                        if (kHasAux) {
+                            ptx::mbar_wait(&my_aux_bar[i], (aux_phase >> i) & 1u);
+                            aux_phase ^= 1u << i;
+                        }
                     }
                     ptx::tmem_ld_wait_bind(ra);
                     ptx::tmem_ld_32x16(taddr0 + 32 * i + 16, rb);

@@ -120,16 +120,27 @@ class StepEngine:
         w.e = buf(B * n, d)
         RT = m._res_dtype  # residual stream: fp32 for deep models in bf16 mode (config.residual_dtype)
         w.x = [buf(M, d, dtype=RT) for _ in range(depth + 1)]  # x[l] = input of block l; x[depth] = encoder output
-        w.ln1 = [buf(M, d) for _ in range(depth)]
-        w.ln2 = [buf(M, d) for _ in range(depth)]
-        w.stat1 = [buf(2, M, dtype=torch.float32) for _ in range(depth)]
-        w.stat2 = [buf(2, M, dtype=torch.float32) for _ in range(depth)]
-        w.qkv = [buf(M, 3 * inner) for _ in range(depth)]
-        w.lse = [buf(B, H, N, dtype=torch.float32) for _ in range(depth)]
-        w.o = [buf(M, inner) for _ in range(depth)]
-        w.y = [buf(M, d, dtype=RT) for _ in range(depth)]
-        w.u = [buf(M, mlp) for _ in range(depth)]
-        w.h = [buf(M, mlp) for _ in range(depth)]
+        # Activation checkpointing (config.activation_checkpointing; BASELINE.json configs[4]): only the block inputs x[l]
+        # are kept per layer; everything inside a block lives in TWO buffer sets used alternately (layer l -> set l % 2)
+        # and is recomputed from x[l] in backward.  Two sets, so that the weight-gradient GEMMs of layer l (side stream)
+        # can still read their operands while layer l - 1 is being recomputed into the other set.
+        w.ckpt = bool(getattr(c, 'activation_checkpointing', False)) and depth > 2
+        n_sets = 2 if w.ckpt else depth
+
+        def per_layer(make):
+            sets = [make() for _ in range(n_sets)]
+            return [sets[l % n_sets] for l in range(depth)]
+
+        w.ln1 = per_layer(lambda: buf(M, d))
+        w.ln2 = per_layer(lambda: buf(M, d))
+        w.stat1 = per_layer(lambda: buf(2, M, dtype=torch.float32))
+        w.stat2 = per_layer(lambda: buf(2, M, dtype=torch.float32))
+        w.qkv = per_layer(lambda: buf(M, 3 * inner))
+        w.lse = per_layer(lambda: buf(B, H, N, dtype=torch.float32))
+        w.o = per_layer(lambda: buf(M, inner))
+        w.y = per_layer(lambda: buf(M, d, dtype=RT))
+        w.u = per_layer(lambda: buf(M, mlp))
+        w.h = per_layer(lambda: buf(M, mlp))
         # head
         n_class = m.num_class
         w.xn = buf(B, d, dtype=torch.float32)
@@ -210,34 +221,8 @@ class StepEngine:
         _lib.check(lib.ecgvit_embed_assemble(w.e.data_ptr(), pf['cls'].data_ptr(), pf['pos'].data_ptr(),
                                              w.x[0].data_ptr(), B, n, d, p_emb, 0, seed_ptr if p_emb > 0 else None,
                                              rdt, st), 'embed_assemble')
-        scale = float(dh) ** -0.5
-        blk_seed = seed_ptr if p_blk > 0 else None
         for l in range(c.num_hidden_layers):
-            p = f'l{l}.'
-            # dropout sites of block l: 1+4l attention probabilities, 2+4l after to_out, 3+4l after GELU, 4+4l after net[3]
-            s_att, s_out, s_act, s_ff2 = 1 + 4 * l, 2 + 4 * l, 3 + 4 * l, 4 + 4 * l
-            _lib.check(lib.ecgvit_layernorm_fwd(w.x[l].data_ptr(), pf[p + 'ln1.w'].data_ptr(), pf[p + 'ln1.b'].data_ptr(),
-                                                w.ln1[l].data_ptr(), w.stat1[l][0].data_ptr(), w.stat1[l][1].data_ptr(),
-                                                M, d, LN_EPS, rdt, st), 'layernorm_fwd')
-            self._gemm(M, 3 * inner, d, w.ln1[l], d, 1, wt[p + 'qkv.w'], d, 1, EPI_STORE, w.qkv[l], 3 * inner)
-            if record_attention:
-                if l == 0:
-                    self.recorded_attention = torch.empty(B, c.num_hidden_layers, H, N, N, device=x.device,
-                                                          dtype=torch.float32)
-                rec = self.recorded_attention
-                _lib.check(lib.ecgvit_attention_probs(w.qkv[l].data_ptr(), rec[:, l].data_ptr(), B, N, H, dh, scale,
-                                                      rec.stride(0), dt, st), 'attention_probs')
-            _lib.check(lib.ecgvit_attention_fwd(w.qkv[l].data_ptr(), w.o[l].data_ptr(), w.lse[l].data_ptr(), B, N, H, dh,
-                                                scale, p_blk, s_att, blk_seed, dt, st), 'attention_fwd')
-            self._gemm(M, d, inner, w.o[l], inner, 1, wt[p + 'out.w'], inner, 1, epi_res, w.y[l], d,
-                       aux=w.x[l], bias=pf[p + 'out.b'], drop=(p_blk, s_out))
-            _lib.check(lib.ecgvit_layernorm_fwd(w.y[l].data_ptr(), pf[p + 'ln2.w'].data_ptr(), pf[p + 'ln2.b'].data_ptr(),
-                                                w.ln2[l].data_ptr(), w.stat2[l][0].data_ptr(), w.stat2[l][1].data_ptr(),
-                                                M, d, LN_EPS, rdt, st), 'layernorm_fwd')
-            self._gemm(M, mlp, d, w.ln2[l], d, 1, wt[p + 'ff1.w'], d, 1, EPI_BIAS_GELU, w.u[l], mlp,
-                       out2=w.h[l], bias=pf[p + 'ff1.b'], drop=(p_blk, s_act))
-            self._gemm(M, d, mlp, w.h[l], mlp, 1, wt[p + 'ff2.w'], mlp, 1, epi_res, w.x[l + 1], d,
-                       aux=w.y[l], bias=pf[p + 'ff2.b'], drop=(p_blk, s_ff2))
+            self._block_forward(l, w, record_attention=record_attention)
         red = _lib.REDUCTION[reduction]
         loss_buf = None
         if labels is not None:
@@ -254,6 +239,49 @@ class StepEngine:
         if labels is not None:
             loss = w.loss_none if reduction == 'none' else w.loss[0]
         return loss, w.logits
+
+    def _block_forward(self, l, w, record_attention=False, recompute=False):
+        """block l: x[l] -> x[l + 1] (PreNorm attention + residual, PreNorm feed-forward + residual).
+        recompute=True (activation checkpointing, from backward): rebuild what backward reads of the block -- ln1, qkv,
+        lse, o, y, ln2, u, h -- from x[l]; the last Linear (whose output x[l + 1] is kept) is skipped.  Dropout masks are
+        a function of (seed, site, element), so the recomputed tensors are bit-identical to the forward pass's."""
+        m, lib, st = self.model, self.lib, self._stream
+        c = m.config
+        dt, rdt = m._dtype_code, m._res_code
+        epi_res = EPI_BIAS_RES_F32 if m._res_f32 else EPI_BIAS_RES
+        d, mlp, H = c.hidden_size, c.intermediate_size, c.num_attention_heads
+        inner, dh = d, d // H
+        B, N, M = w.B, w.N, w.M
+        wt, pf = m._weights(), m._params_f32()
+        p_blk = w.p_blk
+        scale = float(dh) ** -0.5
+        blk_seed = self.rng.data_ptr() if p_blk > 0 else None
+        p = f'l{l}.'
+        # dropout sites of block l: 1+4l attention probabilities, 2+4l after to_out, 3+4l after GELU, 4+4l after net[3]
+        s_att, s_out, s_act, s_ff2 = 1 + 4 * l, 2 + 4 * l, 3 + 4 * l, 4 + 4 * l
+        _lib.check(lib.ecgvit_layernorm_fwd(w.x[l].data_ptr(), pf[p + 'ln1.w'].data_ptr(), pf[p + 'ln1.b'].data_ptr(),
+                                            w.ln1[l].data_ptr(), w.stat1[l][0].data_ptr(), w.stat1[l][1].data_ptr(),
+                                            M, d, LN_EPS, rdt, st), 'layernorm_fwd')
+        self._gemm(M, 3 * inner, d, w.ln1[l], d, 1, wt[p + 'qkv.w'], d, 1, EPI_STORE, w.qkv[l], 3 * inner)
+        if record_attention:
+            if l == 0:
+                self.recorded_attention = torch.empty(B, c.num_hidden_layers, H, N, N, device=self.device,
+                                                      dtype=torch.float32)
+            rec = self.recorded_attention
+            _lib.check(lib.ecgvit_attention_probs(w.qkv[l].data_ptr(), rec[:, l].data_ptr(), B, N, H, dh, scale,
+                                                  rec.stride(0), dt, st), 'attention_probs')
+        _lib.check(lib.ecgvit_attention_fwd(w.qkv[l].data_ptr(), w.o[l].data_ptr(), w.lse[l].data_ptr(), B, N, H, dh,
+                                            scale, p_blk, s_att, blk_seed, dt, st), 'attention_fwd')
+        self._gemm(M, d, inner, w.o[l], inner, 1, wt[p + 'out.w'], inner, 1, epi_res, w.y[l], d,
+                   aux=w.x[l], bias=pf[p + 'out.b'], drop=(p_blk, s_out))
+        _lib.check(lib.ecgvit_layernorm_fwd(w.y[l].data_ptr(), pf[p + 'ln2.w'].data_ptr(), pf[p + 'ln2.b'].data_ptr(),
+                                            w.ln2[l].data_ptr(), w.stat2[l][0].data_ptr(), w.stat2[l][1].data_ptr(),
+                                            M, d, LN_EPS, rdt, st), 'layernorm_fwd')
+        self._gemm(M, mlp, d, w.ln2[l], d, 1, wt[p + 'ff1.w'], d, 1, EPI_BIAS_GELU, w.u[l], mlp,
+                   out2=w.h[l], bias=pf[p + 'ff1.b'], drop=(p_blk, s_act))
+        if not recompute:
+            self._gemm(M, d, mlp, w.h[l], mlp, 1, wt[p + 'ff2.w'], mlp, 1, epi_res, w.x[l + 1], d,
+                       aux=w.y[l], bias=pf[p + 'ff2.b'], drop=(p_blk, s_ff2))
 
     def span_buffer(self, B):
         """device int32 [B, 2] (start, length) of the TimeOut span of every record; a persistent buffer, so a captured
@@ -366,9 +394,15 @@ class StepEngine:
                     ev_fold[which].record(side)
 
         ev_ff2 = ev_ff1 = ev_out = ev_qkv = None
+        layer_events = {}   # checkpointing: side-stream events of the weight gradients that read layer l's buffer set
         for l in range(depth - 1, -1, -1):
             p = f'l{l}.'
             s_att, s_out, s_act, s_ff2 = 1 + 4 * l, 2 + 4 * l, 3 + 4 * l, 4 + 4 * l
+            if w.ckpt and l < depth - 2:
+                # the set of layer l was last used by layer l + 2: its weight-gradient GEMMs must have read their operands
+                for ev in layer_events.pop(l + 2, ()):
+                    before_overwrite(ev)
+                self._block_forward(l, w, recompute=True)
             # ---- feed-forward branch: x[l+1] = y + drop(W2 drop(gelu(W1 ln2(y) + b1)) + b2)
             if l == depth - 1:
                 dzl = masked(dz, gr[p + 'ff2.b'], s_ff2, 0)   # below the top block LayerNorm' writes the masked copy
@@ -403,6 +437,8 @@ class StepEngine:
                        'attention_bwd' if w.attn_scratch is None else 'attention_bwd_flash')
             ev_qkv = wgrad(3 * inner, d, M, w.dqkv, 3 * inner, 0, w.ln1[l], d, 0, EPI_ATOMIC_F32, gr[p + 'qkv.w'], d,
                            split_k=0)
+            if w.ckpt:
+                layer_events[l] = (ev_ff2, ev_ff1, ev_out, ev_qkv)
             self._gemm(M, d, 3 * inner, w.dqkv, 3 * inner, 1, wt[p + 'qkv.w'], d, 0, EPI_STORE, w.dln, d)
             below_bias = gr[f'l{l - 1}.ff2.b'] if l > 0 else None
             drop_below = p_blk > 0 and l > 0

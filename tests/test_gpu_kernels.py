@@ -433,3 +433,30 @@ def test_embed_assemble_and_head_take_fp32_stream(lib):
     assert rel(bb[2], a[2]) < 4e-3
     for ga, gb in zip(a[3], bb[3]):
         assert rel(gb, ga) < 1e-3
+
+
+@pytest.mark.parametrize('epi', ['res', 'res_f32', 'dgelu'])
+def test_gemm_aux_epilogues_many_row_tiles_partial_last_column_tile(lib, epi):
+    """persistent loop: every cluster walks several tiles, and the last column tile is partial (N = 1024 on 192-wide tiles,
+    the shape of the 'large' model's out-proj): the residual / pre-activation tiles of units outside the matrix are never
+    fetched, so their barriers must not be waited on (nor their phase advanced)"""
+    M, N, K = 256 * 90, 1024, 256
+    A, B, acc = _operands(M, N, K, 1, 1 if epi != 'dgelu' else 0, torch.bfloat16, seed=17)
+    bias = torch.randn(N, device='cuda')
+    if epi == 'res_f32':
+        aux = torch.randn(M, N, device='cuda')
+        out = torch.zeros(M, N, device='cuda')
+        gemm(lib, A, B, M, N, K, 1, 1, L.EPI_BIAS_RES_F32, out, L.BF16, aux=aux, bias=bias)
+        assert rel(out, acc + bias + aux) < 2e-5
+    elif epi == 'res':
+        aux = torch.randn(M, N, device='cuda').bfloat16()
+        out = torch.zeros(M, N, device='cuda', dtype=torch.bfloat16)
+        gemm(lib, A, B, M, N, K, 1, 1, L.EPI_BIAS_RES, out, L.BF16, aux=aux, bias=bias)
+        assert rel(out, acc + bias + aux.float()) < 4e-3
+    else:
+        aux = torch.randn(M, N, device='cuda').bfloat16()
+        out = torch.zeros(M, N, device='cuda', dtype=torch.bfloat16)
+        gemm(lib, A, B, M, N, K, 1, 0, L.EPI_DGELU, out, L.BF16, aux=aux)
+        uu = aux.float().requires_grad_(True)
+        torch.nn.functional.gelu(uu).sum().backward()
+        assert rel(out, acc * uu.grad) < 5e-3

@@ -465,3 +465,43 @@ def test_fp32_residual_stream_with_dropout_masks():
     assert rel(got.logits, want.logits) < BF16_TOL
     for (k, p), (_, q) in zip(model.named_parameters(), oracle.named_parameters()):
         assert cosine(p.grad, q.grad) > BF16_GRAD_COS, (k, cosine(p.grad, q.grad))
+
+
+@pytest.mark.parametrize('p_drop,res', [(0.0, 'bf16'), (0.1, 'bf16'), (0.1, 'fp32')])
+def test_activation_checkpointing_reproduces_the_stored_activation_step(p_drop, res):
+    """BASELINE.json configs[4] asks for activation checkpointing: with `activation_checkpointing=True` only the block
+    inputs are kept and every block is recomputed in backward (dropout masks regenerate from the counter).  Same loss,
+    same gradients (up to the order of the split-K red.adds), same three optimisation steps as the default path, and
+    still inside the bf16 bar against the oracle."""
+    cfg = dict(CFG_MID, num_hidden_layers=5, hidden_dropout_prob=p_drop, attention_probs_dropout_prob=p_drop)
+    torch.manual_seed(77)
+    oracle = OracleEcgVit(config=OracleConfig(**cfg)).train()
+    models = []
+    for ckpt in (False, True):
+        m = EcgVit(config=EcgVitConfig(compute_dtype='bf16', residual_dtype=res, activation_checkpointing=ckpt, **cfg))
+        m.load_state_dict(oracle.state_dict(), strict=True)
+        m.cuda().train()
+        m._prepare(torch.device('cuda', torch.cuda.current_device()))
+        models.append(m)
+    x, y = synthetic_batch(6, length=cfg['max_signal_length'])
+    xd, yd = x.cuda(), y.cuda()
+    outs = []
+    for m in models:
+        m._engine.new_dropout_seed(seed=4242)
+        loss, logits = m._engine.forward(xd, yd, 'mean')
+        loss, logits = loss.clone(), logits.clone()
+        m._engine.backward()
+        outs.append((loss, logits, m._flat_g.clone()))
+    assert models[1]._engine._cur.ckpt and not models[0]._engine._cur.ckpt
+    assert models[1]._engine._cur.ln1[0] is models[1]._engine._cur.ln1[2]          # shared buffer sets
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert rel(outs[1][2], outs[0][2]) < 1e-5
+    if p_drop == 0.0:
+        o = oracle(sample_values=x, labels=y)
+        assert rel(outs[1][1], o.logits) < BF16_TOL
+    trainers = [FusedTrainer(m, use_cuda_graph=True, data_parallel=False) for m in models]
+    for step in range(3):
+        for m, tr in zip(models, trainers):
+            m._engine._seed_counter = 100 + step          # both draw the same masks
+            tr.step(xd, yd)
+    assert rel(models[1]._flat_p, models[0]._flat_p) < 1e-6
