@@ -67,8 +67,8 @@ SIGNATURES = {
                              c_float, c_float, c_int, c_void_p, c_int, c_void_p],
     'ecgvit_head_fwd': [c_void_p] * 7 + [c_int] + [c_void_p] * 5 + [c_int, c_int, c_int, c_int, c_int, c_float, c_int,
                                                                      c_void_p],
-    'ecgvit_head_bwd': [c_void_p] * 5 + [c_int] + [c_void_p] * 11 + [c_int, c_int, c_int, c_int, c_int, c_float, c_int,
-                                                                      c_void_p],
+    'ecgvit_head_bwd': [c_void_p] * 5 + [c_int] + [c_void_p] * 11 + [c_int, c_int, c_int, c_int, c_int, c_float, c_void_p,
+                                                                      c_int, c_void_p],
     'ecgvit_colsum': [c_void_p, c_void_p, c_int, c_int, c_int64, c_int, c_void_p],
     'ecgvit_grad_sumsq': [c_void_p, c_int64, c_void_p, c_void_p, c_void_p],
     'ecgvit_adamw_step': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p],

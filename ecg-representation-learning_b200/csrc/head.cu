@@ -119,11 +119,14 @@ __global__ void __launch_bounds__(128) head_bwd_rows_kernel(const TX *__restrict
                                                              const float *__restrict__ rstd_in,
                                                              const float *__restrict__ logits, T *__restrict__ dtok,
                                                              float *__restrict__ dxn_out, float *__restrict__ dlog_out,
-                                                             int B, int N, int d, int n_class, float coef,
+                                                             int B, int N, int d, int n_class, float coef_host,
+                                                             const float *__restrict__ coef_dev,
                                                              const float *__restrict__ loss_weight, int n_weight) {
     const int lane = threadIdx.x & 31;
     const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (b >= B) return;
+    // upstream gradient of the loss: a host scalar and / or a DEVICE scalar (autograd's grad_output: no host sync)
+    const float coef = coef_dev != nullptr ? coef_host * __ldg(coef_dev) : coef_host;
     float dxn[HEAD_MAXV][8];
 #pragma unroll
     for (int i = 0; i < HEAD_MAXV; ++i)
@@ -280,7 +283,7 @@ int ecgvit_head_bwd(const void *tok, const float *gamma, const float *w, const f
                     int n_weight, const float *xn, const float *mean, const float *rstd, const float *logits, void *dtok,
                     float *dw, float *db,
                     float *dgamma, float *dbeta, float *dcolsum, float *scratch, int B, int N, int d, int n_class,
-                    int reduction, float grad_scale, int dtype, void *stream) {
+                    int reduction, float grad_scale, const float *grad_scale_dev, int dtype, void *stream) {
     ECGVIT_REQUIRE(tok && gamma && w && labels && xn && mean && rstd && logits && dtok && dw && db && dgamma &&
                        dbeta && scratch,
                    "head_bwd: null argument");
@@ -297,13 +300,13 @@ int ecgvit_head_bwd(const void *tok, const float *gamma, const float *w, const f
     float *dxn = scratch, *dlog = scratch + (size_t)B * d;
     const int grid = (B + 3) / 4;
     if (dtype == ECGVIT_BF16) {
-        head_bwd_rows_kernel<bf16><<<grid, 128, 0, s>>>((const bf16 *)tok, gamma, w, labels, mean, rstd, logits, (bf16 *)dtok, dxn, dlog, B, N, d, n_class, coef, loss_weight, n_weight);
+        head_bwd_rows_kernel<bf16><<<grid, 128, 0, s>>>((const bf16 *)tok, gamma, w, labels, mean, rstd, logits, (bf16 *)dtok, dxn, dlog, B, N, d, n_class, coef, grad_scale_dev, loss_weight, n_weight);
         head_bwd_cols_kernel<bf16><<<(d + 31) / 32, 256, 0, s>>>((const bf16 *)tok, (const bf16 *)dtok, dxn, mean, rstd, dgamma, dbeta, dcolsum, B, N, d);
     } else if (dtype == ECGVIT_BF16_RES32) {
-        head_bwd_rows_kernel<bf16, float><<<grid, 128, 0, s>>>((const float *)tok, gamma, w, labels, mean, rstd, logits, (bf16 *)dtok, dxn, dlog, B, N, d, n_class, coef, loss_weight, n_weight);
+        head_bwd_rows_kernel<bf16, float><<<grid, 128, 0, s>>>((const float *)tok, gamma, w, labels, mean, rstd, logits, (bf16 *)dtok, dxn, dlog, B, N, d, n_class, coef, grad_scale_dev, loss_weight, n_weight);
         head_bwd_cols_kernel<bf16, float><<<(d + 31) / 32, 256, 0, s>>>((const float *)tok, (const bf16 *)dtok, dxn, mean, rstd, dgamma, dbeta, dcolsum, B, N, d);
     } else if (dtype == ECGVIT_F32) {
-        head_bwd_rows_kernel<float><<<grid, 128, 0, s>>>((const float *)tok, gamma, w, labels, mean, rstd, logits, (float *)dtok, dxn, dlog, B, N, d, n_class, coef, loss_weight, n_weight);
+        head_bwd_rows_kernel<float><<<grid, 128, 0, s>>>((const float *)tok, gamma, w, labels, mean, rstd, logits, (float *)dtok, dxn, dlog, B, N, d, n_class, coef, grad_scale_dev, loss_weight, n_weight);
         head_bwd_cols_kernel<float><<<(d + 31) / 32, 256, 0, s>>>((const float *)tok, (const float *)dtok, dxn, mean, rstd, dgamma, dbeta, dcolsum, B, N, d);
     } else return fail(-1, "head_bwd: unknown dtype %d", dtype);
     dim3 gw((d + 31) / 32, n_class);

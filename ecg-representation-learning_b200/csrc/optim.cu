@@ -11,7 +11,7 @@ namespace {
 
 enum { H_LR = 0, H_BETA1, H_BETA2, H_EPS, H_WD, H_BC1, H_BC2, H_MAXNORM, H_GSCALE,
        H_ONE_MINUS_B1, H_ONE_MINUS_B2, H_DECAY, H_STEP_SIZE, H_BC2_SQRT };
-enum { S_SUMSQ = 0, S_NONFINITE, S_NORM };
+enum { S_SUMSQ = 0, S_NONFINITE, S_NORM, S_SKIPPED };
 
 // Stage 1: one partial sum of squares per CTA (fixed grid-stride order inside the CTA).
 // Stage 2: a single CTA adds the partials in index order.  No atomics: the total norm must be BIT-IDENTICAL on every
@@ -74,8 +74,12 @@ __global__ void __launch_bounds__(256) adamw_kernel(float *__restrict__ p, float
     float total_norm;
     const float clip = clip_coef_from(hyper, stats, total_norm);
     if (blockIdx.x == 0 && threadIdx.x == 0) stats[S_NORM] = total_norm;
-    // error_if_nonfinite: leave parameters and state untouched; the host raises when it polls the flag
-    if (!isfinite(total_norm)) return;
+    // error_if_nonfinite: leave parameters and state untouched and COUNT the skipped update (sticky until the host clears
+    // it: a poll every k steps cannot miss one); the host raises when it polls
+    if (!isfinite(total_norm)) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) stats[S_SKIPPED] += 1.0f;
+        return;
+    }
     // the derived scalars are computed by the host in double precision exactly like torch.optim.AdamW does
     // (1 - beta in fp32 differs from fp32(1 - beta) by 1.3e-5 relative for beta2 = 0.999)
     const float beta2 = hyper[H_BETA2], eps = hyper[H_EPS];

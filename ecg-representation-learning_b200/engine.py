@@ -49,17 +49,24 @@ class StepEngine:
             if os.environ.get('ECGVIT_WGRAD_STREAM', '1') != '0' else None
         self._seed_counter = 0
         self._seed_ring = None
-        self.base_seed = 0x5EED
+        self.base_seed = 0x5EED     # rank-independent (saved in trainer state); replicas add `rank_offset`
+        self.rank_offset = 0
+        self._fwd_id = 0            # generation of the last forward (the autograd bridge checks it at backward)
+        self.last_seed = None       # (seed, counter) uploaded last
 
     def new_dropout_seed(self, seed=None):
         """draw the seed of the next training forward (its backward regenerates the same masks from it)"""
         self._seed_counter += 1
         if seed is None:
-            seed = (self.base_seed * 0x9E3779B1 + self._seed_counter * 0x85EBCA6B) & 0x7FFFFFFF
+            seed = ((self.base_seed + self.rank_offset) * 0x9E3779B1 + self._seed_counter * 0x85EBCA6B) & 0x7FFFFFFF
+        self.upload_seed(seed, self._seed_counter & 0x7FFFFFFF)
+        return seed
+
+    def upload_seed(self, seed, counter):
         if self._seed_ring is None:
             self._seed_ring = _lib.PinnedRing(2, torch.int32)
-        self._seed_ring.upload(self.rng, [seed, self._seed_counter & 0x7FFFFFFF])  # asynchronous: no host stall
-        return seed
+        self._seed_ring.upload(self.rng, [seed, counter])  # asynchronous: no host stall
+        self.last_seed = (seed, counter)
 
     def _dropout_probs(self):
         """(p_embedding, p_block) as the reference wires them (ecg_vit.py:113-114); zero in eval mode"""
@@ -186,6 +193,8 @@ class StepEngine:
         L = L_in if pipe is None else pipe.padded_length(L_in)  # TimeEndPad happens inside the gather
         w = self.workspace(B, L)
         self._cur = w
+        self._fwd_id += 1
+        w.fwd_id = self._fwd_id   # a later forward through the same workspace invalidates this one's backward
         P, d, mlp, H = c.patch_size, c.hidden_size, c.intermediate_size, c.num_attention_heads
         inner, dh = d, d // H
         n, N, M = w.n, w.N, w.M
@@ -308,8 +317,9 @@ class StepEngine:
         return self._lw_table.data_ptr(), len(key)
 
     # ---- backward --------------------------------------------------------------------------------
-    def backward(self, grad_scale=1.0, zero_grads=True):
-        """Gradients of the last forward's loss w.r.t. every parameter, accumulated into the flat grad buffer."""
+    def backward(self, grad_scale=1.0, zero_grads=True, grad_scale_dev=None):
+        """Gradients of the last forward's loss w.r.t. every parameter, accumulated into the flat grad buffer.
+        grad_scale_dev: optional fp32 CUDA scalar multiplied into the upstream gradient on the device (no host sync)."""
         m, lib, st = self.model, self.lib, self._stream
         c = m.config
         dt = m._dtype_code
@@ -336,7 +346,7 @@ class StepEngine:
             *self._loss_weight_table(), w.xn.data_ptr(), w.hstat[0].data_ptr(), w.hstat[1].data_ptr(), w.logits.data_ptr(), dz.data_ptr(),
             gr['head.w'].data_ptr(), gr['head.b'].data_ptr(), gr['head.ln.w'].data_ptr(), gr['head.ln.b'].data_ptr(),
             gr[last + 'ff2.b'].data_ptr() if p_blk == 0 else None, w.head_scratch.data_ptr(), B, N, d, m.num_class,
-            _lib.REDUCTION[w.reduction], float(grad_scale), rdt, st), 'head_bwd')
+            _lib.REDUCTION[w.reduction], float(grad_scale), _lib.ptr(grad_scale_dev), rdt, st), 'head_bwd')
         scale = float(dh) ** -0.5
 
         main, side = torch.cuda.current_stream(), self.side_stream

@@ -106,6 +106,8 @@ class _EcgVitFunction(torch.autograd.Function):
         loss, logits = model._engine.forward(sample_values, labels, model.loss_reduction)
         ctx.model = model
         ctx.ws = model._engine._cur
+        ctx.fwd_id = ctx.ws.fwd_id           # workspaces are cached per shape: the object alone does not identify a pass
+        ctx.seed = model._engine.last_seed   # dropout seed of THIS forward: backward regenerates its masks from it
         # hand out copies: the workspace buffers are overwritten by the next forward
         loss, logits = loss.clone(), logits.clone()
         ctx.mark_non_differentiable(logits)
@@ -114,20 +116,33 @@ class _EcgVitFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_loss, _grad_logits):
         model = ctx.model
-        assert model._engine._cur is ctx.ws, 'backward must follow its own forward (workspaces are reused)'
+        eng = model._engine
+        if ctx.ws.fwd_id != ctx.fwd_id:
+            raise RuntimeError(
+                'ecg_b200.EcgVit: another forward of the same input shape ran between this forward and its backward; '
+                'the activation workspace (cached per shape) holds the later pass.  Call backward() before the next '
+                'forward of that shape, or run the extra forward under torch.no_grad() on a different batch size.')
+        eng._cur = ctx.ws   # a forward of ANOTHER shape may have run in between: its workspace is not ours
+        if ctx.seed is not None and eng.last_seed != ctx.seed:
+            eng.upload_seed(*ctx.seed)   # ... and it drew a new dropout seed
+        # the upstream gradient stays on the device (float(grad_loss) would stall the host on the whole queue)
+        g_dev = grad_loss.detach().to(torch.float32).reshape(1).contiguous()
         # Gradients are produced straight into the flat fp32 buffer and `.grad` is pointed at its views, so the
         # clip / AdamW kernels later see one contiguous array (no per-tensor copies through AccumulateGrad).
         params, views = model._param_list(), model._grad_views()
-        ours = [p.grad is not None and p.grad.data_ptr() == v.data_ptr() for p, v in zip(params, views)]
+        # frozen parameters (requires_grad=False) never get a .grad, as with autograd; the kernels still write their slot
+        # of the flat buffer, which the optimizer front end ignores for them
+        live = [(p, v) for p, v in zip(params, views) if p.requires_grad]
+        ours = [p.grad is not None and p.grad.data_ptr() == v.data_ptr() for p, v in live]
         if all(ours):
-            model._engine.backward(grad_scale=float(grad_loss), zero_grads=False)  # accumulate, like autograd
+            eng.backward(grad_scale=1.0, zero_grads=False, grad_scale_dev=g_dev)  # accumulate, like autograd
         else:
-            earlier = [(v, p.grad.clone()) for p, v in zip(params, views) if p.grad is not None]
-            model._engine.backward(grad_scale=float(grad_loss), zero_grads=True)
+            earlier = [(v, p.grad.clone()) for p, v in live if p.grad is not None]
+            eng.backward(grad_scale=1.0, zero_grads=True, grad_scale_dev=g_dev)
             with torch.no_grad():
                 for v, g in earlier:  # gradients accumulated before this backward (mixed ownership: rare)
                     v.add_(g)
-                for p, v in zip(params, views):
+                for p, v in live:
                     p.grad = v
         return (None, None, None) + (None,) * len(params)
 

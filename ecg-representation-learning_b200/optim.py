@@ -42,9 +42,13 @@ def _scratch(model):
     return model._opt_scratch
 
 
-def _upload(hyper, values):
-    # pageable source: the driver stages the 64 bytes before returning, so the list can be reused immediately
-    hyper.copy_(torch.tensor(values, dtype=torch.float32))
+def _upload(model, hyper, values):
+    """asynchronous upload of the 64-byte hyper-parameter block through a ring of pinned slots (a copy from pageable
+    memory would make the host wait for everything queued on the stream, i.e. for the previous step)"""
+    ring = getattr(model, '_opt_ring', None)
+    if ring is None:
+        ring = model._opt_ring = _lib.PinnedRing(len(values), torch.float32)
+    ring.upload(hyper, values)
 
 
 def clip_grad_norm_(model, max_norm, norm_type=2.0, error_if_nonfinite=False):
@@ -54,12 +58,12 @@ def clip_grad_norm_(model, max_norm, norm_type=2.0, error_if_nonfinite=False):
     lib = _lib.load()
     g = _flat_grads(model)
     hyper, stats = _scratch(model)
-    _upload(hyper, _lib.adamw_hyper(0.0, 0.9, 0.999, 1e-8, 0.0, 1, float(max_norm), 1.0))
+    _upload(model, hyper, _lib.adamw_hyper(0.0, 0.9, 0.999, 1e-8, 0.0, 1, float(max_norm), 1.0))
     st = torch.cuda.current_stream().cuda_stream
     _lib.check(lib.ecgvit_grad_sumsq(g.data_ptr(), g.numel(), hyper.data_ptr(), stats.data_ptr(), st), 'grad_sumsq')
     _lib.check(lib.ecgvit_grad_scale_by_clip(g.data_ptr(), g.numel(), hyper.data_ptr(), stats.data_ptr(), st),
                'grad_scale_by_clip')
-    total_norm = stats[2].clone()
+    total_norm = stats[2].clone()   # a device scalar, like torch's; only error_if_nonfinite reads it on the host
     if error_if_nonfinite and not math.isfinite(float(total_norm)):
         raise RuntimeError(
             f'The total norm of order {float(norm_type)} for gradients from `parameters` is non-finite, so it cannot '
@@ -69,7 +73,11 @@ def clip_grad_norm_(model, max_norm, norm_type=2.0, error_if_nonfinite=False):
 
 
 class FusedAdamW(torch.optim.Optimizer):
-    """AdamW over the model's flat parameter buffer; one group, decay on everything (train.py:242-244)."""
+    """AdamW over the model's flat parameter buffer; one group, decay on everything (train.py:242-244).
+
+    `state_dict()` / `load_state_dict()` carry the moments and the step count (as flat tensors under `state['flat']`),
+    so the usual `torch.save(optimizer.state_dict())` checkpoint resumes exactly.  Parameters whose `.grad` is None are
+    left untouched (value and moments), as torch.optim.AdamW leaves them."""
 
     def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2):
         self.model = model
@@ -77,24 +85,65 @@ class FusedAdamW(torch.optim.Optimizer):
         self._step = 0
         self._m = self._v = None
 
+    def _ensure_moments(self, g):
+        n = g.numel()
+        if self._m is None or self._m.numel() != n or self._m.device != g.device:
+            old = (self._m, self._v)
+            self._m, self._v = torch.zeros_like(g), torch.zeros_like(g)
+            if old[0] is not None and old[0].numel() == n:   # moved device / loaded on the CPU before the first step
+                self._m.copy_(old[0])
+                self._v.copy_(old[1])
+
     @torch.no_grad()
     def step(self, closure=None):
         loss = closure() if closure is not None else None
         model = self.model
         model._prepare(next(model.parameters()).device)
+        # parameters without a gradient keep their value and moments (torch skips them); they are rare (frozen tensors)
+        frozen = [k for (k, _), p in zip(model._layout.items(), model._param_list()) if p.grad is None]
         g = _flat_grads(model)
         n = g.numel()
-        if self._m is None or self._m.numel() != n or self._m.device != g.device:
-            self._m, self._v = torch.zeros_like(g), torch.zeros_like(g)
+        self._ensure_moments(g)
+        keep = []
+        for k in frozen:
+            o, cnt, _, _ = model._layout[k]
+            keep.append((o, cnt, model._flat_p[o:o + cnt].clone(), self._m[o:o + cnt].clone(), self._v[o:o + cnt].clone()))
         grp = self.param_groups[0]
         self._step += 1
         hyper, stats = _scratch(model)
         b1, b2 = grp['betas']
         # max_norm 0: clipping is a separate call in the reference loop
-        _upload(hyper, _lib.adamw_hyper(grp['lr'], b1, b2, grp['eps'], grp['weight_decay'], self._step, 0.0, 1.0))
+        _upload(model, hyper, _lib.adamw_hyper(grp['lr'], b1, b2, grp['eps'], grp['weight_decay'], self._step, 0.0, 1.0))
         stats.zero_()
         st = torch.cuda.current_stream().cuda_stream
         _lib.check(_lib.load().ecgvit_adamw_step(model._flat_p.data_ptr(), self._m.data_ptr(), self._v.data_ptr(),
                                                  g.data_ptr(), _lib.ptr(model._shadow), n, hyper.data_ptr(),
                                                  stats.data_ptr(), st), 'adamw_step')
+        for o, cnt, p0, m0, v0 in keep:
+            model._flat_p[o:o + cnt].copy_(p0)
+            self._m[o:o + cnt].copy_(m0)
+            self._v[o:o + cnt].copy_(v0)
+        if keep:
+            model.sync_shadow(force=True)
         return loss
+
+    # ---- checkpointing: torch.optim.Optimizer.state is empty here (the moments are flat), so carry them explicitly ----
+    def state_dict(self):
+        sd = super().state_dict()
+        sd['flat'] = {'step': self._step,
+                      'exp_avg': None if self._m is None else self._m.detach().clone(),
+                      'exp_avg_sq': None if self._v is None else self._v.detach().clone()}
+        return sd
+
+    def load_state_dict(self, state_dict):
+        state_dict = dict(state_dict)
+        flat = state_dict.pop('flat', None)
+        super().load_state_dict(state_dict)
+        if flat is not None:
+            self._step = int(flat['step'])
+            if flat['exp_avg'] is not None:
+                dev = next(self.model.parameters()).device
+                self._m = flat['exp_avg'].detach().to(device=dev, dtype=torch.float32).clone()
+                self._v = flat['exp_avg_sq'].detach().to(device=dev, dtype=torch.float32).clone()
+            else:
+                self._m = self._v = None

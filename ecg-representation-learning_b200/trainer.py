@@ -13,6 +13,7 @@ stream while backward is still running (`parallel.py`).
 """
 import collections
 import math
+import os
 
 import torch
 
@@ -50,6 +51,7 @@ class FusedTrainer:
                  schedule='constant', n_warmup=0, n_step=1 << 30, max_grad_norm=1.0, process_group=None,
                  bucket_layers=1, use_cuda_graph=False, data_parallel=True):
         self.model = model
+        self._flat_ptr = None
         self.lr, self.wd, self.betas, self.eps = learning_rate, weight_decay, betas, eps
         self.schedule, self.n_warmup, self.n_step = schedule, n_warmup, n_step
         self.max_grad_norm = max_grad_norm
@@ -73,17 +75,36 @@ class FusedTrainer:
     def _ensure_state(self, device):
         m = self.model
         m._prepare(device)
-        if self._state_ready and self.exp_avg.device == device and self.exp_avg.numel() == m._flat_p.numel():
+        if (self._state_ready and self.exp_avg.device == device and self.exp_avg.numel() == m._flat_p.numel()
+                and self._flat_ptr == m._flat_p.data_ptr()):
             return
+        # (re-)create the flat optimizer state: first use, or the model re-flattened its parameters (.to(), a dtype move,
+        # load_state_dict(assign=True)): the reducer, the captured graph and the moments must follow the new buffers
+        old = (self.exp_avg, self.exp_avg_sq) if self._state_ready and self.exp_avg.numel() == m._flat_p.numel() else None
         n = m._flat_p.numel()
         self.exp_avg = torch.zeros(n, device=device, dtype=torch.float32)
         self.exp_avg_sq = torch.zeros(n, device=device, dtype=torch.float32)
+        if old is not None:
+            self.exp_avg.copy_(old[0])
+            self.exp_avg_sq.copy_(old[1])
         self.hyper = torch.zeros(16, device=device, dtype=torch.float32)
         self.stats = torch.zeros(_lib.STATS_FLOATS, device=device, dtype=torch.float32)
+        self._flat_ptr = m._flat_p.data_ptr()
+        self._graph = None   # a captured graph points at the old flat buffers
         if self.world > 1:
             from .parallel import BucketedGradReducer
+            dist = torch.distributed
             self._reducer = BucketedGradReducer(m, self.group, self.bucket_layers)
-            m._engine.base_seed += 7919 * torch.distributed.get_rank(self.group)  # independent masks per replica
+            m._engine.rank_offset = 7919 * dist.get_rank(self.group)  # independent dropout masks per replica
+            # replicas must start from the same weights and optimizer state whatever each rank's RNG or checkpoint did
+            # (torch DDP broadcasts at construction too): rank 0 wins
+            src = dist.get_global_rank(self.group, 0) if self.group is not None else 0
+            for t in (m._flat_p, self.exp_avg, self.exp_avg_sq):
+                dist.broadcast(t, src=src, group=self.group)
+            cnt = torch.tensor([self.step_count], device=device, dtype=torch.int64)
+            dist.broadcast(cnt, src=src, group=self.group)
+            self.step_count = int(cnt)
+            m.sync_shadow(force=True)
         self._state_ready = True
 
     def current_lr(self):
@@ -158,8 +179,13 @@ class FusedTrainer:
     def _graph_step(self, sample_values, labels):
         lw = self.model.loss_weight
         pipe = self.model.input_pipeline
+        cfg = self.model.config
+        # everything the capture bakes in: shapes, loss weighting / reduction, train vs eval (dropout on or off and its
+        # probabilities), the input pipeline, and the flat buffers the kernels point at
         key = (tuple(sample_values.shape), tuple(labels.shape), tuple(float(v) for v in lw) if lw else None,
-               None if pipe is None else (id(pipe), pipe.pad, pipe.timeout, self.model.training))
+               self.model.training, float(cfg.hidden_dropout_prob), float(cfg.attention_probs_dropout_prob),
+               self.model.loss_reduction, self.model._flat_p.data_ptr(),
+               None if pipe is None else (id(pipe), pipe.pad, pipe.timeout))
         if self._graph is None or self._graph_key != key:
             self._static_x = torch.empty_like(sample_values)
             self._static_y = torch.empty(labels.shape, device=labels.device, dtype=torch.float32)
@@ -219,12 +245,16 @@ class FusedTrainer:
         return float(self.stats[2])
 
     def check_finite(self):
-        """`error_if_nonfinite=True` of clip_grad_norm_ (train.py:281): raises like torch does, one poll late"""
-        s = self.stats.tolist()
-        if s[1] != 0.0 or not math.isfinite(s[2]):
+        """`error_if_nonfinite=True` of clip_grad_norm_ (train.py:281): raises like torch does, at the next poll.  The
+        kernels skip an update whose gradient norm is non-finite and COUNT it in a sticky device counter, so polling every
+        k steps cannot miss one.  (The host-side step count, hence the LR schedule and AdamW's bias correction, has
+        advanced past the skipped update: treat the error as fatal, as the reference does.)"""
+        s = self.stats[:4].tolist()
+        if s[3] != 0.0 or s[1] != 0.0 or not math.isfinite(s[2]):
+            self.stats[3] = 0.0
             raise RuntimeError(
                 'The total norm of order 2.0 for gradients from `parameters` is non-finite, so it cannot be clipped. '
-                '(the fused step skipped this update)')
+                f'(the fused step skipped {int(s[3]) or 1} update(s))')
 
     def state_dict(self):
         """optimizer + schedule (+ dropout stream) state for a true resume; the reference saves the model only
@@ -232,7 +262,9 @@ class FusedTrainer:
         self._ensure_state(next(self.model.parameters()).device)
         eng = self.model._engine
         return {'step': self.step_count, 'exp_avg': self.exp_avg.clone(), 'exp_avg_sq': self.exp_avg_sq.clone(),
-                'dropout_counter': eng._seed_counter, 'dropout_base_seed': eng.base_seed}
+                'dropout_counter': eng._seed_counter, 'dropout_base_seed': eng.base_seed,  # rank-independent
+                'schedule': self.schedule, 'n_warmup': self.n_warmup, 'n_step': self.n_step, 'lr': self.lr,
+                'weight_decay': self.wd, 'betas': tuple(self.betas), 'eps': self.eps, 'max_grad_norm': self.max_grad_norm}
 
     def load_state_dict(self, sd):
         self._ensure_state(next(self.model.parameters()).device)
@@ -241,10 +273,116 @@ class FusedTrainer:
         self.exp_avg_sq.copy_(sd['exp_avg_sq'])
         eng = self.model._engine
         eng._seed_counter = sd.get('dropout_counter', eng._seed_counter)
-        eng.base_seed = sd.get('dropout_base_seed', eng.base_seed)
+        eng.base_seed = sd.get('dropout_base_seed', eng.base_seed)   # the rank offset stays this process's own
+        for k, attr in (('schedule', 'schedule'), ('n_warmup', 'n_warmup'), ('n_step', 'n_step'), ('lr', 'lr'),
+                        ('weight_decay', 'wd'), ('betas', 'betas'), ('eps', 'eps'), ('max_grad_norm', 'max_grad_norm')):
+            if k in sd:
+                setattr(self, attr, sd[k])
+        self.model.sync_shadow(force=True)
 
 
-_TRAINERS = {}
+    # ---- the reference's outer loop (MyTrainer.train, train.py:263-319), re-hosted -------------------------------------
+    def fit(self, train_data, eval_data=None, num_train_epoch=3, train_batch_size=64, eval_batch_size=None,
+            do_eval=True, patience=8, save_every_n_epoch=0, output_dir=None, log_every=10, shuffle_seed=0,
+            on_log=None, drop_last=False):
+        """Epochs of fused steps with the control flow of `MyTrainer.train`: per epoch a shuffled pass over `train_data`
+        (`(sample_values [n, C, L], labels [n, n_class])` host tensors -- what the reference's Dataset yields, stacked),
+        then `evaluate` on `eval_data`, early stop after `patience` epochs without a better eval loss, a model checkpoint
+        every `save_every_n_epoch` epochs and at the end (`model - <tag>.pt`, the reference's format) -- and, which the
+        reference does not save, the trainer state next to it (`trainer - <tag>.pt`) so `resume()` restarts the schedule,
+        AdamW's moments and the dropout stream where they stopped.
+
+        Unlike the reference nothing here synchronises per step (it calls `.item()` and sklearn every step,
+        train.py:278,287-290): batches are staged one step ahead on a copy stream, the loss of every `log_every`-th step
+        is copied to pinned memory asynchronously and read one logging interval later; the non-finite check is polled at
+        the same cadence.  Returns the list of log records."""
+        from .metrics import evaluate
+        x_all, y_all = train_data
+        n = x_all.shape[0]
+        bsz = train_batch_size
+        steps_per_epoch = n // bsz if drop_last else (n + bsz - 1) // bsz
+        logs, best_eval, n_bad = [], float('inf'), 0
+        emit = on_log or (lambda rec: None)
+        ring = [(torch.zeros(1).pin_memory(), torch.cuda.Event()) for _ in range(2)]
+        pending = None   # (record, slot) whose loss is in flight
+        gen = torch.Generator().manual_seed(shuffle_seed + self.step_count)
+
+        def flush():
+            nonlocal pending
+            if pending is not None:
+                rec, slot = pending
+                ring[slot][1].synchronize()
+                rec['train/loss'] = float(ring[slot][0])
+                logs.append(rec)
+                emit(rec)
+                pending = None
+
+        def batches(perm):
+            for i in range(steps_per_epoch):
+                idx = perm[i * bsz:(i + 1) * bsz]
+                yield x_all[idx].pin_memory(), y_all[idx].pin_memory()
+
+        for epoch in range(1, num_train_epoch + 1):
+            self.model.train()
+            perm = torch.randperm(n, generator=gen)
+            it = batches(perm)
+            staged = None
+            for i in range(steps_per_epoch):
+                if staged is None:
+                    staged = self.stage(*next(it))
+                xd, yd = staged
+                if xd.shape[0] != bsz and self.use_cuda_graph:
+                    # the ragged last batch has its own shape: run it outside the captured graph
+                    self.use_cuda_graph, saved = False, True
+                else:
+                    saved = False
+                loss, _ = self.step(xd, yd)
+                if saved:
+                    self.use_cuda_graph = True
+                staged = self.stage(*next(it)) if i + 1 < steps_per_epoch else None
+                if self.step_count % log_every == 0 or i + 1 == steps_per_epoch:
+                    flush()
+                    slot = (self.step_count // max(1, log_every)) & 1
+                    ring[slot][0].copy_(loss.reshape(1), non_blocking=True)
+                    ring[slot][1].record()
+                    pending = ({'epoch': epoch, 'step': self.step_count, 'train/learning_rate': self.current_lr()}, slot)
+                    self.check_finite()
+            flush()
+            tag = f'ep{epoch}'
+            if output_dir and save_every_n_epoch and epoch % save_every_n_epoch == 0:
+                self.save(output_dir, tag)
+            if do_eval and eval_data is not None:
+                ebsz = eval_batch_size or bsz
+                xe, ye = eval_data
+                d = evaluate(self.model, ({'sample_values': xe[j:j + ebsz], 'labels': ye[j:j + ebsz]}
+                                          for j in range(0, xe.shape[0], ebsz)))
+                rec = dict(epoch=epoch, step=self.step_count, **d)
+                logs.append(rec)
+                emit(rec)
+                if d['eval/loss'] < best_eval:   # train.py:304-314
+                    best_eval, n_bad = d['eval/loss'], 0
+                else:
+                    n_bad += 1
+                if n_bad >= patience:
+                    logs.append({'epoch': epoch, 'early_stop': True, 'patience': patience, 'best_eval_loss': best_eval})
+                    break
+        if output_dir:
+            self.save(output_dir, 'final')
+        return logs
+
+    def save(self, output_dir, tag):
+        """`model - <tag>.pt` = `model.state_dict()` as the reference saves it (train.py:297-300,319; loadable by its
+        `load_trained`), `trainer - <tag>.pt` = optimizer / schedule / dropout-stream state"""
+        os.makedirs(output_dir, exist_ok=True)
+        torch.cuda.synchronize()
+        torch.save(self.model.state_dict(), os.path.join(output_dir, f'model - {tag}.pt'))
+        torch.save(self.state_dict(), os.path.join(output_dir, f'trainer - {tag}.pt'))
+
+    def resume(self, output_dir, tag):
+        self.model.load_state_dict(torch.load(os.path.join(output_dir, f'model - {tag}.pt'), map_location='cpu'), strict=True)
+        self.load_state_dict(torch.load(os.path.join(output_dir, f'trainer - {tag}.pt'), map_location='cpu'))
+
+
 
 
 def fused_train_step(model, batch, lr=3e-4, **trainer_kwargs):
@@ -252,9 +390,10 @@ def fused_train_step(model, batch, lr=3e-4, **trainer_kwargs):
     the reference's DataLoader yields it (`sample_values`, `labels`); the `FusedTrainer` behind it is created on first
     use and kept per model.  Returns `ModelOutput(loss, logits)` (device tensors, valid until the next step)."""
     from .model import ModelOutput
-    tr = _TRAINERS.get(id(model))
-    if tr is None or tr.model is not model:
-        tr = _TRAINERS[id(model)] = FusedTrainer(model, learning_rate=lr, **trainer_kwargs)
+    tr = getattr(model, '_fused_trainer', None)   # kept ON the model (a collectable cycle), not in a global registry
+    if tr is None:
+        tr = FusedTrainer(model, learning_rate=lr, **trainer_kwargs)
+        object.__setattr__(model, '_fused_trainer', tr)
     tr.lr = lr
     loss, logits = tr.step(batch['sample_values'].cuda(non_blocking=True), batch['labels'].cuda(non_blocking=True))
     return ModelOutput(loss=loss, logits=logits)

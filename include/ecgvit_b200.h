@@ -169,14 +169,15 @@ int ecgvit_head_fwd(const void *tok, const float *gamma, const float *beta, cons
                     const float *labels, const float *loss_weight, int n_weight, float *xn, float *mean,
                     float *rstd, float *logits, float *loss, int B, int N, int d, int n_class, int reduction,
                     float eps, int dtype, void *stream);
-/* backward for reduction mean|sum with upstream gradient `grad_scale` (a host scalar, normally 1):
+/* backward for reduction mean|sum with upstream gradient `grad_scale` (a host scalar, normally 1) times, when
+ * `grad_scale_dev` is not NULL, the DEVICE scalar it points to (autograd's grad_output, read without a host sync):
  *      dlogits = grad_scale * weight * (sigmoid(z) - y) [/ (B*n_class)];  dw += ..; db += ..; dgamma/dbeta += ..;
  *      dtok is FULLY written: LN' rows at the CLS positions, zeros elsewhere; dcolsum += sum_b dtok[b,0,:] */
 int ecgvit_head_bwd(const void *tok, const float *gamma, const float *w, const float *labels,
                     const float *loss_weight, int n_weight, const float *xn, const float *mean,
                     const float *rstd, const float *logits, void *dtok, float *dw, float *db, float *dgamma,
                     float *dbeta, float *dcolsum, float *scratch, int B, int N, int d, int n_class, int reduction,
-                    float grad_scale, int dtype, void *stream);
+                    float grad_scale, const float *grad_scale_dev, int dtype, void *stream);
 
 /* ---- evaluation metrics on the device: replaces the sklearn calls of
  *      ecg_transformer/util/train.py:12-56 `get_accuracy(preds, labels)`.
@@ -212,7 +213,9 @@ int ecgvit_colsum(const void *x, float *out, int M, int N, int64_t ld, int dtype
  *        [9] 1-beta1  [10] 1-beta2  [11] 1-lr*weight_decay  [12] lr/(1-beta1^t)  [13] sqrt(1-beta2^t)
  *        ([9..13] are derived by the host in double precision, as torch.optim.AdamW derives them)
  *      stats (device, fp32[ECGVIT_STATS_FLOATS]): [0] sum of squares of (grad_scale*g)  [1] non-finite flag
- *        [2] total_norm (written by adamw / grad_scale_by_clip)  [4..] per-CTA partials (scratch).
+ *        [2] total_norm (written by adamw / grad_scale_by_clip)  [3] updates SKIPPED because the norm was non-finite
+ *        (incremented by adamw, never cleared by the library: `error_if_nonfinite` for a host that polls every k steps)
+ *        [4..] per-CTA partials (scratch).
  *      The norm is reduced without atomics, so it is bit-identical on every replica and from run to run. */
 #define ECGVIT_STATS_FLOATS 2052
 int ecgvit_grad_sumsq(const float *g, int64_t n, const float *hyper, float *stats, void *stream);

@@ -23,7 +23,9 @@ def main():
     per_rank = 8
     x, y = synthetic_batch(per_rank * world, seed=3)
     for dtype, tol in (('fp32', 2e-5), ('bf16', 2e-2)):
-        torch.manual_seed(11)
+        # every rank draws DIFFERENT initial weights: the trainer must broadcast rank 0's replica (and optimizer state)
+        # at start-up, as torch DDP does, or the replicas would silently train different models
+        torch.manual_seed(11 + 1000 * rank)
         model = ecg_b200.EcgVit(config=ecg_b200.EcgVitConfig(compute_dtype=dtype, **CFG)).to(dev).train()
         tr = ecg_b200.FusedTrainer(model, learning_rate=1e-3, max_grad_norm=0.05, bucket_layers=1,
                                    use_cuda_graph=use_graph)

@@ -262,7 +262,7 @@ def test_head_fwd_bwd(lib, dtype, reduction, weighted):
     L.check(lib.ecgvit_head_bwd(tok.data_ptr(), gamma.data_ptr(), w.data_ptr(), labels.data_ptr(), tp, nw,
                                 xn.data_ptr(), mean.data_ptr(), rstd.data_ptr(), logits.data_ptr(), dtok.data_ptr(),
                                 grads[0].data_ptr(), grads[1].data_ptr(), grads[2].data_ptr(), grads[3].data_ptr(),
-                                dcol.data_ptr(), scratch.data_ptr(), B, N, d, C, red, 1.0, dtype, stream()), 'head_bwd')
+                                dcol.data_ptr(), scratch.data_ptr(), B, N, d, C, red, 1.0, None, dtype, stream()), 'head_bwd')
     tol = 1e-5 if dtype == L.F32 else 5e-3
     assert rel(dtok, tr.grad) < tol
     assert rel(grads[0], pr[2].grad) < 1e-5 and rel(grads[1], pr[3].grad) < 1e-5
@@ -426,7 +426,7 @@ def test_embed_assemble_and_head_take_fp32_stream(lib):
         L.check(lib.ecgvit_head_bwd(tok.data_ptr(), gamma.data_ptr(), w.data_ptr(), labels.data_ptr(), None, 0,
                                     xn.data_ptr(), mean.data_ptr(), rstd.data_ptr(), logits.data_ptr(), dtok.data_ptr(),
                                     grads[0].data_ptr(), grads[1].data_ptr(), grads[2].data_ptr(), grads[3].data_ptr(),
-                                    dcol.data_ptr(), scratch.data_ptr(), B, N, d, C, 0, 1.0, code, stream()), 'head_bwd')
+                                    dcol.data_ptr(), scratch.data_ptr(), B, N, d, C, 0, 1.0, None, code, stream()), 'head_bwd')
         outs[code] = (logits, loss, dtok.float(), grads)
     a, bb = outs[L.F32], outs[L.BF16_RES32]
     assert torch.equal(a[0], bb[0]) and torch.equal(a[1], bb[1])
