@@ -357,11 +357,11 @@ def hbm_kernel_rooflines(torch, _lib, cfg, B, p_drop, n_params, peaks, launches)
     shadow = torch.empty(n, device=dev, dtype=bf)
     hyper = torch.tensor(_lib.adamw_hyper(3e-4, 0.9, 0.999, 1e-8, 1e-2, 1, 1.0, 1.0), device=dev, dtype=torch.float32)
     stats = torch.zeros(_lib.STATS_FLOATS, device=dev)
-    ms = time_graph(torch, lambda: [_lib.check(lib.ecgvit_grad_sumsq(g_.data_ptr(), n, hyper.data_ptr(), stats.data_ptr(),
+    ms = time_graph(torch, lambda: [_lib.check(lib.ecgvit_grad_sumsq(g_.data_ptr(), _lib.F32, n, hyper.data_ptr(), stats.data_ptr(),
                                                                       st()), 'grad_sumsq') for _ in range(4)], 4)
     add('grad_sumsq_kernel', 4 * n, ms, 1)
     ms = time_graph(torch, lambda: [_lib.check(lib.ecgvit_adamw_step(
-        p_.data_ptr(), m_.data_ptr(), v_.data_ptr(), g_.data_ptr(), shadow.data_ptr(), n, hyper.data_ptr(),
+        p_.data_ptr(), m_.data_ptr(), v_.data_ptr(), g_.data_ptr(), _lib.F32, shadow.data_ptr(), n, hyper.data_ptr(),
         stats.data_ptr(), st()), 'adamw_step') for _ in range(4)], 4)
     add('adamw_kernel (clip + AdamW + bf16 shadow)', 30 * n, ms, 1)
     return out
@@ -385,6 +385,10 @@ def main():
                     help='also time the reference-style loop through the nn.Module API (INTEGRATION.md section A)')
     ap.add_argument('--dropout', type=float, default=0.1, help='hidden / attention-probs dropout (reference default 0.1)')
     ap.add_argument('--profile-json', default=None, help='write the per-kernel event breakdown here')
+    ap.add_argument('--nccl-max-ctas', type=int, default=None,
+                    help='cap the CTAs of NCCL\'s collectives (communicator config): they compete with the persistent GEMMs for SMs')
+    ap.add_argument('--bucket-layers', type=int, default=1, help='encoder layers per gradient all-reduce bucket')
+    ap.add_argument('--grad-reduce', default='auto', choices=['auto', 'fp32', 'bf16'], help='dtype of the gradient all-reduce')
     args = ap.parse_args()
     wl = WORKLOADS[args.config]
     MODEL_CFG = dict(wl['model'])
@@ -408,7 +412,13 @@ def main():
     dev = torch.device('cuda', local_rank)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        dist.init_process_group('nccl', device_id=dev)
+        if args.nccl_max_ctas:
+            opts = dist.ProcessGroupNCCL.Options()
+            opts.config.max_ctas = args.nccl_max_ctas
+            opts.config.min_ctas = min(args.nccl_max_ctas, 1)
+            dist.init_process_group('nccl', device_id=dev, pg_options=opts)
+        else:
+            dist.init_process_group('nccl', device_id=dev)
     assert _lib.load().ecgvit_device_ok() == 1, 'bench.py needs an sm_100 (B200) device: there is no fallback path'
 
     if args.global_batch is not None:
@@ -420,7 +430,8 @@ def main():
     model = ecg_b200.EcgVit(config=ecg_b200.EcgVitConfig(compute_dtype='bf16', **MODEL_CFG)).to(dev).train()
     use_graph = not args.no_graph  # NCCL all-reduces are captured into the step graph as well
     trainer = ecg_b200.FusedTrainer(model, learning_rate=3e-4, weight_decay=1e-2, schedule='constant',
-                                    max_grad_norm=1.0, use_cuda_graph=use_graph)
+                                    max_grad_norm=1.0, use_cuda_graph=use_graph, bucket_layers=args.bucket_layers,
+                                    grad_reduce_dtype=args.grad_reduce)
     xh, yh = synthetic_batch(B, length=MODEL_CFG['max_signal_length'], seed=77 + rank)
     xh, yh = xh.pin_memory(), yh.pin_memory()
     x, y = xh.to(dev), yh.to(dev)
@@ -603,7 +614,7 @@ def main():
             'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': scaling, 'vs_baseline': None,
             'dtype': 'bf16', 'data': 'synthetic',
             'config': {'workload': wl['name'], 'global_batch': world * B, 'per_gpu_batch': B, 'dropout': args.dropout,
-                       'parallelism': f'dp{world}',
+                       'parallelism': f'dp{world}', 'nccl_max_ctas': args.nccl_max_ctas, 'bucket_layers': args.bucket_layers, 'grad_reduce': args.grad_reduce,
                        'l2': 'per-step working set (GBs of activations + optimizer traffic) exceeds the 126 MB L2, no '
                              'explicit flush',
                        'cuda_graph': use_graph, 'optimizer': 'AdamW lr 3e-4 wd 1e-2, clip_grad_norm 1.0',

@@ -54,6 +54,20 @@ int make_tmap(CUtensorMap *tm, const void *base, uint64_t inner, uint64_t outer,
     return 0;
 }
 
+// CTA pairs the persistent GEMM grid may use: all of them (SMs / 2) unless ecgvit_set_gemm_sm_budget() or the environment
+// variable ECGVIT_GEMM_CLUSTERS lowered it (data-parallel runs leave a few SMs to NCCL's collective kernels: a persistent
+// grid that cannot place its last CTAs runs a second, nearly empty wave)
+int g_gemm_clusters = -1;
+int gemm_clusters() {
+    if (g_gemm_clusters < 0) {
+        const char *e = getenv("ECGVIT_GEMM_CLUSTERS");
+        const int all = sm_count() / 2;
+        int v = e != nullptr ? atoi(e) : all;
+        g_gemm_clusters = (v >= 1 && v <= all) ? v : all;
+    }
+    return g_gemm_clusters;
+}
+
 template <int BN, bool A_MN, bool B_MN, int MODE>
 int launch_pair(const ecgvit_gemm_args *g, int split_k, cudaStream_t stream) {
     constexpr bool kWide = MODE == ECGVIT_EPI_BIAS_RES_F32;   // fp32 residual stream: 128-byte staging rows
@@ -88,7 +102,7 @@ int launch_pair(const ecgvit_gemm_args *g, int split_k, cudaStream_t stream) {
     }
     const int tiles_m = (g->M + 2 * BM - 1) / (2 * BM), tiles_n = (g->N + BN - 1) / BN;
     const int units = tiles_m * tiles_n * split_k;
-    const int clusters = sm_count() / 2;
+    const int clusters = gemm_clusters();
     const int grid = 2 * (units < clusters ? units : clusters);
     EpiParams ep{g->out, g->out2, g->aux, g->bias, g->ldo, make_dropout(g->dropout_p, g->dropout_stream, g->dropout_seed)};
     cudaError_t le = launch_pdl(kern, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, ta, tb, to, to2, tx, g->M,
@@ -142,7 +156,7 @@ int gemm_bf16_tc(const ecgvit_gemm_args *g, cudaStream_t stream) {
     if (g->epilogue == ECGVIT_EPI_ATOMIC_F32 && g->split_k <= 0) {
         // auto: smallest split (>= 8 k blocks each) whose work units fill >= 90 % of their last wave
         const int pair = 2;  // work units are 256-row tiles run by CTA pairs
-        const int workers = sms / pair;
+        const int workers = gemm_clusters();
         const long tiles = (long)((g->M + pair * BM - 1) / (pair * BM)) * ((g->N + 255) / 256);
         int best = 1;
         double best_eff = 0.0;
@@ -165,7 +179,7 @@ int gemm_bf16_tc(const ecgvit_gemm_args *g, cudaStream_t stream) {
     // 256 x BN pair tile can sustain at most min(1, 128 / (2 * bytes per k block / MMA clocks per k block)) of the
     // tensor peak: 1.00 at BN = 256, 0.88 at 192, 0.67 at 128.  Pick the width with the best (tile efficiency x
     // last-wave occupancy).
-    const int clusters = sms / 2;
+    const int clusters = gemm_clusters();
     const long tiles_m2 = (g->M + 2 * BM - 1) / (2 * BM);
     auto score = [&](int bn, double eff) {
         const long units = tiles_m2 * ((g->N + bn - 1) / bn) * split_k;

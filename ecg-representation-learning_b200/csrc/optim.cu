@@ -19,19 +19,30 @@ enum { S_SUMSQ = 0, S_NONFINITE, S_NORM, S_SKIPPED };
 constexpr int SUMSQ_MAX_BLOCKS = 2048;
 constexpr int S_PARTIALS = 4;  // stats[4 .. 4 + SUMSQ_MAX_BLOCKS) is scratch for the per-CTA partials
 
-__global__ void __launch_bounds__(256) grad_sumsq_kernel(const float *__restrict__ g, int64_t n,
+// four consecutive gradients as fp32 (the flat gradient buffer is fp32, or bf16 after a data-parallel bf16 all-reduce)
+__device__ __forceinline__ float4 load_grad4(const float *g, int64_t i) { return __ldg(reinterpret_cast<const float4 *>(g) + i); }
+__device__ __forceinline__ float4 load_grad4(const bf16 *g, int64_t i) {
+    const uint2 u = __ldg(reinterpret_cast<const uint2 *>(g) + i);
+    float4 v;
+    unpack_bf16x2(u.x, v.x, v.y);
+    unpack_bf16x2(u.y, v.z, v.w);
+    return v;
+}
+
+template <typename TG>
+__global__ void __launch_bounds__(256) grad_sumsq_kernel(const TG *__restrict__ g, int64_t n,
                                                           const float *__restrict__ hyper, float *__restrict__ stats) {
     __shared__ float red[8];
     const float gs = hyper[H_GSCALE];
     const int64_t n4 = n / 4;
     float s = 0.f;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-        const float4 v = __ldg(reinterpret_cast<const float4 *>(g) + i);
+        const float4 v = load_grad4(g, i);
         const float a = v.x * gs, b = v.y * gs, c = v.z * gs, d = v.w * gs;
         s = fmaf(a, a, s); s = fmaf(b, b, s); s = fmaf(c, c, s); s = fmaf(d, d, s);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0)
-        for (int64_t i = n4 * 4; i < n; ++i) { const float a = g[i] * gs; s = fmaf(a, a, s); }
+        for (int64_t i = n4 * 4; i < n; ++i) { const float a = to_f32(g[i]) * gs; s = fmaf(a, a, s); }
     s = warp_sum(s);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
     __syncthreads();
@@ -66,9 +77,9 @@ __device__ __forceinline__ float clip_coef_from(const float *hyper, const float 
     return fminf(max_norm / (total_norm + 1e-6f), 1.0f);
 }
 
-template <bool kShadow>
+template <bool kShadow, typename TG>
 __global__ void __launch_bounds__(256) adamw_kernel(float *__restrict__ p, float *__restrict__ m,
-                                                     float *__restrict__ v, const float *__restrict__ g,
+                                                     float *__restrict__ v, const TG *__restrict__ g,
                                                      bf16 *__restrict__ shadow, int64_t n,
                                                      const float *__restrict__ hyper, float *__restrict__ stats) {
     float total_norm;
@@ -88,7 +99,7 @@ __global__ void __launch_bounds__(256) adamw_kernel(float *__restrict__ p, float
     const float gmul = hyper[H_GSCALE] * clip;
     const int64_t n4 = n / 4;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-        const float4 g4 = __ldg(reinterpret_cast<const float4 *>(g) + i);
+        const float4 g4 = load_grad4(g, i);
         float4 p4 = reinterpret_cast<float4 *>(p)[i], m4 = reinterpret_cast<float4 *>(m)[i],
                v4 = reinterpret_cast<float4 *>(v)[i];
         float pp[4] = {p4.x, p4.y, p4.z, p4.w}, mm[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
@@ -143,29 +154,40 @@ using namespace ecgvit;
 
 extern "C" {
 
-int ecgvit_grad_sumsq(const float *g, int64_t n, const float *hyper, float *stats, void *stream) {
+int ecgvit_grad_sumsq(const void *g, int grad_dtype, int64_t n, const float *hyper, float *stats, void *stream) {
     ECGVIT_REQUIRE(g && hyper && stats && n > 0, "grad_sumsq: bad arguments");
     ECGVIT_REQUIRE((reinterpret_cast<uintptr_t>(g) & 15) == 0, "grad_sumsq: g must be 16-byte aligned");
+    ECGVIT_REQUIRE(grad_dtype == ECGVIT_F32 || grad_dtype == ECGVIT_BF16, "grad_sumsq: unknown gradient dtype %d", grad_dtype);
     int grid = flat_grid(n);
     if (grid > SUMSQ_MAX_BLOCKS) grid = SUMSQ_MAX_BLOCKS;
-    grad_sumsq_kernel<<<grid, 256, 0, as_stream(stream)>>>(g, n, hyper, stats);
+    if (grad_dtype == ECGVIT_F32)
+        grad_sumsq_kernel<float><<<grid, 256, 0, as_stream(stream)>>>((const float *)g, n, hyper, stats);
+    else
+        grad_sumsq_kernel<bf16><<<grid, 256, 0, as_stream(stream)>>>((const bf16 *)g, n, hyper, stats);
     int rc = check_launch("grad_sumsq");
     if (rc) return rc;
     grad_sumsq_finalize_kernel<<<1, 256, 0, as_stream(stream)>>>(stats, grid);
     return check_launch("grad_sumsq_finalize");
 }
 
-int ecgvit_adamw_step(float *p, float *m, float *v, const float *g, void *shadow_bf16, int64_t n,
+int ecgvit_adamw_step(float *p, float *m, float *v, const void *g, int grad_dtype, void *shadow_bf16, int64_t n,
                       const float *hyper, float *stats, void *stream) {
     ECGVIT_REQUIRE(p && m && v && g && hyper && stats && n > 0, "adamw_step: bad arguments");
     ECGVIT_REQUIRE(n % 4 == 0, "adamw_step: flat length %lld must be a multiple of 4 (pad the flat buffer)", (long long)n);
     ECGVIT_REQUIRE(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v) |
                      reinterpret_cast<uintptr_t>(g)) & 15) == 0,
                    "adamw_step: buffers must be 16-byte aligned");
-    if (shadow_bf16 != nullptr)
-        adamw_kernel<true><<<flat_grid(n), 256, 0, as_stream(stream)>>>(p, m, v, g, (bf16 *)shadow_bf16, n, hyper, stats);
-    else
-        adamw_kernel<false><<<flat_grid(n), 256, 0, as_stream(stream)>>>(p, m, v, g, nullptr, n, hyper, stats);
+    ECGVIT_REQUIRE(grad_dtype == ECGVIT_F32 || grad_dtype == ECGVIT_BF16, "adamw_step: unknown gradient dtype %d", grad_dtype);
+    cudaStream_t s = as_stream(stream);
+    const int grid = flat_grid(n);
+    bf16 *sh = (bf16 *)shadow_bf16;
+    if (grad_dtype == ECGVIT_F32) {
+        if (sh) adamw_kernel<true, float><<<grid, 256, 0, s>>>(p, m, v, (const float *)g, sh, n, hyper, stats);
+        else adamw_kernel<false, float><<<grid, 256, 0, s>>>(p, m, v, (const float *)g, nullptr, n, hyper, stats);
+    } else {
+        if (sh) adamw_kernel<true, bf16><<<grid, 256, 0, s>>>(p, m, v, (const bf16 *)g, sh, n, hyper, stats);
+        else adamw_kernel<false, bf16><<<grid, 256, 0, s>>>(p, m, v, (const bf16 *)g, nullptr, n, hyper, stats);
+    }
     return check_launch("adamw_step");
 }
 

@@ -60,7 +60,7 @@ def clip_grad_norm_(model, max_norm, norm_type=2.0, error_if_nonfinite=False):
     hyper, stats = _scratch(model)
     _upload(model, hyper, _lib.adamw_hyper(0.0, 0.9, 0.999, 1e-8, 0.0, 1, float(max_norm), 1.0))
     st = torch.cuda.current_stream().cuda_stream
-    _lib.check(lib.ecgvit_grad_sumsq(g.data_ptr(), g.numel(), hyper.data_ptr(), stats.data_ptr(), st), 'grad_sumsq')
+    _lib.check(lib.ecgvit_grad_sumsq(g.data_ptr(), _lib.F32, g.numel(), hyper.data_ptr(), stats.data_ptr(), st), 'grad_sumsq')
     _lib.check(lib.ecgvit_grad_scale_by_clip(g.data_ptr(), g.numel(), hyper.data_ptr(), stats.data_ptr(), st),
                'grad_scale_by_clip')
     total_norm = stats[2].clone()   # a device scalar, like torch's; only error_if_nonfinite reads it on the host
@@ -117,7 +117,7 @@ class FusedAdamW(torch.optim.Optimizer):
         stats.zero_()
         st = torch.cuda.current_stream().cuda_stream
         _lib.check(_lib.load().ecgvit_adamw_step(model._flat_p.data_ptr(), self._m.data_ptr(), self._v.data_ptr(),
-                                                 g.data_ptr(), _lib.ptr(model._shadow), n, hyper.data_ptr(),
+                                                 g.data_ptr(), _lib.F32, _lib.ptr(model._shadow), n, hyper.data_ptr(),
                                                  stats.data_ptr(), st), 'adamw_step')
         for o, cnt, p0, m0, v0 in keep:
             model._flat_p[o:o + cnt].copy_(p0)

@@ -33,7 +33,9 @@ def bucket_slices(layer_offsets, total, depth, bucket_layers):
 
 
 class BucketedGradReducer:
-    def __init__(self, model=None, group=None, bucket_layers=1, flat_g=None, layer_offsets=None, depth=None):
+    def __init__(self, model=None, group=None, bucket_layers=1, flat_g=None, layer_offsets=None, depth=None, bf16=False):
+        """bf16=True: every bucket is cast to bf16 (a contiguous slice of `flat_g16`) right before its all-reduce and the
+        optimizer kernels read the reduced bf16 image; the fp32 buffer keeps receiving the split-K red.adds."""
         self.group = group
         if model is not None:
             flat_g = model._flat_g
@@ -41,6 +43,7 @@ class BucketedGradReducer:
             layer_offsets = [model._layout[f'l{l}.ln1.w'][0] for l in range(depth)]
             model._after_layer_backward = self.on_layer_done
         self.flat_g = flat_g
+        self.flat_g16 = torch.empty(flat_g.numel(), device=flat_g.device, dtype=torch.bfloat16) if bf16 else None
         self.slices = bucket_slices(layer_offsets, flat_g.numel(), depth, bucket_layers)
         self.by_trigger = {t: (lo, hi) for (t, lo, hi) in self.slices}
         self.works = []
@@ -53,7 +56,16 @@ class BucketedGradReducer:
         if s is None:
             return
         lo, hi = s
-        self.works.append(dist.all_reduce(self.flat_g[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        buf = self.flat_g[lo:hi]
+        if self.flat_g16 is not None:
+            if buf.is_cuda:
+                from . import _lib
+                _lib.check(_lib.load().ecgvit_cast_f32_to_bf16(buf.data_ptr(), self.flat_g16[lo:hi].data_ptr(), hi - lo,
+                                                               torch.cuda.current_stream().cuda_stream), 'cast')
+            else:
+                self.flat_g16[lo:hi].copy_(buf)   # host-side tests of the bucketing logic (gloo)
+            buf = self.flat_g16[lo:hi]
+        self.works.append(dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
     def finish(self):
         for w in self.works:

@@ -49,7 +49,7 @@ def get_train_args(args=None, n_train=None):
 class FusedTrainer:
     def __init__(self, model, learning_rate=3e-4, weight_decay=1e-2, betas=(0.9, 0.999), eps=1e-8,
                  schedule='constant', n_warmup=0, n_step=1 << 30, max_grad_norm=1.0, process_group=None,
-                 bucket_layers=1, use_cuda_graph=False, data_parallel=True):
+                 bucket_layers=1, use_cuda_graph=False, data_parallel=True, grad_reduce_dtype='auto'):
         self.model = model
         self._flat_ptr = None
         self.lr, self.wd, self.betas, self.eps = learning_rate, weight_decay, betas, eps
@@ -63,6 +63,10 @@ class FusedTrainer:
                               (torch.distributed.is_available() and torch.distributed.is_initialized())):
             self.world = torch.distributed.get_world_size(process_group)
         self.bucket_layers = bucket_layers
+        # dtype of the gradient all-reduce: 'fp32', 'bf16', or 'auto' = bf16 in bf16 compute mode (half the NVLink bytes,
+        # half the time NCCL's kernels share the SMs with backward), fp32 in fp32 parity mode
+        assert grad_reduce_dtype in ('auto', 'fp32', 'bf16')
+        self.grad_reduce_dtype = grad_reduce_dtype
         self.use_cuda_graph = use_cuda_graph
         self._state_ready = False
         self._graph = None
@@ -94,7 +98,8 @@ class FusedTrainer:
         if self.world > 1:
             from .parallel import BucketedGradReducer
             dist = torch.distributed
-            self._reducer = BucketedGradReducer(m, self.group, self.bucket_layers)
+            bf16 = self.grad_reduce_dtype == 'bf16' or (self.grad_reduce_dtype == 'auto' and m._dtype_code == _lib.BF16)
+            self._reducer = BucketedGradReducer(m, self.group, self.bucket_layers, bf16=bf16)
             m._engine.rank_offset = 7919 * dist.get_rank(self.group)  # independent dropout masks per replica
             # replicas must start from the same weights and optimizer state whatever each rank's RNG or checkpoint did
             # (torch DDP broadcasts at construction too): rank 0 wins
@@ -144,10 +149,14 @@ class FusedTrainer:
         if self._reducer is not None:
             self._reducer.finish()
         n = m._flat_g.numel()
-        _lib.check(self.lib.ecgvit_grad_sumsq(m._flat_g.data_ptr(), n, self.hyper.data_ptr(), self.stats.data_ptr(), st),
+        # the buffer the exchanged gradients ended up in: the fp32 accumulation buffer, or its bf16 image when the
+        # all-reduce ran in bf16
+        g, g_code = (m._flat_g, _lib.F32) if self._reducer is None or self._reducer.flat_g16 is None \
+            else (self._reducer.flat_g16, _lib.BF16)
+        _lib.check(self.lib.ecgvit_grad_sumsq(g.data_ptr(), g_code, n, self.hyper.data_ptr(), self.stats.data_ptr(), st),
                    'grad_sumsq')
         _lib.check(self.lib.ecgvit_adamw_step(m._flat_p.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
-                                              m._flat_g.data_ptr(), _lib.ptr(m._shadow), n, self.hyper.data_ptr(),
+                                              g.data_ptr(), g_code, _lib.ptr(m._shadow), n, self.hyper.data_ptr(),
                                               self.stats.data_ptr(), st), 'adamw_step')
         return loss, logits
 

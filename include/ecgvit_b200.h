@@ -218,8 +218,10 @@ int ecgvit_colsum(const void *x, float *out, int M, int N, int64_t ld, int dtype
  *        [4..] per-CTA partials (scratch).
  *      The norm is reduced without atomics, so it is bit-identical on every replica and from run to run. */
 #define ECGVIT_STATS_FLOATS 2052
-int ecgvit_grad_sumsq(const float *g, int64_t n, const float *hyper, float *stats, void *stream);
-int ecgvit_adamw_step(float *p, float *m, float *v, const float *g, void *shadow_bf16, int64_t n,
+/* `g` is the flat gradient buffer in `grad_dtype`: ECGVIT_F32, or ECGVIT_BF16 when a data-parallel run all-reduced the
+ * gradients in bf16 (half the NVLink bytes; the moments and parameters stay fp32 either way). */
+int ecgvit_grad_sumsq(const void *g, int grad_dtype, int64_t n, const float *hyper, float *stats, void *stream);
+int ecgvit_adamw_step(float *p, float *m, float *v, const void *g, int grad_dtype, void *shadow_bf16, int64_t n,
                       const float *hyper, float *stats, void *stream);
 /* in-place  g *= clip_coef  for API-compatible clip_grad_norm_ on a flat buffer */
 int ecgvit_grad_scale_by_clip(float *g, int64_t n, const float *hyper, float *stats, void *stream);

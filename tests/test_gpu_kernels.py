@@ -321,8 +321,8 @@ def test_clip_and_adamw_match_torch(lib, max_norm):
             norm = g.norm()
         opt.step()
         hyper.copy_(torch.tensor(L.adamw_hyper(3e-4, 0.9, 0.999, 1e-8, 1e-2, t, max_norm, 1.0)))
-        L.check(lib.ecgvit_grad_sumsq(g.data_ptr(), n, hyper.data_ptr(), stats.data_ptr(), stream()), 'sumsq')
-        L.check(lib.ecgvit_adamw_step(p.data_ptr(), m.data_ptr(), v.data_ptr(), g.data_ptr(), shadow.data_ptr(), n,
+        L.check(lib.ecgvit_grad_sumsq(g.data_ptr(), L.F32, n, hyper.data_ptr(), stats.data_ptr(), stream()), 'sumsq')
+        L.check(lib.ecgvit_adamw_step(p.data_ptr(), m.data_ptr(), v.data_ptr(), g.data_ptr(), L.F32, shadow.data_ptr(), n,
                                       hyper.data_ptr(), stats.data_ptr(), stream()), 'adamw')
         assert abs(float(stats[2]) - float(norm)) < 1e-5 * float(norm)
         assert rel(p, ref.data) < 1e-6
@@ -339,8 +339,8 @@ def test_adamw_skips_update_on_nonfinite_gradients(lib):
     g[17] = float('inf')
     hyper, stats = torch.zeros(16, device='cuda'), torch.zeros(L.STATS_FLOATS, device='cuda')
     hyper.copy_(torch.tensor(L.adamw_hyper(3e-4, 0.9, 0.999, 1e-8, 1e-2, 1, 1.0, 1.0)))
-    L.check(lib.ecgvit_grad_sumsq(g.data_ptr(), n, hyper.data_ptr(), stats.data_ptr(), stream()), 'sumsq')
-    L.check(lib.ecgvit_adamw_step(p.data_ptr(), m.data_ptr(), v.data_ptr(), g.data_ptr(), None, n, hyper.data_ptr(),
+    L.check(lib.ecgvit_grad_sumsq(g.data_ptr(), L.F32, n, hyper.data_ptr(), stats.data_ptr(), stream()), 'sumsq')
+    L.check(lib.ecgvit_adamw_step(p.data_ptr(), m.data_ptr(), v.data_ptr(), g.data_ptr(), L.F32, None, n, hyper.data_ptr(),
                                   stats.data_ptr(), stream()), 'adamw')
     assert torch.equal(p, p0) and float(m.abs().sum()) == 0.0
     assert float(stats[1]) == 1.0 and not math.isfinite(float(stats[2]))
@@ -460,3 +460,25 @@ def test_gemm_aux_epilogues_many_row_tiles_partial_last_column_tile(lib, epi):
         uu = aux.float().requires_grad_(True)
         torch.nn.functional.gelu(uu).sum().backward()
         assert rel(out, acc * uu.grad) < 5e-3
+
+
+def test_clip_adamw_read_bf16_gradients(lib):
+    """data-parallel runs all-reduce the gradients in bf16: norm and AdamW then read the bf16 image (grad_dtype BF16)"""
+    n = 4096 * 5 + 8
+    g32 = torch.randn(n, device='cuda') * 0.3
+    g16 = g32.bfloat16()
+    outs = []
+    for g, code in ((g16.float(), L.F32), (g16, L.BF16)):
+        p = torch.linspace(-1, 1, n, device='cuda')
+        m, v = torch.zeros(n, device='cuda'), torch.zeros(n, device='cuda')
+        shadow = torch.empty(n, device='cuda', dtype=torch.bfloat16)
+        hyper = torch.tensor(L.adamw_hyper(1e-2, 0.9, 0.999, 1e-8, 0.1, 1, 0.5, 0.125), device='cuda', dtype=torch.float32)
+        stats = torch.zeros(L.STATS_FLOATS, device='cuda')
+        L.check(lib.ecgvit_grad_sumsq(g.data_ptr(), code, n, hyper.data_ptr(), stats.data_ptr(), stream()), 'sumsq')
+        L.check(lib.ecgvit_adamw_step(p.data_ptr(), m.data_ptr(), v.data_ptr(), g.data_ptr(), code, shadow.data_ptr(), n,
+                                      hyper.data_ptr(), stats.data_ptr(), stream()), 'adamw')
+        outs.append((p, m, v, shadow, float(stats[2])))
+    for a, b in zip(outs[0][:4], outs[1][:4]):
+        assert torch.equal(a, b)                      # bf16 -> fp32 is exact: same arithmetic either way
+    want = float((g16.float() * 0.125).norm())
+    assert abs(outs[1][4] - want) < 1e-5 * want
