@@ -234,83 +234,98 @@ __device__ __forceinline__ float pair_sum(uint64_t v) {
     return a + b;
 }
 
-// LayerNorm forward: one warp per row, NV 8-element vectors per lane (d <= 256 * NV), packed fp32x2 math,
-// two-pass statistics (mean, then centred sum of squares) like ATen.  R rows are in flight per warp and MINB CTAs per
-// SM are requested from ptxas; the launcher picks R = 1, MINB = 5 (see the measurements there).
+// LayerNorm forward: one warp per row, NV 8-element vectors per lane (d <= 256 * NV), packed fp32x2 math, two-pass
+// statistics (mean, then centred sum of squares) like ATen.  Persistent: MINB CTAs per SM, every warp walks its rows with
+// gamma / beta held in registers for the whole kernel and the NEXT row's loads in flight while the current row is reduced
+// (the kernel is latency bound: a row is load -> two shuffle reductions -> store, and the first version re-read gamma /
+// beta from L1 for every row and had nothing in flight during the reductions: 19.5 us for 40 MB in the round-1 profile).
 template <typename T, int NV, int R, int MINB, typename TX = T>
 __global__ void __launch_bounds__(256, MINB) layernorm_fwd_kernel(const TX *__restrict__ x, const float *__restrict__ gamma,
                                                              const float *__restrict__ beta, T *__restrict__ y,
                                                              float *__restrict__ mean_out, float *__restrict__ rstd_out,
                                                              int M, int d, float eps) {
     pdl_launch_dependents();
-    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;
     const int64_t total_warps = (int64_t)gridDim.x * warps_per_block;
     const float inv_d = 1.0f / (float)d;
-    for (int64_t row0 = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5); row0 < M; row0 += R * total_warps) {
-        uint64_t v[R][NV][4];
-        bool live[R];
+    // parameters: not produced by the previous kernel, so they are fetched before the dependency wait
+    uint64_t g2[NV][4], b2[NV][4];
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const int64_t row = row0 + r * total_warps;
-            live[r] = row < M;
+    for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 8;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            g2[i][k] = c < d ? __ldg(reinterpret_cast<const uint64_t *>(gamma + c) + k) : 0ull;
+            b2[i][k] = c < d ? __ldg(reinterpret_cast<const uint64_t *>(beta + c) + k) : 0ull;
+        }
+    }
+    pdl_wait();
+    int64_t row = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    Packed8<TX> cur[NV], nxt[NV];
+    if (row < M) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = (i * 32 + lane) * 8;
+            if (c < d) ld_packed(cur[i], x + row * d + c);
+        }
+    }
+    for (; row < M; row += total_warps) {
+        const int64_t row_n = row + total_warps;
+        if (row_n < M) {
 #pragma unroll
             for (int i = 0; i < NV; ++i) {
                 const int c = (i * 32 + lane) * 8;
-                if (live[r] && c < d) {
-                    Packed8<TX> p;
-                    ld_packed(p, x + row * d + c);
-                    unpack_pairs(p, v[r][i]);
-                } else {
+                if (c < d) ld_packed(nxt[i], x + row_n * d + c);
+            }
+        }
+        uint64_t v[NV][4];
+        uint64_t s2 = 0ull;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) v[r][i][k] = 0ull;
+        for (int i = 0; i < NV; ++i) {
+            const int c = (i * 32 + lane) * 8;
+            if (c < d) {
+                unpack_pairs(cur[i], v[i]);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) s2 = add2(s2, v[i][k]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) v[i][k] = 0ull;
+            }
+        }
+        const float mean = warp_sum(pair_sum(s2)) * inv_d;
+        const uint64_t nmean2 = splat2(-mean);
+        uint64_t sq2 = 0ull;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = (i * 32 + lane) * 8;
+            if (c < d) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    v[i][k] = add2(v[i][k], nmean2);  // centred
+                    sq2 = fma2(v[i][k], v[i][k], sq2);
                 }
             }
         }
+        const float rstd = rsqrtf(warp_sum(pair_sum(sq2)) * inv_d + eps);
+        const uint64_t rstd2 = splat2(rstd);
+        T *yr = y + row * d;
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            if (!live[r]) continue;  // warp-uniform
-            const int64_t row = row0 + r * total_warps;
-            uint64_t s2 = 0ull;
+        for (int i = 0; i < NV; ++i) {
+            const int c = (i * 32 + lane) * 8;
+            if (c < d) {
+                uint64_t o[4];
 #pragma unroll
-            for (int i = 0; i < NV; ++i)
-#pragma unroll
-                for (int k = 0; k < 4; ++k) s2 = add2(s2, v[r][i][k]);  // lanes past d hold zeros
-            const float mean = warp_sum(pair_sum(s2)) * inv_d;
-            const uint64_t nmean2 = splat2(-mean);
-            uint64_t sq2 = 0ull;
-#pragma unroll
-            for (int i = 0; i < NV; ++i) {
-                const int c = (i * 32 + lane) * 8;
-                if (c < d) {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        v[r][i][k] = add2(v[r][i][k], nmean2);  // centred
-                        sq2 = fma2(v[r][i][k], v[r][i][k], sq2);
-                    }
-                }
-            }
-            const float rstd = rsqrtf(warp_sum(pair_sum(sq2)) * inv_d + eps);
-            const uint64_t rstd2 = splat2(rstd);
-            T *yr = y + row * d;
-#pragma unroll
-            for (int i = 0; i < NV; ++i) {
-                const int c = (i * 32 + lane) * 8;
-                if (c < d) {
-                    const uint64_t *g2 = reinterpret_cast<const uint64_t *>(gamma + c);
-                    const uint64_t *b2 = reinterpret_cast<const uint64_t *>(beta + c);
-                    uint64_t o[4];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) o[k] = fma2(mul2(v[r][i][k], rstd2), __ldg(g2 + k), __ldg(b2 + k));
-                    store_pairs(yr + c, o);
-                }
-            }
-            if (lane == 0) {
-                if (mean_out) mean_out[row] = mean;
-                if (rstd_out) rstd_out[row] = rstd;
+                for (int k = 0; k < 4; ++k) o[k] = fma2(mul2(v[i][k], rstd2), g2[i][k], b2[i][k]);
+                store_pairs(yr + c, o);
             }
         }
+        if (lane == 0) {
+            if (mean_out) mean_out[row] = mean;
+            if (rstd_out) rstd_out[row] = rstd;
+        }
+#pragma unroll
+        for (int i = 0; i < NV; ++i) cur[i] = nxt[i];
     }
 }
 
@@ -682,12 +697,12 @@ int ecgvit_layernorm_fwd(const void *x, const float *gamma, const float *beta, v
                    8 * 32 * LN_MAXV);
     const int nv = (d + 255) / 256;
     cudaStream_t st = as_stream(stream);
-    // one row in flight per warp at 5 CTAs (40 warps) per SM, grid-stride over the rows: measured 14.9 us at cfg2 against
-    // 15.7 us for two rows in flight at 3 CTAs per SM and 15.1 us at 4 CTAs per SM
+    // persistent: 2 CTAs (16 warps) per SM (gamma / beta / two rows live in registers: ~100 of them), each warp walks its
+    // rows with the next row's loads in flight
     int grid = grid_for((int64_t)M * 32, 256);
-    if (grid > sm_count() * 5) grid = sm_count() * 5;
+    if (grid > sm_count() * 2) grid = sm_count() * 2;
 #define ECGVIT_LN_FWD(TT, NVV)                                                                                          \
-    launch_pdl(layernorm_fwd_kernel<TT, NVV, 1, 5>, dim3(grid), dim3(256), 0, st, (const TT *)x, gamma, beta, (TT *)y,   \
+    launch_pdl(layernorm_fwd_kernel<TT, NVV, 1, 2>, dim3(grid), dim3(256), 0, st, (const TT *)x, gamma, beta, (TT *)y,   \
                mean, rstd, M, d, eps)
     if (dtype == ECGVIT_BF16) {
         switch (nv) {
@@ -698,7 +713,7 @@ int ecgvit_layernorm_fwd(const void *x, const float *gamma, const float *beta, v
         }
     } else if (dtype == ECGVIT_BF16_RES32) {   // fp32 residual stream in, bf16 operand out
 #define ECGVIT_LN_FWD_R(NVV)                                                                                            \
-    launch_pdl(layernorm_fwd_kernel<bf16, NVV, 1, 4, float>, dim3(grid), dim3(256), 0, st, (const float *)x, gamma, beta, \
+    launch_pdl(layernorm_fwd_kernel<bf16, NVV, 1, 2, float>, dim3(grid), dim3(256), 0, st, (const float *)x, gamma, beta, \
                (bf16 *)y, mean, rstd, M, d, eps)
         switch (nv) {
             case 1: ECGVIT_LN_FWD_R(1); break;
