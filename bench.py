@@ -362,7 +362,7 @@ def hbm_kernel_rooflines(torch, _lib, cfg, B, p_drop, n_params, peaks, launches)
     add('grad_sumsq_kernel', 4 * n, ms, 1)
     ms = time_graph(torch, lambda: [_lib.check(lib.ecgvit_adamw_step(
         p_.data_ptr(), m_.data_ptr(), v_.data_ptr(), g_.data_ptr(), _lib.F32, shadow.data_ptr(), n, hyper.data_ptr(),
-        stats.data_ptr(), st()), 'adamw_step') for _ in range(4)], 4)
+        stats.data_ptr(), 0, st()), 'adamw_step') for _ in range(4)], 4)
     add('adamw_kernel (clip + AdamW + bf16 shadow)', 30 * n, ms, 1)
     return out
 
@@ -388,6 +388,9 @@ def main():
     ap.add_argument('--nccl-max-ctas', type=int, default=None,
                     help='cap the CTAs of NCCL\'s collectives (communicator config): they compete with the persistent GEMMs for SMs')
     ap.add_argument('--bucket-layers', type=int, default=1, help='encoder layers per gradient all-reduce bucket')
+    ap.add_argument('--defer', action='store_true',
+                    help='run clip + AdamW of step k beside the forward pass of step k + 1 (FusedTrainer(defer_optimizer=True)); '
+                         'measured neutral at cfg2: the slices displace CTAs of the persistent forward GEMMs')
     ap.add_argument('--grad-reduce', default='auto', choices=['auto', 'fp32', 'bf16'], help='dtype of the gradient all-reduce')
     args = ap.parse_args()
     wl = WORKLOADS[args.config]
@@ -431,7 +434,7 @@ def main():
     use_graph = not args.no_graph  # NCCL all-reduces are captured into the step graph as well
     trainer = ecg_b200.FusedTrainer(model, learning_rate=3e-4, weight_decay=1e-2, schedule='constant',
                                     max_grad_norm=1.0, use_cuda_graph=use_graph, bucket_layers=args.bucket_layers,
-                                    grad_reduce_dtype=args.grad_reduce)
+                                    grad_reduce_dtype=args.grad_reduce, defer_optimizer=args.defer)
     xh, yh = synthetic_batch(B, length=MODEL_CFG['max_signal_length'], seed=77 + rank)
     xh, yh = xh.pin_memory(), yh.pin_memory()
     x, y = xh.to(dev), yh.to(dev)
@@ -501,6 +504,8 @@ def main():
     e2e_ms = timed(e2e_step, args.steps) / args.steps
     e2e_value = world * B / (e2e_ms / 1e3)
     assert all(l == l for l in losses), 'non-finite loss read back in the end-to-end arm'
+    trainer.flush()          # the deferred optimizer's last update (nothing below may see half-updated state)
+    trainer.check_finite()
 
     # ---- optional: the reference-style loop through the nn.Module API ------------
     api_loop = None
@@ -618,6 +623,9 @@ def main():
                        'l2': 'per-step working set (GBs of activations + optimizer traffic) exceeds the 126 MB L2, no '
                              'explicit flush',
                        'cuda_graph': use_graph, 'optimizer': 'AdamW lr 3e-4 wd 1e-2, clip_grad_norm 1.0',
+                       'optimizer_placement': 'each step runs clip + AdamW of the PREVIOUS step beside its forward pass '
+                                              '(every timed step contains exactly one full update)' if args.defer
+                                              else 'end of step',
                        'residual_stream': 'fp32' if model._res_f32 else 'bf16',
                        'activation_checkpointing': bool(MODEL_CFG.get('activation_checkpointing', False))},
             'clocks': clocks,

@@ -71,7 +71,8 @@ SIGNATURES = {
                                                                       c_int, c_void_p],
     'ecgvit_colsum': [c_void_p, c_void_p, c_int, c_int, c_int64, c_int, c_void_p],
     'ecgvit_grad_sumsq': [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p],
-    'ecgvit_adamw_step': [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int64, c_void_p, c_void_p, c_void_p],
+    'ecgvit_adamw_step': [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int64, c_void_p, c_void_p, c_int,
+                          c_void_p],
     'ecgvit_grad_scale_by_clip': [c_void_p, c_int64, c_void_p, c_void_p, c_void_p],
     'ecgvit_cast_f32_to_bf16': [c_void_p, c_void_p, c_int64, c_void_p],
 }
@@ -159,12 +160,15 @@ def dropout_keep_mask(seed, stream, p, index):
     return torch.where(bits >= thr, torch.tensor(scale, dtype=torch.float32), torch.tensor(0.0, dtype=torch.float32))
 
 
-def adamw_hyper(lr, beta1, beta2, eps, weight_decay, step, max_norm, grad_scale):
+ADAMW_SLICE, ADAMW_FIRST_SLICE = 1, 2
+
+
+def adamw_hyper(lr, beta1, beta2, eps, weight_decay, step, max_norm, grad_scale, skip=False):
     """the 16-float `hyper` block of ecgvit_grad_sumsq / ecgvit_adamw_step (include/ecgvit_b200.h); derived scalars
     are evaluated in double precision here, exactly where torch.optim.AdamW evaluates them"""
     bc1, bc2 = 1.0 - beta1 ** step, 1.0 - beta2 ** step
     vals = [lr, beta1, beta2, eps, weight_decay, bc1, bc2, max_norm, grad_scale,
-            1.0 - beta1, 1.0 - beta2, 1.0 - lr * weight_decay, lr / bc1, bc2 ** 0.5]
+            1.0 - beta1, 1.0 - beta2, 1.0 - lr * weight_decay, lr / bc1, bc2 ** 0.5, 1.0 if skip else 0.0]
     return vals + [0.0] * (16 - len(vals))
 
 

@@ -10,7 +10,7 @@ namespace ecgvit {
 namespace {
 
 enum { H_LR = 0, H_BETA1, H_BETA2, H_EPS, H_WD, H_BC1, H_BC2, H_MAXNORM, H_GSCALE,
-       H_ONE_MINUS_B1, H_ONE_MINUS_B2, H_DECAY, H_STEP_SIZE, H_BC2_SQRT };
+       H_ONE_MINUS_B1, H_ONE_MINUS_B2, H_DECAY, H_STEP_SIZE, H_BC2_SQRT, H_SKIP };
 enum { S_SUMSQ = 0, S_NONFINITE, S_NORM, S_SKIPPED };
 
 // Stage 1: one partial sum of squares per CTA (fixed grid-stride order inside the CTA).
@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(256) grad_sumsq_finalize_kernel(float *__restr
         if (threadIdx.x == 0) {
             stats[S_SUMSQ] = t;
             stats[S_NONFINITE] = isfinite(t) ? 0.0f : 1.0f;
+            stats[S_NORM] = sqrtf(t);   // the total norm is known here already (AdamW may run much later when deferred)
         }
     }
 }
@@ -81,14 +82,16 @@ template <bool kShadow, typename TG>
 __global__ void __launch_bounds__(256) adamw_kernel(float *__restrict__ p, float *__restrict__ m,
                                                      float *__restrict__ v, const TG *__restrict__ g,
                                                      bf16 *__restrict__ shadow, int64_t n,
-                                                     const float *__restrict__ hyper, float *__restrict__ stats) {
+                                                     const float *__restrict__ hyper, float *__restrict__ stats,
+                                                     bool count_skips) {
+    if (hyper[H_SKIP] != 0.f) return;   // a deferred-update slot with nothing pending (first step, or just flushed)
     float total_norm;
     const float clip = clip_coef_from(hyper, stats, total_norm);
-    if (blockIdx.x == 0 && threadIdx.x == 0) stats[S_NORM] = total_norm;
+    if (count_skips && blockIdx.x == 0 && threadIdx.x == 0) stats[S_NORM] = total_norm;
     // error_if_nonfinite: leave parameters and state untouched and COUNT the skipped update (sticky until the host clears
     // it: a poll every k steps cannot miss one); the host raises when it polls
     if (!isfinite(total_norm)) {
-        if (blockIdx.x == 0 && threadIdx.x == 0) stats[S_SKIPPED] += 1.0f;
+        if (count_skips && blockIdx.x == 0 && threadIdx.x == 0) stats[S_SKIPPED] += 1.0f;
         return;
     }
     // the derived scalars are computed by the host in double precision exactly like torch.optim.AdamW does
@@ -171,7 +174,7 @@ int ecgvit_grad_sumsq(const void *g, int grad_dtype, int64_t n, const float *hyp
 }
 
 int ecgvit_adamw_step(float *p, float *m, float *v, const void *g, int grad_dtype, void *shadow_bf16, int64_t n,
-                      const float *hyper, float *stats, void *stream) {
+                      const float *hyper, float *stats, int flags, void *stream) {
     ECGVIT_REQUIRE(p && m && v && g && hyper && stats && n > 0, "adamw_step: bad arguments");
     ECGVIT_REQUIRE(n % 4 == 0, "adamw_step: flat length %lld must be a multiple of 4 (pad the flat buffer)", (long long)n);
     ECGVIT_REQUIRE(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v) |
@@ -179,14 +182,19 @@ int ecgvit_adamw_step(float *p, float *m, float *v, const void *g, int grad_dtyp
                    "adamw_step: buffers must be 16-byte aligned");
     ECGVIT_REQUIRE(grad_dtype == ECGVIT_F32 || grad_dtype == ECGVIT_BF16, "adamw_step: unknown gradient dtype %d", grad_dtype);
     cudaStream_t s = as_stream(stream);
-    const int grid = flat_grid(n);
+    // ECGVIT_ADAMW_SLICE: this call updates one slice of a larger buffer next to other work (the deferred optimizer runs
+    // layer by layer beside the next forward pass): short-lived CTAs (one pass each) that never hold an SM for long, and
+    // only the call flagged ECGVIT_ADAMW_FIRST_SLICE records the norm / counts a skipped update
+    const bool slice = (flags & ECGVIT_ADAMW_SLICE) != 0;
+    const bool count = !slice || (flags & ECGVIT_ADAMW_FIRST_SLICE) != 0;
+    const int grid = slice ? (int)((n / 4 + 255) / 256) : flat_grid(n);
     bf16 *sh = (bf16 *)shadow_bf16;
     if (grad_dtype == ECGVIT_F32) {
-        if (sh) adamw_kernel<true, float><<<grid, 256, 0, s>>>(p, m, v, (const float *)g, sh, n, hyper, stats);
-        else adamw_kernel<false, float><<<grid, 256, 0, s>>>(p, m, v, (const float *)g, nullptr, n, hyper, stats);
+        if (sh) adamw_kernel<true, float><<<grid, 256, 0, s>>>(p, m, v, (const float *)g, sh, n, hyper, stats, count);
+        else adamw_kernel<false, float><<<grid, 256, 0, s>>>(p, m, v, (const float *)g, nullptr, n, hyper, stats, count);
     } else {
-        if (sh) adamw_kernel<true, bf16><<<grid, 256, 0, s>>>(p, m, v, (const bf16 *)g, sh, n, hyper, stats);
-        else adamw_kernel<false, bf16><<<grid, 256, 0, s>>>(p, m, v, (const bf16 *)g, nullptr, n, hyper, stats);
+        if (sh) adamw_kernel<true, bf16><<<grid, 256, 0, s>>>(p, m, v, (const bf16 *)g, sh, n, hyper, stats, count);
+        else adamw_kernel<false, bf16><<<grid, 256, 0, s>>>(p, m, v, (const bf16 *)g, nullptr, n, hyper, stats, count);
     }
     return check_launch("adamw_step");
 }

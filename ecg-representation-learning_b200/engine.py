@@ -218,6 +218,9 @@ class StepEngine:
             _lib.check(lib.ecgvit_patchify_transform(x.data_ptr(), _lib.ptr(mean), _lib.ptr(std), _lib.ptr(spans),
                                                      w.a_patch.data_ptr(), B, C, x.stride(1), L_in, n, P, dt, st),
                        'patchify_transform')
+        hook = m._before_layer_forward
+        if hook is not None:
+            hook(-1)   # embedding weights, cls, pos
         # e = a_patch @ We^T + be
         w_embed = wt['embed.w']
         if Kp != K:
@@ -231,7 +234,11 @@ class StepEngine:
                                              w.x[0].data_ptr(), B, n, d, p_emb, 0, seed_ptr if p_emb > 0 else None,
                                              rdt, st), 'embed_assemble')
         for l in range(c.num_hidden_layers):
+            if hook is not None:
+                hook(l)
             self._block_forward(l, w, record_attention=record_attention)
+        if hook is not None:
+            hook(c.num_hidden_layers)   # head
         red = _lib.REDUCTION[reduction]
         loss_buf = None
         if labels is not None:

@@ -192,6 +192,8 @@ class EcgVit(nn.Module):
         self._engine = None
         self._shadow_versions = None
         self._after_layer_backward = None  # hook used by the data-parallel gradient bucketing
+        self._before_layer_forward = None  # hook used by the deferred optimizer (a layer waits for ITS weights only)
+        self._flush_pending = None         # set by a trainer whose last update is still pending (deferred optimizer)
 
     # ---- reference API -----------------------------------------------------------------------------
     def to_str(self):
@@ -205,9 +207,16 @@ class EcgVit(nn.Module):
     def loss_reduction(self, r):
         self._loss_reduction = r
 
+    def state_dict(self, *args, **kwargs):
+        if self._flush_pending is not None:
+            self._flush_pending()   # a deferred optimizer update is applied before anyone reads the weights
+        return super().state_dict(*args, **kwargs)
+
     def forward(self, sample_values: torch.FloatTensor, labels: torch.LongTensor = None, time_out_spans=None):
         """`time_out_spans` (only with an `input_pipeline` that has TimeOut, training mode): int [B, 2] (start, length)
         per record; drawn on the host like the reference's TimeOut when omitted."""
+        if self._flush_pending is not None:
+            self._flush_pending()
         self._prepare(sample_values.device)
         pipe = self.input_pipeline
         if pipe is not None and pipe.timeout is not None and self.training:

@@ -118,7 +118,7 @@ class FusedAdamW(torch.optim.Optimizer):
         st = torch.cuda.current_stream().cuda_stream
         _lib.check(_lib.load().ecgvit_adamw_step(model._flat_p.data_ptr(), self._m.data_ptr(), self._v.data_ptr(),
                                                  g.data_ptr(), _lib.F32, _lib.ptr(model._shadow), n, hyper.data_ptr(),
-                                                 stats.data_ptr(), st), 'adamw_step')
+                                                 stats.data_ptr(), 0, st), 'adamw_step')
         for o, cnt, p0, m0, v0 in keep:
             model._flat_p[o:o + cnt].copy_(p0)
             self._m[o:o + cnt].copy_(m0)

@@ -212,8 +212,9 @@ int ecgvit_colsum(const void *x, float *out, int M, int N, int64_t ld, int dtype
  *        [7] max_grad_norm (<=0: no clipping)  [8] grad_scale (1/world for DDP sum-allreduce)
  *        [9] 1-beta1  [10] 1-beta2  [11] 1-lr*weight_decay  [12] lr/(1-beta1^t)  [13] sqrt(1-beta2^t)
  *        ([9..13] are derived by the host in double precision, as torch.optim.AdamW derives them)
+ *        [14] skip: non-zero makes ecgvit_adamw_step a no-op
  *      stats (device, fp32[ECGVIT_STATS_FLOATS]): [0] sum of squares of (grad_scale*g)  [1] non-finite flag
- *        [2] total_norm (written by adamw / grad_scale_by_clip)  [3] updates SKIPPED because the norm was non-finite
+ *        [2] total_norm (written by grad_sumsq, adamw and grad_scale_by_clip)  [3] updates SKIPPED because the norm was non-finite
  *        (incremented by adamw, never cleared by the library: `error_if_nonfinite` for a host that polls every k steps)
  *        [4..] per-CTA partials (scratch).
  *      The norm is reduced without atomics, so it is bit-identical on every replica and from run to run. */
@@ -221,8 +222,14 @@ int ecgvit_colsum(const void *x, float *out, int M, int N, int64_t ld, int dtype
 /* `g` is the flat gradient buffer in `grad_dtype`: ECGVIT_F32, or ECGVIT_BF16 when a data-parallel run all-reduced the
  * gradients in bf16 (half the NVLink bytes; the moments and parameters stay fp32 either way). */
 int ecgvit_grad_sumsq(const void *g, int grad_dtype, int64_t n, const float *hyper, float *stats, void *stream);
+/* flags: 0 for a whole-buffer update.  ECGVIT_ADAMW_SLICE: the call updates one slice (p, m, v, g, shadow all offset
+ * alike) of the flat buffers; the slices of one update may be issued in any order and beside other kernels
+ * (short-lived CTAs); exactly one of them carries ECGVIT_ADAMW_FIRST_SLICE and records the norm / the skipped-update
+ * count.  hyper[14] != 0 turns the call into a no-op (a deferred-update slot with nothing pending). */
+#define ECGVIT_ADAMW_SLICE 1
+#define ECGVIT_ADAMW_FIRST_SLICE 2
 int ecgvit_adamw_step(float *p, float *m, float *v, const void *g, int grad_dtype, void *shadow_bf16, int64_t n,
-                      const float *hyper, float *stats, void *stream);
+                      const float *hyper, float *stats, int flags, void *stream);
 /* in-place  g *= clip_coef  for API-compatible clip_grad_norm_ on a flat buffer */
 int ecgvit_grad_scale_by_clip(float *g, int64_t n, const float *hyper, float *stats, void *stream);
 

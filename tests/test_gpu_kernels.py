@@ -323,7 +323,7 @@ def test_clip_and_adamw_match_torch(lib, max_norm):
         hyper.copy_(torch.tensor(L.adamw_hyper(3e-4, 0.9, 0.999, 1e-8, 1e-2, t, max_norm, 1.0)))
         L.check(lib.ecgvit_grad_sumsq(g.data_ptr(), L.F32, n, hyper.data_ptr(), stats.data_ptr(), stream()), 'sumsq')
         L.check(lib.ecgvit_adamw_step(p.data_ptr(), m.data_ptr(), v.data_ptr(), g.data_ptr(), L.F32, shadow.data_ptr(), n,
-                                      hyper.data_ptr(), stats.data_ptr(), stream()), 'adamw')
+                                      hyper.data_ptr(), stats.data_ptr(), 0, stream()), 'adamw')
         assert abs(float(stats[2]) - float(norm)) < 1e-5 * float(norm)
         assert rel(p, ref.data) < 1e-6
         assert torch.equal(shadow, p.bfloat16())
@@ -341,7 +341,7 @@ def test_adamw_skips_update_on_nonfinite_gradients(lib):
     hyper.copy_(torch.tensor(L.adamw_hyper(3e-4, 0.9, 0.999, 1e-8, 1e-2, 1, 1.0, 1.0)))
     L.check(lib.ecgvit_grad_sumsq(g.data_ptr(), L.F32, n, hyper.data_ptr(), stats.data_ptr(), stream()), 'sumsq')
     L.check(lib.ecgvit_adamw_step(p.data_ptr(), m.data_ptr(), v.data_ptr(), g.data_ptr(), L.F32, None, n, hyper.data_ptr(),
-                                  stats.data_ptr(), stream()), 'adamw')
+                                  stats.data_ptr(), 0, stream()), 'adamw')
     assert torch.equal(p, p0) and float(m.abs().sum()) == 0.0
     assert float(stats[1]) == 1.0 and not math.isfinite(float(stats[2]))
 
@@ -476,7 +476,7 @@ def test_clip_adamw_read_bf16_gradients(lib):
         stats = torch.zeros(L.STATS_FLOATS, device='cuda')
         L.check(lib.ecgvit_grad_sumsq(g.data_ptr(), code, n, hyper.data_ptr(), stats.data_ptr(), stream()), 'sumsq')
         L.check(lib.ecgvit_adamw_step(p.data_ptr(), m.data_ptr(), v.data_ptr(), g.data_ptr(), code, shadow.data_ptr(), n,
-                                      hyper.data_ptr(), stats.data_ptr(), stream()), 'adamw')
+                                      hyper.data_ptr(), stats.data_ptr(), 0, stream()), 'adamw')
         outs.append((p, m, v, shadow, float(stats[2])))
     for a, b in zip(outs[0][:4], outs[1][:4]):
         assert torch.equal(a, b)                      # bf16 -> fp32 is exact: same arithmetic either way

@@ -216,3 +216,37 @@ def test_fused_train_step_keeps_its_trainer_on_the_model():
     assert out.loss.ndim == 0 and model._fused_trainer.step_count == 1
     fused_train_step(model, {'sample_values': x, 'labels': y}, lr=1e-3)
     assert model._fused_trainer.step_count == 2
+
+
+@pytest.mark.parametrize('graph', [False, True])
+def test_deferred_optimizer_is_the_same_training_run(graph):
+    """defer_optimizer=True moves clip + AdamW of step k next to the forward pass of step k + 1 (slice by slice, each
+    layer waiting for its own weights): same losses, same gradient norms, and after flush() the same parameters and
+    moments as the immediate trainer -- cosine schedule with warm-up and an active clip, so a shifted hyper-parameter
+    block or a double-applied update would show"""
+    kw = dict(learning_rate=1e-3, weight_decay=1e-2, schedule='cosine', n_warmup=2, n_step=6, max_grad_norm=0.05)
+    _, m_now = pair()
+    _, m_def = pair()
+    t_now = FusedTrainer(m_now, use_cuda_graph=graph, data_parallel=False, **kw)
+    t_def = FusedTrainer(m_def, use_cuda_graph=graph, data_parallel=False, defer_optimizer=True, **kw)
+    x, y = synthetic_batch(6, length=2560, seed=12)
+    xd, yd = x.cuda(), y.cuda()
+    for step in range(5):
+        l_now, _ = t_now.step(xd, yd)
+        l_def, _ = t_def.step(xd, yd)
+        assert rel(l_def, l_now) < 1e-6, (step, float(l_def), float(l_now))
+        assert abs(t_def.grad_norm() - t_now.grad_norm()) < 1e-5 * t_now.grad_norm()
+        if step == 2:
+            # reading the weights mid-run applies the pending update (and must not apply it twice afterwards)
+            sd = m_def.state_dict()
+            assert rel(sd['vit.pos_embedding'], m_now.state_dict()['vit.pos_embedding']) < 1e-6
+    assert t_def._pending_step == 5
+    assert rel(m_def._flat_p, m_now._flat_p) > 1e-6          # the last update is still pending ...
+    t_def.flush()
+    assert rel(m_def._flat_p, m_now._flat_p) < 1e-6          # ... and flush() applies exactly it
+    assert rel(t_def.exp_avg, t_now.exp_avg) < 1e-5 and rel(t_def.exp_avg_sq, t_now.exp_avg_sq) < 1e-5
+    if m_def._shadow is not None:
+        assert torch.equal(m_def._shadow, m_def._flat_p.bfloat16())
+    t_def.check_finite()
+    t_def.flush()                                             # idempotent
+    assert rel(m_def._flat_p, m_now._flat_p) < 1e-6
