@@ -50,7 +50,7 @@ constexpr uint32_t F_TM_S = 0, F_TM_O = 256, F_TM_P = 384;  // S_t at S + 128 t,
 struct FwdBars {
     uint64_t q_full[2][2], q_empty[2][2];
     uint64_t kv_full[F_KV_STAGES], kv_empty[F_KV_STAGES];
-    uint64_t s_full[2], s_free[2], p_full[2], pv_done[2];
+    uint64_t s_full[2], s_free[2], p_full[2], pv_done[2], out_full[2], out_free[2];
     uint32_t tmem_ptr;
 };
 static_assert(sizeof(FwdBars) <= 256, "barrier block");
@@ -184,6 +184,8 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
             ptx::mbar_init(&bars->s_free[t], 4);   // one arrival per warp of the tile's softmax warpgroup
             ptx::mbar_init(&bars->p_full[t], 4);
             ptx::mbar_init(&bars->pv_done[t], 1);
+            ptx::mbar_init(&bars->out_full[t], 4);
+            ptx::mbar_init(&bars->out_free[t], 1);
         }
         for (int s = 0; s < F_KV_STAGES; ++s) {
             ptx::mbar_init(&bars->kv_full[s], 1);
@@ -368,6 +370,39 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
             }
             it = nxt;
         }
+    } else if (warp == 3) {
+        // ================================ result warp: TMA stores of the finished O tiles ==============
+        uint32_t oph[2] = {0, 0};
+        for (int kk = 0;; ++kk) {
+            FwdItem<kPacked> it;
+            fwd_decode<kPacked>(kk, B, N, H, it);
+            if (!it.valid[0]) break;
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                if (!it.valid[t]) continue;
+                ptx::mbar_wait(&bars->out_full[t], oph[t]);
+                oph[t] ^= 1;
+                if (ptx::elect_one()) {
+                    const uint8_t *ost = smem + F_OST_OFF + t * TILE_BYTES;
+                    if (kPacked) {
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                            const int p = it.prob[t][i];
+                            ptx::tma_store_3d(&tm_o, ost + i * (TILE_BYTES / 2), (p % H) * DH, 0, p / H);
+                        }
+                    } else {
+                        const int p = it.prob[t][0];
+                        ptx::tma_store_3d(&tm_o, ost, (p % H) * DH, it.q0[t], p / H);
+                    }
+                    ptx::tma_store_commit();
+                    ptx::tma_store_wait_read<0>();
+                    ptx::mbar_arrive(&bars->out_free[t]);
+                }
+                __syncwarp();
+            }
+        }
+        if (ptx::elect_one()) ptx::tma_store_wait_all<0>();
+        __syncwarp();
     }
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
@@ -395,7 +430,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
             ptx::tmem_st_32x16(tP + (hf ? 0 : 32) + 16, z);
             ptx::tmem_st_wait();
         }
-        uint32_t sph = 0, dph = 0;
+        uint32_t sph = 0, dph = 0, oph = 0;
         for (int kk = 0;; ++kk) {
             FwdItem<kPacked> it;
             fwd_decode<kPacked>(kk, B, N, H, it);
@@ -473,8 +508,8 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
             dph ^= 1;
             ptx::tcgen05_fence_after();
             if (q == 0) stamp(1 + t, 5);
-            if (q == 0 && lane == 0) ptx::tma_store_wait_read<0>();  // the previous store of this tile has read `ost`
-            ptx::named_bar_sync(1 + t, 128);
+            ptx::mbar_wait(&bars->out_free[t], oph ^ 1);   // warp 3's previous store of this tile has read `ost`
+            oph ^= 1;
             if (q == 0) stamp(1 + t, 7);
             const float inv_l = drop.scale / l;   // drop.scale = 1 / (1 - p) of the attention dropout (1 when off)
 #pragma unroll 1
@@ -496,25 +531,10 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
             if (q == 0) stamp(1 + t, 8);
             if (qrow < N && prob < B * H) lse[static_cast<int64_t>(prob) * N + qrow] = m * scale + __logf(l);
             ptx::fence_proxy_async_smem();
-            if (q == 0) stamp(1 + t, 9);
-            ptx::named_bar_sync(1 + t, 128);
-            if (q == 0) stamp(1 + t, 11);
-            if (q == 0 && lane == 0) {
-                if (kPacked) {
-#pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        const int p = it.prob[t][i];
-                        ptx::tma_store_3d(&tm_o, ost + i * (TILE_BYTES / 2), (p % H) * DH, 0, p / H);
-                    }
-                } else {
-                    const int p = it.prob[t][0];
-                    ptx::tma_store_3d(&tm_o, ost, (p % H) * DH, it.q0[t], p / H);
-                }
-                ptx::tma_store_commit();
-            }
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&bars->out_full[t]);   // warp 3 issues the TMA store
             if (q == 0) stamp(1 + t, 6);
         }
-        if (q == 0 && lane == 0) ptx::tma_store_wait_all<0>();
     }
 
     ptx::tcgen05_fence_before();
@@ -877,6 +897,8 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
                     ptx::mbar_wait(&bars->sdp_free, fph);   // S and dP are in the compute warps' registers
                     fph ^= 1;
                     stamp(0, 11);
+                    // (issuing this step's second group of products first whenever the next operands are still in flight
+                    // was measured slower: 43.1 vs 41.1 us at cfg2 -- the next S / dP then arrive late for the warps)
                     if (last) kv_next = wait_kv();
                     st_next = wait_qd();
                     mma1(kv_next, st_next);
@@ -1029,6 +1051,23 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
             }
         };
 
+        // row statistics of step (kk, i): log-sum-exp (+inf for rows that do not exist: P = 0) and, long geometry, D.
+        // They come from HBM / L2 and are fetched ONE STEP AHEAD (the packed kernel stalled ~1.5 k cycles per tile on them)
+        auto row_stats = [&](int kk_, int i_, float &lse_o, float &D_o) {
+            BwdItem<kPacked> it_;
+            bwd_decode<kPacked>(kk_, B, N, H, it_);
+            lse_o = INFINITY;
+            D_o = 0.f;
+            if (!it_.valid) return;
+            const int prob_ = it_.prob[hf];
+            const int qrow_ = kPacked ? (r & 63) : i_ * TM + r;
+            if (qrow_ < N && prob_ < B * H) {
+                lse_o = __ldg(lse + static_cast<int64_t>(prob_) * N + qrow_);
+                if (!kPacked) D_o = __ldg(Drow + static_cast<int64_t>(prob_) * N + qrow_);
+            }
+        };
+        float lse_next, D_next;
+        row_stats(0, 0, lse_next, D_next);
         for (int kk = 0;; ++kk) {
             BwdItem<kPacked> it;
             bwd_decode<kPacked>(kk, B, N, H, it);
@@ -1036,11 +1075,10 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
             const int prob = it.prob[hf];
             for (int i = 0; i < nsteps; ++i, ++step) {
                 const int qrow = kPacked ? (r & 63) : i * TM + r;       // query index inside the problem
-                const bool row_ok = qrow < N && prob < B * H;
-                // row statistics (in flight while we wait for the tensor core)
-                const float lse_r = row_ok ? __ldg(lse + static_cast<int64_t>(prob) * N + qrow) : INFINITY;
-                float D = 0.f;
-                if (!kPacked && row_ok) D = __ldg(Drow + static_cast<int64_t>(prob) * N + qrow);
+                const float lse_r = lse_next;
+                float D = D_next;
+                if (i + 1 < nsteps) row_stats(kk, i + 1, lse_next, D_next);
+                else row_stats(kk + 1, 0, lse_next, D_next);
                 if (warp == 4) stamp(1, 1);
                 ptx::mbar_wait(&bars->sdp_full, sph);
                 sph ^= 1;
