@@ -158,14 +158,18 @@ class StepEngine:
         w.head_scratch = buf(B * d + B * n_class, dtype=torch.float32)
         w.labels = buf(B, n_class, dtype=torch.float32)
         # backward scratch
-        w.dres = [buf(M, d), buf(M, d)]
+        # Every scratch buffer that a side-stream weight-gradient GEMM reads exists TWICE, indexed by layer parity: the main
+        # chain of layer l - 1 then never has to wait for the weight gradients of layer l (it waits for those of layer
+        # l + 1, a whole layer old), so the side stream is free to lag and fill whatever the chain leaves idle
+        w.dz = [buf(M, d), buf(M, d)]          # gradient w.r.t. a block's output (input of its backward)
+        w.dy = [buf(M, d), buf(M, d)]          # gradient w.r.t. the block's middle residual sum y
         w.dln = buf(M, d)
         w.d_o = buf(M, inner)
-        w.dqkv = buf(M, 3 * inner)
-        w.du = buf(M, mlp)
+        w.dqkv = [buf(M, 3 * inner), buf(M, 3 * inner)]
+        w.du = [buf(M, mlp), buf(M, mlp)]
         w.de = buf(B * n, d)
         # dropout-masked copies of the residual-stream gradients (only used when p > 0): one per site of a block
-        w.dzm = [buf(M, d), buf(M, d)]
+        w.dzm = [[buf(M, d), buf(M, d)], [buf(M, d), buf(M, d)]]   # [site 0 = after net[3], 1 = after to_out][parity]
         # two partial-row scratch buffers (one per LayerNorm of a block): their fold runs off the critical chain
         w.ln_scratch = [buf(int(self.lib.ecgvit_layernorm_bwd_scratch_floats(d)), dtype=torch.float32) for _ in range(2)]
         n_attn = int(self.lib.ecgvit_attention_bwd_scratch_floats(B, N, H, d // H, m._dtype_code))
@@ -341,30 +345,23 @@ class StepEngine:
         wt, pf, gr = m._weights(), m._params_f32(), m._grads_f32()
         if zero_grads:
             m._flat_g.zero_()
-        dz, dy = w.dres[0], w.dres[1]
         p_emb, p_blk = w.p_emb, w.p_blk
         seed_ptr = self.rng.data_ptr()
         blk_seed = seed_ptr if p_blk > 0 else None
         last = f'l{depth - 1}.'
+        top = (depth - 1) & 1
         # with dropout between net[3] / to_out[0] and the residual add, the Linear sees mask * dz / (1 - p): its operand
         # and its bias gradient come from the masked copy, so the producers must not pre-sum the unmasked gradient
         _lib.check(lib.ecgvit_head_bwd(
             w.x[depth].data_ptr(), pf['head.ln.w'].data_ptr(), pf['head.w'].data_ptr(), w.labels.data_ptr(),
-            *self._loss_weight_table(), w.xn.data_ptr(), w.hstat[0].data_ptr(), w.hstat[1].data_ptr(), w.logits.data_ptr(), dz.data_ptr(),
+            *self._loss_weight_table(), w.xn.data_ptr(), w.hstat[0].data_ptr(), w.hstat[1].data_ptr(), w.logits.data_ptr(),
+            w.dz[top].data_ptr(),
             gr['head.w'].data_ptr(), gr['head.b'].data_ptr(), gr['head.ln.w'].data_ptr(), gr['head.ln.b'].data_ptr(),
             gr[last + 'ff2.b'].data_ptr() if p_blk == 0 else None, w.head_scratch.data_ptr(), B, N, d, m.num_class,
             _lib.REDUCTION[w.reduction], float(grad_scale), _lib.ptr(grad_scale_dev), rdt, st), 'head_bwd')
         scale = float(dh) ** -0.5
 
         main, side = torch.cuda.current_stream(), self.side_stream
-
-        def masked(g, bias_grad, site, which):
-            """gradient w.r.t. the output of a Linear that is followed by dropout (identity when p = 0)"""
-            if p_blk == 0:
-                return g
-            _lib.check(lib.ecgvit_dropout_bwd_copy(g.data_ptr(), w.dzm[which].data_ptr(), bias_grad.data_ptr(), M, d, d,
-                                                   p_blk, site, seed_ptr, dt, st), 'dropout_bwd_copy')
-            return w.dzm[which]
 
         def wgrad(*args, **kw):
             """weight-gradient GEMM on the side stream, ordered after everything issued so far on the main stream;
@@ -410,59 +407,65 @@ class StepEngine:
                     ev_fold[which] = torch.cuda.Event()
                     ev_fold[which].record(side)
 
-        ev_ff2 = ev_ff1 = ev_out = ev_qkv = None
-        layer_events = {}   # checkpointing: side-stream events of the weight gradients that read layer l's buffer set
+        # side-stream events per layer: ev[l] = {'ff2', 'ff1', 'out', 'qkv'} -> completion of that weight gradient
+        evs = {}
+        if p_blk > 0:
+            # the top block's input gradient comes from the head, not from a LayerNorm': mask it here
+            _lib.check(lib.ecgvit_dropout_bwd_copy(w.dz[top].data_ptr(), w.dzm[0][top].data_ptr(),
+                                                   gr[last + 'ff2.b'].data_ptr(), M, d, d, p_blk, 4 * depth, seed_ptr, dt, st),
+                       'dropout_bwd_copy')
         for l in range(depth - 1, -1, -1):
             p = f'l{l}.'
+            q, qn = l & 1, (l - 1) & 1      # buffer parity of this layer / of the layer below
             s_att, s_out, s_act, s_ff2 = 1 + 4 * l, 2 + 4 * l, 3 + 4 * l, 4 + 4 * l
+            old = evs.pop(l + 2, {})        # the previous users of this parity's buffers (a whole layer ago)
             if w.ckpt and l < depth - 2:
-                # the set of layer l was last used by layer l + 2: its weight-gradient GEMMs must have read their operands
-                for ev in layer_events.pop(l + 2, ()):
+                # the activation set of layer l was last used by layer l + 2: its weight gradients must have read it
+                for ev in old.values():
                     before_overwrite(ev)
                 self._block_forward(l, w, recompute=True)
+            e = evs.setdefault(l, {})
+            dz, dy, du, dqkv = w.dz[q], w.dy[q], w.du[q], w.dqkv[q]
+            dzl = w.dzm[0][q] if p_blk > 0 else dz      # what net[3] saw: mask * dz / (1 - p)
             # ---- feed-forward branch: x[l+1] = y + drop(W2 drop(gelu(W1 ln2(y) + b1)) + b2)
-            if l == depth - 1:
-                dzl = masked(dz, gr[p + 'ff2.b'], s_ff2, 0)   # below the top block LayerNorm' writes the masked copy
-            ev_ff2 = wgrad(d, mlp, M, dzl, d, 0, w.h[l], mlp, 0, EPI_ATOMIC_F32, gr[p + 'ff2.w'], mlp, split_k=0)
-            before_overwrite(ev_ff1)   # du
-            self._gemm(M, mlp, d, dzl, d, 1, wt[p + 'ff2.w'], mlp, 0, EPI_DGELU, w.du, mlp, aux=w.u[l],
-                       drop=(p_blk, s_act))
+            e['ff2'] = wgrad(d, mlp, M, dzl, d, 0, w.h[l], mlp, 0, EPI_ATOMIC_F32, gr[p + 'ff2.w'], mlp, split_k=0)
+            before_overwrite(old.get('ff1'))   # du of this parity
+            self._gemm(M, mlp, d, dzl, d, 1, wt[p + 'ff2.w'], mlp, 0, EPI_DGELU, du, mlp, aux=w.u[l], drop=(p_blk, s_act))
             # FF1's bias gradient (column sums of du) feeds nothing in the chain: it rides on the side stream in front of
             # FF1's weight gradient (same operand, so the event that guards `du` covers both)
             if side is None:
-                _lib.check(lib.ecgvit_colsum(w.du.data_ptr(), gr[p + 'ff1.b'].data_ptr(), M, mlp, mlp, dt, st), 'colsum')
+                _lib.check(lib.ecgvit_colsum(du.data_ptr(), gr[p + 'ff1.b'].data_ptr(), M, mlp, mlp, dt, st), 'colsum')
             else:
                 ready = torch.cuda.Event()
                 ready.record(main)
                 side.wait_event(ready)
                 with torch.cuda.stream(side):
-                    _lib.check(lib.ecgvit_colsum(w.du.data_ptr(), gr[p + 'ff1.b'].data_ptr(), M, mlp, mlp, dt,
+                    _lib.check(lib.ecgvit_colsum(du.data_ptr(), gr[p + 'ff1.b'].data_ptr(), M, mlp, mlp, dt,
                                                  side.cuda_stream), 'colsum')
-            ev_ff1 = wgrad(mlp, d, M, w.du, mlp, 0, w.ln2[l], d, 0, EPI_ATOMIC_F32, gr[p + 'ff1.w'], d, split_k=0)
-            self._gemm(M, d, mlp, w.du, mlp, 1, wt[p + 'ff1.w'], d, 0, EPI_STORE, w.dln, d)
-            before_overwrite(ev_out)   # dy / dzm[1] were read by the previous layer's out-proj wgrad
-            dyl = w.dzm[1] if p_blk > 0 else dy
+            e['ff1'] = wgrad(mlp, d, M, du, mlp, 0, w.ln2[l], d, 0, EPI_ATOMIC_F32, gr[p + 'ff1.w'], d, split_k=0)
+            self._gemm(M, d, mlp, du, mlp, 1, wt[p + 'ff1.w'], d, 0, EPI_STORE, w.dln, d)
+            before_overwrite(old.get('out'))   # dy / its masked copy of this parity
+            dyl = w.dzm[1][q] if p_blk > 0 else dy
             layernorm_bwd(0, w.dln, w.y[l], pf[p + 'ln2.w'], w.stat2[l], dz, dy, gr[p + 'ln2.w'], gr[p + 'ln2.b'],
                           gr[p + 'out.b'], dyl if p_blk > 0 else None, p_blk, s_out)
             # ---- attention branch: y = x + drop(Wo attn(Wqkv ln1(x)) + bo); dyl = mask * dy / (1 - p)
-            ev_out = wgrad(d, inner, M, dyl, d, 0, w.o[l], inner, 0, EPI_ATOMIC_F32, gr[p + 'out.w'], inner, split_k=0)
+            e['out'] = wgrad(d, inner, M, dyl, d, 0, w.o[l], inner, 0, EPI_ATOMIC_F32, gr[p + 'out.w'], inner, split_k=0)
             self._gemm(M, inner, d, dyl, d, 1, wt[p + 'out.w'], inner, 0, EPI_STORE, w.d_o, inner)
-            before_overwrite(ev_qkv)   # dqkv
+            before_overwrite(old.get('qkv'))   # dqkv of this parity
             _lib.check(lib.ecgvit_attention_bwd(w.qkv[l].data_ptr(), w.o[l].data_ptr(), w.d_o.data_ptr(),
-                                                w.lse[l].data_ptr(), w.dqkv.data_ptr(), _lib.ptr(w.attn_scratch), B, N,
+                                                w.lse[l].data_ptr(), dqkv.data_ptr(), _lib.ptr(w.attn_scratch), B, N,
                                                 H, dh, scale, p_blk, s_att, blk_seed, dt, st),
                        'attention_bwd' if w.attn_scratch is None else 'attention_bwd_flash')
-            ev_qkv = wgrad(3 * inner, d, M, w.dqkv, 3 * inner, 0, w.ln1[l], d, 0, EPI_ATOMIC_F32, gr[p + 'qkv.w'], d,
-                           split_k=0)
-            if w.ckpt:
-                layer_events[l] = (ev_ff2, ev_ff1, ev_out, ev_qkv)
-            self._gemm(M, d, 3 * inner, w.dqkv, 3 * inner, 1, wt[p + 'qkv.w'], d, 0, EPI_STORE, w.dln, d)
+            e['qkv'] = wgrad(3 * inner, d, M, dqkv, 3 * inner, 0, w.ln1[l], d, 0, EPI_ATOMIC_F32, gr[p + 'qkv.w'], d,
+                             split_k=0)
+            self._gemm(M, d, 3 * inner, dqkv, 3 * inner, 1, wt[p + 'qkv.w'], d, 0, EPI_STORE, w.dln, d)
             below_bias = gr[f'l{l - 1}.ff2.b'] if l > 0 else None
             drop_below = p_blk > 0 and l > 0
-            before_overwrite(ev_ff2)   # this layer's ff2 wgrad reads dz (p = 0) / dzm[0], which LayerNorm' now rewrites
-            layernorm_bwd(1, w.dln, w.x[l], pf[p + 'ln1.w'], w.stat1[l], dy, dz, gr[p + 'ln1.w'], gr[p + 'ln1.b'],
-                          below_bias, w.dzm[0] if drop_below else None, p_blk if drop_below else 0.0, s_ff2 - 4)
-            dzl = w.dzm[0] if drop_below else dz
+            # LayerNorm' writes the input gradient of layer l - 1 into the OTHER parity, last read by the ff2 weight
+            # gradient of layer l + 1
+            before_overwrite(evs.get(l + 1, {}).get('ff2'))
+            layernorm_bwd(1, w.dln, w.x[l], pf[p + 'ln1.w'], w.stat1[l], dy, w.dz[qn], gr[p + 'ln1.w'], gr[p + 'ln1.b'],
+                          below_bias, w.dzm[0][qn] if drop_below else None, p_blk if drop_below else 0.0, s_ff2 - 4)
             if m._after_layer_backward is not None:
                 # the gradient bucket of layer l is complete once its side-stream wgrads AND everything the main stream
                 # has issued so far (LayerNorm / bias gradients) are done.  The collective is therefore issued from the
@@ -476,8 +479,12 @@ class StepEngine:
                     side.wait_event(here)
                     with torch.cuda.stream(side):
                         m._after_layer_backward(l)
-        for ev in (ev_ff2, ev_ff1, ev_out, ev_qkv, ev_fold[0], ev_fold[1]):
-            before_overwrite(ev)  # join the side stream
+        for e in evs.values():
+            for ev in e.values():
+                before_overwrite(ev)  # join the side stream
+        for ev in ev_fold:
+            before_overwrite(ev)
+        dz = w.dz[(-1) & 1]   # gradient w.r.t. the token matrix (input of block 0)
         # ---- embedding: tok = [cls | a_patch We^T + be] + pos
         _lib.check(lib.ecgvit_embed_assemble_bwd(dz.data_ptr(), w.de.data_ptr(), gr['cls'].data_ptr(),
                                                  gr['pos'].data_ptr(), gr['embed.b'].data_ptr(), B, n, d, p_emb, 0,
