@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(256, MINB) layernorm_fwd_kernel(const TX *__re
 // kDrop: dx feeds a Linear through a dropout (to_out[1] / net[4] of the block below): additionally write
 // dxm = mask * dx / (1 - p) (that Linear's dgrad / wgrad operand) and make the column sums those of dxm (its bias grad).
 template <typename T, int NV, bool kDrop, typename TX = T>
-__global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const T *__restrict__ dy, const TX *__restrict__ x,
+__global__ void __launch_bounds__(256, 1) layernorm_bwd_kernel(const T *__restrict__ dy, const TX *__restrict__ x,
                                                                 const float *__restrict__ gamma,
                                                                 const float *__restrict__ mean_in,
                                                                 const float *__restrict__ rstd_in, const T *dres, T *dx,
@@ -366,19 +366,27 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const T *__restri
     __syncthreads();
     const uint64_t *sg2 = reinterpret_cast<const uint64_t *>(sgamma) + lane;  // + (i * 4 + k) * 32
 
-    for (int64_t row = (int64_t)blockIdx.x * warps_per_block + warp; row < M;
-         row += (int64_t)gridDim.x * warps_per_block) {
-        Packed8<T> pdy[NV], pres[NV];
-        Packed8<TX> px[NV];
+    // one CTA (8 warps) per SM with the whole register file: the NEXT row's three inputs are in flight while the current
+    // row is processed (the kernel used to sit at 16 warps / SM x one row each and stalled on every row's loads:
+    // 29 us for 100 MB in the round-2 profile)
+    const int64_t stride = (int64_t)gridDim.x * warps_per_block;
+    int64_t row = (int64_t)blockIdx.x * warps_per_block + warp;
+    Packed8<T> pdy[NV], pres[NV], ndy[NV], nres[NV];
+    Packed8<TX> px[NV], nx[NV];
+    auto fetch = [&](int64_t r_, Packed8<T> *a, Packed8<TX> *b, Packed8<T> *c_) {
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
             const int c = (i * 32 + lane) * 8;
             if (c < d) {
-                ld_packed(pdy[i], dy + row * d + c);
-                ld_packed(px[i], x + row * d + c);
-                if (dres != nullptr) ld_packed(pres[i], dres + row * d + c);
+                ld_packed(a[i], dy + r_ * d + c);
+                ld_packed(b[i], x + r_ * d + c);
+                if (dres != nullptr) ld_packed(c_[i], dres + r_ * d + c);
             }
         }
+    };
+    if (row < M) fetch(row, pdy, px, pres);
+    for (; row < M; row += stride) {
+        if (row + stride < M) fetch(row + stride, ndy, nx, nres);
         const float mean = mean_in[row], rstd = rstd_in[row];
         const uint64_t rstd2 = splat2(rstd), nmr2 = splat2(-mean * rstd);
         uint64_t s1_2 = 0ull, s2_2 = 0ull;
@@ -437,6 +445,12 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const T *__restri
                 }
             }
         }
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            pdy[i] = ndy[i];
+            px[i] = nx[i];
+            pres[i] = nres[i];
+        }
     }
     // block reduce: every warp parks its per-lane column sums in its own smem slab (plain stores), then the CTA adds
     // the slabs and writes ONE partial row per CTA; a tiny second kernel folds the partial rows into the gradients.
@@ -489,7 +503,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_finalize_kernel(const float
     }
 }
 
-constexpr int LN_BWD_MAX_BLOCKS = 2 * 160;  // >= 2 CTAs x SM count
+constexpr int LN_BWD_MAX_BLOCKS = 2 * 160;  // scratch rows; the kernel runs one CTA per SM
 
 // ---------------------------------------------------------------------------------------------------
 // dym = mask * dy / (1 - p);  dcolsum[n] += sum_m dym[m, n].  Same block shape as colsum_kernel.
@@ -737,7 +751,7 @@ int ecgvit_layernorm_fwd(const void *x, const float *gamma, const float *beta, v
 int64_t ecgvit_layernorm_bwd_scratch_floats(int d) { return (int64_t)LN_BWD_MAX_BLOCKS * 3 * d; }
 
 static int ln_bwd_blocks(int M) {
-    int grid = grid_for((int64_t)M * 32, 256, 2);
+    int grid = grid_for((int64_t)M * 32, 256, 1);
     return grid > LN_BWD_MAX_BLOCKS ? LN_BWD_MAX_BLOCKS : grid;
 }
 
