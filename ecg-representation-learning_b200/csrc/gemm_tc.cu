@@ -71,7 +71,7 @@ int gemm_clusters() {
 template <int BN, bool A_MN, bool B_MN, int MODE>
 int launch_pair(const ecgvit_gemm_args *g, int split_k, cudaStream_t stream) {
     constexpr bool kWide = MODE == ECGVIT_EPI_BIAS_RES_F32;   // fp32 residual stream: 128-byte staging rows
-    using Cfg = PairCfg<BN, B_MN, kWide>;
+    using Cfg = PairCfgFor<BN, B_MN, MODE>;
     CUtensorMap ta, tb;
     int rc;
     if (!A_MN) rc = make_tmap(&ta, g->A, g->K, g->M, g->lda, BK, BM);
@@ -86,7 +86,10 @@ int launch_pair(const ecgvit_gemm_args *g, int split_k, cudaStream_t stream) {
     if (kWide) {
         if ((rc = make_tmap(&to, g->out, g->N, g->M, g->ldo, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B, true))) return rc;
         if ((rc = make_tmap(&tx, g->aux, g->N, g->M, g->ldo, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B, true))) return rc;
-    } else if (MODE != ECGVIT_EPI_ATOMIC_F32) {
+    } else if (MODE == ECGVIT_EPI_ATOMIC_F32) {
+        // fp32 partial sums are added into the gradient buffer by TMA reduce (cp.reduce.async.bulk.tensor .add)
+        if ((rc = make_tmap(&to, g->out, g->N, g->M, g->ldo, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B, true))) return rc;
+    } else {
         if ((rc = make_tmap(&to, g->out, g->N, g->M, g->ldo, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
         if (MODE == ECGVIT_EPI_BIAS_GELU &&
             (rc = make_tmap(&to2, g->out2, g->N, g->M, g->ldo, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
@@ -188,6 +191,10 @@ int gemm_bf16_tc(const ecgvit_gemm_args *g, cudaStream_t stream) {
         return (double)waves * bn / eff;
     };
     const bool wide_ok = g->epilogue != ECGVIT_EPI_BIAS_RES_F32;   // see dispatch_pair
+    static const int forced_bn = [] { const char *e = getenv("ECGVIT_GEMM_BN"); return e != nullptr ? atoi(e) : 0; }();
+    if (forced_bn == 128) return dispatch_pair<128>(g, split_k, stream);   // experiments only
+    if (forced_bn == 192) return dispatch_pair<192>(g, split_k, stream);
+    if (forced_bn == 256 && wide_ok) return dispatch_pair<256>(g, split_k, stream);
     const double s256 = wide_ok ? score(256, 1.0) : 1e30, s192 = score(192, b_kmajor_eff(g->b_kmajor)), s128 = score(128, 0.67);
     if (g->N <= 128 || (s128 < s256 && s128 < s192)) return dispatch_pair<128>(g, split_k, stream);
     if (s192 < s256) return dispatch_pair<192>(g, split_k, stream);

@@ -14,7 +14,7 @@
 //   tmem_empty[a]  on the LEADER : 8 epilogue warps x 2 CTAs arrive (remote arrive from the peer)
 #pragma once
 
-template <int BN, bool B_MN, bool WIDE = false> struct PairCfg {
+template <int BN, bool B_MN, bool WIDE = false, int TILES = 2> struct PairCfg {
     static constexpr int B_HALF = BN / 2;                                      // B rows (N values) per CTA
     // MN-major B is staged in 64-wide chunks; at BN = 192 the second chunk is only half used (over-fetch)
     static constexpr int B_LOAD_ROWS = B_MN ? ((B_HALF + 63) / 64) * 64 : B_HALF;
@@ -27,9 +27,10 @@ template <int BN, bool B_MN, bool WIDE = false> struct PairCfg {
     static constexpr int THREADS = 128 + 32 * EPI_WARPS;
     static constexpr int UNITS_PER_WARP = 2;                                   // 32-column units per epilogue warp
     // staging: every epilogue warp owns two 32-row x 32-column tiles: 64-byte rows of bf16 (SWIZZLE_64B), or 128-byte
-    // rows of fp32 (SWIZZLE_128B) for the fp32 residual stream (WIDE)
+    // rows of fp32 (SWIZZLE_128B) for the fp32 residual stream and the split-K reduction (WIDE; the latter with one
+    // tile per warp, which leaves the weight-gradient contraction its five pipeline stages at BN = 256)
     static constexpr int EPI_TILE_BYTES = WIDE ? 32 * 128 : 32 * 64;
-    static constexpr int EPI_TILES_PER_WARP = 2;
+    static constexpr int EPI_TILES_PER_WARP = TILES;
     static constexpr int EPI_BYTES = EPI_WARPS * EPI_TILES_PER_WARP * EPI_TILE_BYTES;
     static constexpr int NUM_BARRIERS = 2 * 8 + 4 + EPI_WARPS * EPI_TILES_PER_WARP;
     static constexpr int PIPE_BUDGET = 232448 - 1024 - 1024 - EPI_BYTES;
@@ -39,6 +40,10 @@ template <int BN, bool B_MN, bool WIDE = false> struct PairCfg {
     static_assert(NUM_BARRIERS * 8 + 16 <= 1024, "barrier block");
     static_assert(BN % 64 == 0, "tile width");
 };
+// the configuration of one (tile width, B layout, epilogue) instantiation
+template <int BN, bool B_MN, int MODE>
+using PairCfgFor = PairCfg<BN, B_MN, MODE == ECGVIT_EPI_BIAS_RES_F32 || MODE == ECGVIT_EPI_ATOMIC_F32,
+                           MODE == ECGVIT_EPI_ATOMIC_F32 ? 1 : 2>;
 
 // byte offset of 16-byte chunk j (0..3) of row `lane` inside a 32 x 64-byte SWIZZLE_64B tile
 __device__ __forceinline__ uint32_t sw64_offset(int lane, int j) {
@@ -136,12 +141,12 @@ __device__ __forceinline__ void epilogue_half16_f32(const EpiParams &ep, int64_t
 
 template <int BN, bool A_MN, bool B_MN, int MODE>
 __global__ void __cluster_dims__(2, 1, 1)
-__launch_bounds__(PairCfg<BN, B_MN, MODE == ECGVIT_EPI_BIAS_RES_F32>::THREADS, 1)
+__launch_bounds__(PairCfgFor<BN, B_MN, MODE>::THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                 const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_out2,
                 const __grid_constant__ CUtensorMap tmap_aux, int M, int N, int K, int split_k, EpiParams ep) {
-    constexpr bool kWide = MODE == ECGVIT_EPI_BIAS_RES_F32;
-    using Cfg = PairCfg<BN, B_MN, kWide>;
+    constexpr bool kWide = MODE == ECGVIT_EPI_BIAS_RES_F32;   // (the split-K epilogue has its own fp32 path below)
+    using Cfg = PairCfgFor<BN, B_MN, MODE>;
     constexpr bool kHasAux = (MODE == ECGVIT_EPI_BIAS_RES || MODE == ECGVIT_EPI_DGELU || kWide);
     constexpr int STAGES = Cfg::STAGES;
     constexpr int BM2 = 2 * BM;  // rows of the pair tile
@@ -167,7 +172,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&tmap_a);
         ptx::prefetch_tensormap(&tmap_b);
-        if (MODE != ECGVIT_EPI_ATOMIC_F32) ptx::prefetch_tensormap(&tmap_out);
+        ptx::prefetch_tensormap(&tmap_out);
         if (MODE == ECGVIT_EPI_BIAS_GELU) ptx::prefetch_tensormap(&tmap_out2);
         if (kHasAux) ptx::prefetch_tensormap(&tmap_aux);
     }
@@ -327,22 +332,33 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + group * 64;
             const int64_t row = static_cast<int64_t>(row_base) + lane;
             if (MODE == ECGVIT_EPI_ATOMIC_F32) {
+                // split-K partial sums: fp32 tile -> swizzled staging -> one TMA reduce-add per 32 x 32 unit (the L2
+                // adds whole lines; per-thread red.v4 made this epilogue as long as a 25-k-block mainloop)
+                const int n_units = (col_warp >= N) ? 0 : ((col_warp + 32 < N) ? UNITS : 1);
+                uint32_t ra[16], rb[16];
+                if (n_units > 0) ptx::tmem_ld_32x16(taddr0, ra);
 #pragma unroll 1
-                for (int i = 0; i < 2 * UNITS; ++i) {
-                    uint32_t r[16];
-                    ptx::tmem_ld_32x16(taddr0 + 16 * i, r);
-                    ptx::tmem_ld_wait();
-                    if (row < M) {
+                for (int i = 0; i < n_units; ++i) {
+                    ptx::tmem_ld_wait_bind(ra);
+                    ptx::tmem_ld_32x16(taddr0 + 32 * i + 16, rb);
+                    if (lane == 0) ptx::tma_store_wait_read<0>();   // the previous unit's reduce has read the tile
+                    __syncwarp();
+                    uint8_t *trow = tiles + static_cast<uint32_t>(lane) * 128u;
 #pragma unroll
-                        for (int j = 0; j < 2; ++j) {
-                            const int col = col_warp + 16 * i + j * 8;
-                            if (col < N) {
-                                float v[8];
+                    for (int j = 0; j < 4; ++j)
+                        *reinterpret_cast<uint4 *>(trow + (static_cast<uint32_t>(j ^ (lane & 7)) << 4)) =
+                            make_uint4(ra[4 * j], ra[4 * j + 1], ra[4 * j + 2], ra[4 * j + 3]);
+                    ptx::tmem_ld_wait_bind(rb);
+                    if (i + 1 < n_units) ptx::tmem_ld_32x16(taddr0 + 32 * (i + 1), ra);
 #pragma unroll
-                                for (int k = 0; k < 8; ++k) v[k] = __uint_as_float(r[j * 8 + k]);
-                                epilogue_store<MODE, bf16, 8, false>(ep, row, col, v);
-                            }
-                        }
+                    for (int j = 0; j < 4; ++j)
+                        *reinterpret_cast<uint4 *>(trow + (static_cast<uint32_t>((4 + j) ^ (lane & 7)) << 4)) =
+                            make_uint4(rb[4 * j], rb[4 * j + 1], rb[4 * j + 2], rb[4 * j + 3]);
+                    ptx::fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        ptx::tma_reduce_add_2d(&tmap_out, tiles, col_warp + 32 * i, row_base);
+                        ptx::tma_store_commit();
                     }
                 }
             } else {
@@ -393,7 +409,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive_cluster(&tmem_empty_bar[acc], 0);  // the leader's barrier
         }
-        if (MODE != ECGVIT_EPI_ATOMIC_F32 && lane == 0) ptx::tma_store_wait_all<0>();
+        if (lane == 0) ptx::tma_store_wait_all<0>();
     }
 
     ptx::tcgen05_fence_before();

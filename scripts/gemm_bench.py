@@ -21,6 +21,7 @@ SHAPES = [
     ('out_dgrad', (M, d, d), 1, 0, L.EPI_STORE), ('qkv_dgrad', (M, d, 3 * d), 1, 0, L.EPI_STORE),
     ('ff2_wgrad', (d, mlp, M), 0, 0, L.EPI_ATOMIC_F32), ('ff1_wgrad', (mlp, d, M), 0, 0, L.EPI_ATOMIC_F32),
     ('out_wgrad', (d, d, M), 0, 0, L.EPI_ATOMIC_F32), ('qkv_wgrad', (3 * d, d, M), 0, 0, L.EPI_ATOMIC_F32),
+    ('out_fwd_store', (M, d, d), 1, 1, L.EPI_STORE),
     ('embed_fwd', (Bn, d, PC), 1, 1, L.EPI_STORE), ('embed_wgrad', (d, PC, Bn), 0, 0, L.EPI_ATOMIC_F32),
 ]
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 20
