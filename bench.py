@@ -79,12 +79,14 @@ def cpu_model_string():
 
 def gemm_traffic():
     """average DRAM bytes per tcgen05-GEMM launch from the committed ncu capture of one step (profiles/)"""
-    path = os.path.join(ROOT, 'profiles', 'r01_step_final.json')
-    try:
-        fam = json.load(open(path))['gemm_family']
-        return fam['dram_bytes_per_launch'], 'profiles/r01_step_final.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, avg over the GEMM launches of one step)'
-    except Exception:
-        return None, 'no ncu capture committed'
+    for name in ('r02_step_launches.json', 'r01_step_final.json'):
+        try:
+            fam = json.load(open(os.path.join(ROOT, 'profiles', name)))['gemm_family']
+            return fam['dram_bytes_per_launch'], ('profiles/%s (ncu dram__bytes_read.sum + dram__bytes_write.sum, avg over '
+                                                  'the GEMM launches of one step)' % name)
+        except Exception:
+            continue
+    return None, 'no ncu capture committed'
 
 
 def measured_peaks():

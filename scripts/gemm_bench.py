@@ -51,12 +51,21 @@ for name, (m, n, k), ak, bk, epi in SHAPES:
         launch(i)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(reps):
-        launch(i)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / reps
+
+    def timed(fn):
+        """median over 5 batches of `reps` back-to-back launches (one batch now and then catches a ~45 ms stall of the
+        box that has nothing to do with the kernel)"""
+        t = []
+        for _ in range(5):
+            e0.record()
+            for i in range(reps):
+                fn(i)
+            e1.record()
+            torch.cuda.synchronize()
+            t.append(e0.elapsed_time(e1) / reps)
+        return sorted(t)[2]
+
+    ms = timed(launch)
     # cuBLAS on the same contraction, for reference only
     Am = A[0] if ak else A[0].t()
     Bm = B[0].t() if bk else B[0]
@@ -65,12 +74,7 @@ for name, (m, n, k), ak, bk, epi in SHAPES:
         for _ in range(3):
             torch.matmul(Am, Bm)
         torch.cuda.synchronize()
-        e0.record()
-        for _ in range(reps):
-            torch.matmul(Am, Bm)
-        e1.record()
-        torch.cuda.synchronize()
-        ms_cublas = e0.elapsed_time(e1) / reps
+        ms_cublas = timed(lambda i: torch.matmul(Am, Bm))
     tf = 2.0 * m * n * k / (ms * 1e-3) / 1e12
     rows.append(dict(name=name, M=m, N=n, K=k, ms=round(ms, 4), tflops=round(tf, 1),
                      cublas_ms=round(ms_cublas, 4), cublas_tflops=round(2.0 * m * n * k / (ms_cublas * 1e-3) / 1e12, 1)))

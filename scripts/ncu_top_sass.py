@@ -5,7 +5,11 @@ import sys
 
 rows = list(csv.reader(open(sys.argv[1]) if len(sys.argv) > 1 else sys.stdin))
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-hdr_i = next(i for i, r in enumerate(rows) if r and r[0] == 'Address')
+# several launches in one report print one table each: pick the one asked for (third argument, default the first)
+hdr_all = [i for i, r in enumerate(rows) if r and r[0] == 'Address']
+which = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+hdr_i = hdr_all[which]
+rows = rows[:hdr_all[which + 1] - 1] if which + 1 < len(hdr_all) else rows
 hdr = rows[hdr_i]
 col = {h: i for i, h in enumerate(hdr)}
 stalls = [h for h in hdr if h.startswith('stall_') and 'Not Issued' not in h]
