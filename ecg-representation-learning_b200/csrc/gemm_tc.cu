@@ -150,6 +150,7 @@ int gemm_bf16_tc(const ecgvit_gemm_args *g, cudaStream_t stream) {
                    "gemm(bf16): operand pointers must be 16-byte aligned");
     ECGVIT_REQUIRE(g->ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(g->out) & 15) == 0,
                    "gemm(bf16): output must be 16-byte aligned with ldo %% 8 == 0");
+    ECGVIT_REQUIRE((reinterpret_cast<uintptr_t>(g->bias) & 15) == 0, "gemm(bf16): bias must be 16-byte aligned");
     ECGVIT_REQUIRE(g->epilogue != ECGVIT_EPI_BIAS_RES_F32 || (g->aux != nullptr && g->a_kmajor && g->b_kmajor),
                    "gemm(bf16): the fp32-residual epilogue needs aux and K-major operands");
     const int sms = sm_count();

@@ -57,7 +57,7 @@ __device__ __forceinline__ uint32_t sw64_offset(int lane, int j) {
 template <int MODE>
 __device__ __forceinline__ void epilogue_half16(const EpiParams &ep, int64_t row, int col_base, int jbase,
                                                 const uint32_t r[16], uint8_t *tile0, uint8_t *tile1, int lane,
-                                                float bias_lane) {
+                                                int n_cols) {
     const bool drop = ep.drop.threshold != 0;  // kernel-uniform
     const uint32_t seed = drop ? __ldg(ep.drop.seed) : 0u;
 #pragma unroll
@@ -67,11 +67,13 @@ __device__ __forceinline__ void epilogue_half16(const EpiParams &ep, int64_t row
         float v[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[8 * jj + i]);
-        if (MODE != ECGVIT_EPI_DGELU && ep.bias != nullptr) {
-            // lane c of the warp holds the bias of column c of this 32-column unit (fetched one tile ahead, so no
-            // global-load latency sits between the TMEM load and the math); 0 beyond N
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] += __shfl_sync(0xffffffffu, bias_lane, 8 * j + i);
+        if (MODE != ECGVIT_EPI_DGELU && ep.bias != nullptr && col < n_cols) {
+            // every lane reads the same 32 bytes (one L1 wavefront per load, the 3 K floats of a bias stay L1 resident):
+            // two broadcast loads instead of eight shuffles per 8 columns
+            const float4 b0 = __ldg(reinterpret_cast<const float4 *>(ep.bias + col));
+            const float4 b1 = __ldg(reinterpret_cast<const float4 *>(ep.bias + col + 4));
+            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+            v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
         }
         const uint32_t soff = sw64_offset(lane, j);
         const uint32_t eidx = static_cast<uint32_t>(row * ep.ldo + col);  // element index of v[0] (even)
@@ -116,7 +118,7 @@ __device__ __forceinline__ void epilogue_half16(const EpiParams &ep, int64_t row
 // fp32 residual stream (ECGVIT_EPI_BIAS_RES_F32): out = drop(acc + bias) + aux with aux / out fp32.  The warp's staging
 // tile is 32 rows x 128 bytes (SWIZZLE_128B) and already holds the residual; 16 columns = four 16-byte pieces per call.
 __device__ __forceinline__ void epilogue_half16_f32(const EpiParams &ep, int64_t row, int col_base, int half,
-                                                    const uint32_t r[16], uint8_t *tile, int lane, float bias_lane) {
+                                                    const uint32_t r[16], uint8_t *tile, int lane, int n_cols) {
     const bool drop = ep.drop.threshold != 0;  // kernel-uniform
     const uint32_t seed = drop ? __ldg(ep.drop.seed) : 0u;
 #pragma unroll
@@ -126,9 +128,9 @@ __device__ __forceinline__ void epilogue_half16_f32(const EpiParams &ep, int64_t
         float v[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[4 * jj + i]);
-        if (ep.bias != nullptr) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) v[i] += __shfl_sync(0xffffffffu, bias_lane, 4 * jc + i);
+        if (ep.bias != nullptr && col < n_cols) {
+            const float4 b = __ldg(reinterpret_cast<const float4 *>(ep.bias + col));
+            v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
         }
         if (drop) dropout_apply<4>(ep.drop, seed, static_cast<uint32_t>(row * ep.ldo + col), v);
         float4 *p = reinterpret_cast<float4 *>(tile + static_cast<uint32_t>(lane) * 128u +
@@ -287,22 +289,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         constexpr int UNITS = Cfg::UNITS_PER_WARP;
         uint8_t *tiles = epi_smem + (warp - 4) * Cfg::EPI_TILES_PER_WARP * Cfg::EPI_TILE_BYTES;
         uint64_t *my_aux_bar = aux_bar + (warp - 4) * Cfg::EPI_TILES_PER_WARP;
-        // bias of the warp's two 32-column units, one column per lane, loaded ONE TILE AHEAD
-        const bool has_bias = MODE != ECGVIT_EPI_DGELU && MODE != ECGVIT_EPI_ATOMIC_F32 && ep.bias != nullptr;
-        float next_bias0 = 0.f, next_bias1 = 0.f;
-        auto fetch_bias = [&](int unit) {
-            const int c = (unit % tiles_n) * BN + group * 64 + lane;
-            next_bias0 = (c < N) ? __ldg(ep.bias + c) : 0.f;
-            next_bias1 = (c + 32 < N) ? __ldg(ep.bias + c + 32) : 0.f;
-        };
-        if (has_bias && cluster_id < num_units) fetch_bias(cluster_id);
         // phase of each aux barrier: it only advances on tiles where the unit lies inside the matrix (a partial last
         // column tile skips the load), so it is tracked per barrier, not derived from the tile count
         uint32_t aux_phase = 0;
         int it = 0;
         for (int u = cluster_id; u < num_units; u += num_clusters, ++it) {
-            const float bias0 = next_bias0, bias1 = next_bias1;
-            if (has_bias && u + num_clusters < num_units) fetch_bias(u + num_clusters);
             const int tile_n = u % tiles_n;
             const int tile_m = (u / tiles_n) % tiles_m;
             const int acc = it & 1;
@@ -371,7 +362,6 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 #pragma unroll 1
                 for (int i = 0; i < n_units; ++i) {
                     const int col_base = col_warp + 32 * i;
-                    const float bias_lane = (i == 0) ? bias0 : bias1;
                     uint8_t *t0, *t1 = nullptr;
                     if (MODE == ECGVIT_EPI_BIAS_GELU) {
                         // one (u, h) tile pair per warp: unit 1 reuses it once unit 0's stores have read it
@@ -390,12 +380,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                         if (lane == 0) ptx::tma_store_wait_read<0>();
                         __syncwarp();
                     }
-                    if (kWide) epilogue_half16_f32(ep, row, col_base, 0, ra, t0, lane, bias_lane);
-                    else epilogue_half16<MODE>(ep, row, col_base, 0, ra, t0, t1, lane, bias_lane);
+                    if (kWide) epilogue_half16_f32(ep, row, col_base, 0, ra, t0, lane, N);
+                    else epilogue_half16<MODE>(ep, row, col_base, 0, ra, t0, t1, lane, N);
                     ptx::tmem_ld_wait_bind(rb);
                     if (i + 1 < n_units) ptx::tmem_ld_32x16(taddr0 + 32 * (i + 1), ra);
-                    if (kWide) epilogue_half16_f32(ep, row, col_base, 1, rb, t0, lane, bias_lane);
-                    else epilogue_half16<MODE>(ep, row, col_base, 2, rb, t0, t1, lane, bias_lane);
+                    if (kWide) epilogue_half16_f32(ep, row, col_base, 1, rb, t0, lane, N);
+                    else epilogue_half16<MODE>(ep, row, col_base, 2, rb, t0, t1, lane, N);
                     ptx::fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
                     __syncwarp();
                     if (lane == 0) {
