@@ -384,10 +384,20 @@ __global__ void __launch_bounds__(256, 1) layernorm_bwd_kernel(const T *__restri
             }
         }
     };
-    if (row < M) fetch(row, pdy, px, pres);
+    // the row statistics come from L2 / HBM as well: fetched one row ahead like the row itself
+    float mean_n = 0.f, rstd_n = 0.f;
+    if (row < M) {
+        fetch(row, pdy, px, pres);
+        mean_n = __ldg(mean_in + row);
+        rstd_n = __ldg(rstd_in + row);
+    }
     for (; row < M; row += stride) {
-        if (row + stride < M) fetch(row + stride, ndy, nx, nres);
-        const float mean = mean_in[row], rstd = rstd_in[row];
+        const float mean = mean_n, rstd = rstd_n;
+        if (row + stride < M) {
+            fetch(row + stride, ndy, nx, nres);
+            mean_n = __ldg(mean_in + row + stride);
+            rstd_n = __ldg(rstd_in + row + stride);
+        }
         const uint64_t rstd2 = splat2(rstd), nmr2 = splat2(-mean * rstd);
         uint64_t s1_2 = 0ull, s2_2 = 0ull;
 #pragma unroll
