@@ -3,75 +3,117 @@
 // (/root/reference/ecg_transformer/models/ecg_vit.py:118,148).  B x n_class is tiny (256 x 71): FFMA + shuffles.
 #include "common.cuh"
 
+#include <algorithm>
+
 namespace ecgvit {
 
 namespace {
 
 constexpr int HEAD_MAXV = 4;  // d <= 1024
 
-// one CTA (4 warps) per sample: every warp LayerNorms the CLS row redundantly (768 elements, cheaper than a barrier +
-// smem round trip), then the warps split the n_class dot products
+constexpr int HEAD_SPB = 8;   // samples per CTA (one warp each)
+
+// One CTA = HEAD_SPB samples, one warp each: the warp LayerNorms its sample's CLS row and parks it in shared memory; then
+// the warps split the classes, and every weight row a warp fetches is used for all HEAD_SPB samples (one CTA per sample
+// made 256 CTAs pull the same 218 KB of W through L2 at the same time: 56 MB of L2 traffic, 23 us for 28 MFLOP).
+// All loads are branch-free (clamped address + select): an `if (c < d) { load; use }` per vector becomes its own basic
+// block and ptxas then waits for every 32-byte piece in turn (the round-1 kernel: 54 serial L2 round trips per warp).
 template <typename T>
-__global__ void __launch_bounds__(128) head_fwd_kernel(const T *__restrict__ tok, const float *__restrict__ gamma,
-                                                        const float *__restrict__ beta, const float *__restrict__ w,
-                                                        const float *__restrict__ bias, float *__restrict__ xn,
-                                                        float *__restrict__ mean_out, float *__restrict__ rstd_out,
-                                                        float *__restrict__ logits, int B, int N, int d, int n_class,
-                                                        float eps) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-    const int b = blockIdx.x;
-    if (b >= B) return;
-    const T *xr = tok + (int64_t)b * N * d;
-    float v[HEAD_MAXV][8];
-    float s = 0.f;
+__global__ void __launch_bounds__(32 * HEAD_SPB) head_fwd_kernel(const T *__restrict__ tok, const float *__restrict__ gamma,
+                                                                  const float *__restrict__ beta,
+                                                                  const float *__restrict__ w,
+                                                                  const float *__restrict__ bias, float *__restrict__ xn,
+                                                                  float *__restrict__ mean_out,
+                                                                  float *__restrict__ rstd_out,
+                                                                  float *__restrict__ logits, int B, int N, int d,
+                                                                  int n_class, float eps) {
+    extern __shared__ float xs[];   // [HEAD_SPB][d] normalised CLS rows (zeros for samples beyond B)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.x * HEAD_SPB + warp;
+    int cc[HEAD_MAXV];
+    bool ok[HEAD_MAXV];
 #pragma unroll
     for (int i = 0; i < HEAD_MAXV; ++i) {
         const int c = (i * 32 + lane) * 8;
-        if (c < d) {
-            load8(xr + c, v[i]);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) s += v[i][k];
-        }
+        ok[i] = c < d;
+        cc[i] = ok[i] ? c : 0;
     }
-    const float mean = warp_sum(s) / (float)d;
-    float sq = 0.f;
+    auto load_w = [&](int cls, float (*dst)[8]) {
+        const float *wr = w + (int64_t)min(cls, n_class - 1) * d;
 #pragma unroll
-    for (int i = 0; i < HEAD_MAXV; ++i) {
-        const int c = (i * 32 + lane) * 8;
-        if (c < d) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) { const float t = v[i][k] - mean; sq += t * t; }
-        }
-    }
-    const float rstd = rsqrtf(warp_sum(sq) / (float)d + eps);
-#pragma unroll
-    for (int i = 0; i < HEAD_MAXV; ++i) {
-        const int c = (i * 32 + lane) * 8;
-        if (c < d) {
-            float g[8], bt[8];
-            load8(gamma + c, g);
-            load8(beta + c, bt);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) v[i][k] = fmaf((v[i][k] - mean) * rstd, g[k], bt[k]);
-            if (warp == 0) store8(xn + (int64_t)b * d + c, v[i]);
-        }
-    }
-    if (warp == 0 && lane == 0) { mean_out[b] = mean; rstd_out[b] = rstd; }
-    for (int cls = warp; cls < n_class; cls += nwarp) {
-        const float *wr = w + (int64_t)cls * d;
-        float acc = 0.f;
+        for (int i = 0; i < HEAD_MAXV; ++i) load8(wr + cc[i], dst[i]);
+    };
+    float wv[HEAD_MAXV][8], wn[HEAD_MAXV][8];
+    // gridDim.y CTAs share a group of samples and split the classes (each normalises the rows for itself: latency, not
+    // throughput); CTA y = 0 writes xn / mean / rstd
+    const int cls_first = warp + HEAD_SPB * blockIdx.y, cls_step = HEAD_SPB * gridDim.y;
+    const bool writer = blockIdx.y == 0;
+    load_w(cls_first, wv);   // the first weight row travels while the row is normalised
+    {
+        const T *xr = tok + (int64_t)min(b, B - 1) * N * d;
+        float v[HEAD_MAXV][8], g[HEAD_MAXV][8], bt[HEAD_MAXV][8];
 #pragma unroll
         for (int i = 0; i < HEAD_MAXV; ++i) {
-            const int c = (i * 32 + lane) * 8;
-            if (c < d) {
-                float wv[8];
-                load8(wr + c, wv);
+            load8(xr + cc[i], v[i]);
+            load8(gamma + cc[i], g[i]);
+            load8(beta + cc[i], bt[i]);
+        }
+        float s = 0.f;
 #pragma unroll
-                for (int k = 0; k < 8; ++k) acc = fmaf(v[i][k], wv[k], acc);
+        for (int i = 0; i < HEAD_MAXV; ++i)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s += ok[i] ? v[i][k] : 0.f;
+        const float mean = warp_sum(s) / (float)d;
+        float sq = 0.f;
+#pragma unroll
+        for (int i = 0; i < HEAD_MAXV; ++i)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { const float t = ok[i] ? v[i][k] - mean : 0.f; sq += t * t; }
+        const float rstd = rsqrtf(warp_sum(sq) / (float)d + eps);
+#pragma unroll
+        for (int i = 0; i < HEAD_MAXV; ++i) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[i][k] = b < B ? fmaf((v[i][k] - mean) * rstd, g[i][k], bt[i][k]) : 0.f;
+            if (ok[i]) {
+                if (b < B && writer) store8(xn + (int64_t)b * d + cc[i], v[i]);
+                store8(xs + warp * d + cc[i], v[i]);
             }
         }
-        acc = warp_sum(acc);
-        if (lane == 0) logits[(int64_t)b * n_class + cls] = acc + bias[cls];
+        if (lane == 0 && b < B && writer) { mean_out[b] = mean; rstd_out[b] = rstd; }
+    }
+    __syncthreads();
+    const int n_here = min(HEAD_SPB, B - blockIdx.x * HEAD_SPB);
+    for (int cls = cls_first; cls < n_class; cls += cls_step) {
+        load_w(cls + cls_step, wn);   // next row in flight (clamped past the end)
+        const float bs = bias[cls];
+        // the dot products of all HEAD_SPB samples with this row, then their shuffle trees interleaved.  Per sample the
+        // order is the one of a lone warp: per-lane FMAs over the vectors, then the butterfly.
+        float acc[HEAD_SPB];
+#pragma unroll
+        for (int sidx = 0; sidx < HEAD_SPB; ++sidx) {
+            acc[sidx] = 0.f;
+#pragma unroll
+            for (int i = 0; i < HEAD_MAXV; ++i) {
+                float xv[8];
+                load8(xs + sidx * d + cc[i], xv);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[sidx] = fmaf(xv[k], ok[i] ? wv[i][k] : 0.f, acc[sidx]);
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+            for (int sidx = 0; sidx < HEAD_SPB; ++sidx) acc[sidx] += __shfl_xor_sync(0xffffffffu, acc[sidx], off);
+        if (lane < n_here) {
+            float mine = acc[0];
+#pragma unroll
+            for (int sidx = 1; sidx < HEAD_SPB; ++sidx) mine = lane == sidx ? acc[sidx] : mine;
+            logits[(int64_t)(blockIdx.x * HEAD_SPB + lane) * n_class + cls] = mine + bs;
+        }
+#pragma unroll
+        for (int i = 0; i < HEAD_MAXV; ++i)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) wv[i][k] = wn[i][k];
     }
 }
 
@@ -94,10 +136,25 @@ __global__ void __launch_bounds__(1024) bce_loss_kernel(const float *__restrict_
                                                          int n_weight) {
     __shared__ float red[32];
     float s = 0.f;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const float l = label_weight(loss_weight, n_weight, labels[i]) * bce_with_logits(logits[i], labels[i]);
-        if (reduction == ECGVIT_REDUCTION_NONE) loss[i] = l;
-        s += l;
+    // four independent (logit, label) loads in flight per thread: a single CTA walking 18 k elements one dependent load
+    // pair at a time was pure latency (10 us)
+    for (int i0 = threadIdx.x; i0 < n; i0 += 4 * blockDim.x) {
+        float z[4], y[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int i = i0 + j * blockDim.x;
+            z[j] = i < n ? logits[i] : 0.f;
+            y[j] = i < n ? labels[i] : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int i = i0 + j * blockDim.x;
+            if (i < n) {
+                const float l = label_weight(loss_weight, n_weight, y[j]) * bce_with_logits(z[j], y[j]);
+                if (reduction == ECGVIT_REDUCTION_NONE) loss[i] = l;
+                s += l;
+            }
+        }
     }
     if (reduction == ECGVIT_REDUCTION_NONE) return;
     s = warp_sum(s);
@@ -110,63 +167,95 @@ __global__ void __launch_bounds__(1024) bce_loss_kernel(const float *__restrict_
     }
 }
 
-// backward A: per sample, dlogits -> dxn = dlogits W -> LayerNorm' -> CLS row of dtok
+// backward A: per sample, dlogits -> dxn = dlogits W -> LayerNorm' -> CLS row of dtok.
+// One CTA = HEAD_SPB samples (one warp each); the weight rows go through shared memory, so W is read once per CTA instead
+// of once per sample.
+__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(dst))),
+                 "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 template <typename T, typename TX = T>
-__global__ void __launch_bounds__(128) head_bwd_rows_kernel(const TX *__restrict__ tok, const float *__restrict__ gamma,
-                                                             const float *__restrict__ w,
-                                                             const float *__restrict__ labels,
-                                                             const float *__restrict__ mean_in,
-                                                             const float *__restrict__ rstd_in,
-                                                             const float *__restrict__ logits, T *__restrict__ dtok,
-                                                             float *__restrict__ dxn_out, float *__restrict__ dlog_out,
-                                                             int B, int N, int d, int n_class, float coef_host,
-                                                             const float *__restrict__ coef_dev,
-                                                             const float *__restrict__ loss_weight, int n_weight) {
-    const int lane = threadIdx.x & 31;
-    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (b >= B) return;
+__global__ void __launch_bounds__(32 * HEAD_SPB) head_bwd_rows_kernel(
+    const TX *__restrict__ tok, const float *__restrict__ gamma, const float *__restrict__ w,
+    const float *__restrict__ labels, const float *__restrict__ mean_in, const float *__restrict__ rstd_in,
+    const float *__restrict__ logits, T *__restrict__ dtok, float *__restrict__ dxn_out, float *__restrict__ dlog_out,
+    int B, int N, int d, int n_class, float coef_host, const float *__restrict__ coef_dev,
+    const float *__restrict__ loss_weight, int n_weight, int ch_classes) {
+    extern __shared__ float wsm[];   // [ch_classes][d]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.x * HEAD_SPB + warp;
+    const bool live = b < B;
     // upstream gradient of the loss: a host scalar and / or a DEVICE scalar (autograd's grad_output: no host sync)
     const float coef = coef_dev != nullptr ? coef_host * __ldg(coef_dev) : coef_host;
+    // dlogits of the sample: lane l holds classes l, l + 32, l + 64 (n_class <= 96 per pass; more classes loop)
     float dxn[HEAD_MAXV][8];
 #pragma unroll
     for (int i = 0; i < HEAD_MAXV; ++i)
 #pragma unroll
         for (int k = 0; k < 8; ++k) dxn[i][k] = 0.f;
-    for (int cls = 0; cls < n_class; ++cls) {
-        const float z = logits[(int64_t)b * n_class + cls], y = labels[(int64_t)b * n_class + cls];
-        const float dl = coef * label_weight(loss_weight, n_weight, y) * (1.0f / (1.0f + expf(-z)) - y);
-        if (lane == 0) dlog_out[(int64_t)b * n_class + cls] = dl;
-        const float *wr = w + (int64_t)cls * d;
+    int cc[HEAD_MAXV];
 #pragma unroll
-        for (int i = 0; i < HEAD_MAXV; ++i) {
-            const int c = (i * 32 + lane) * 8;
-            if (c < d) {
+    for (int i = 0; i < HEAD_MAXV; ++i) {
+        const int c = (i * 32 + lane) * 8;
+        cc[i] = c < d ? c : 0;
+    }
+    // the sample's CLS row, gamma and row statistics are only needed after the class loop: fetched now (branch-free)
+    const int bb = min(b, B - 1);
+    float xv[HEAD_MAXV][8], gm[HEAD_MAXV][8];
+#pragma unroll
+    for (int i = 0; i < HEAD_MAXV; ++i) {
+        load8(tok + (int64_t)bb * N * d + cc[i], xv[i]);
+        load8(gamma + cc[i], gm[i]);
+    }
+    const float mean = mean_in[bb], rstd = rstd_in[bb];
+    // W goes through shared memory in chunks of `ch_classes` rows (all 71 rows of the base model at once: 213 KB), copied
+    // with cp.async by the whole CTA so that every 16-byte piece is in flight at the same time
+    float dl_lane = 0.f;
+    for (int c0 = 0; c0 < n_class; c0 += ch_classes) {
+        const int n_here = min(ch_classes, n_class - c0);
+        if (c0 > 0) __syncthreads();   // everyone is done with the previous chunk
+        {
+            const float4 *src = reinterpret_cast<const float4 *>(w + (int64_t)c0 * d);
+            float4 *dst = reinterpret_cast<float4 *>(wsm);
+            for (int idx = threadIdx.x; idx < n_here * d / 4; idx += blockDim.x) cp_async16(dst + idx, src + idx);
+            cp_async_wait_all();
+        }
+        __syncthreads();
+        for (int j = 0; j < n_here; ++j) {
+            const int cls = c0 + j;
+            if ((cls & 31) == 0) {   // a new group of 32 classes: every lane computes one dlogit
+                const int mine = cls + lane;
+                dl_lane = 0.f;
+                if (live && mine < n_class) {
+                    const float z = logits[(int64_t)b * n_class + mine], y = labels[(int64_t)b * n_class + mine];
+                    dl_lane = coef * label_weight(loss_weight, n_weight, y) * (1.0f / (1.0f + expf(-z)) - y);
+                    dlog_out[(int64_t)b * n_class + mine] = dl_lane;
+                }
+            }
+            const float dl = __shfl_sync(0xffffffffu, dl_lane, cls & 31);
+#pragma unroll
+            for (int i = 0; i < HEAD_MAXV; ++i) {   // lanes beyond d accumulate vector 0 again: never read
                 float wv[8];
-                load8(wr + c, wv);
+                load8(wsm + j * d + cc[i], wv);
 #pragma unroll
                 for (int k = 0; k < 8; ++k) dxn[i][k] = fmaf(dl, wv[k], dxn[i][k]);
             }
         }
     }
-    const float mean = mean_in[b], rstd = rstd_in[b];
-    const TX *xr = tok + (int64_t)b * N * d;
+    if (!live) return;
     float g[HEAD_MAXV][8], xh[HEAD_MAXV][8];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < HEAD_MAXV; ++i) {
-        const int c = (i * 32 + lane) * 8;
-        if (c < d) {
-            float xv[8], gm[8];
-            load8(xr + c, xv);
-            load8(gamma + c, gm);
-            store8(dxn_out + (int64_t)b * d + c, dxn[i]);
+        const bool ok = (i * 32 + lane) * 8 < d;
+        if (ok) store8(dxn_out + (int64_t)b * d + cc[i], dxn[i]);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                xh[i][k] = (xv[k] - mean) * rstd;
-                g[i][k] = dxn[i][k] * gm[k];
-                s1 += g[i][k];
-                s2 = fmaf(g[i][k], xh[i][k], s2);
-            }
+        for (int k = 0; k < 8; ++k) {
+            xh[i][k] = (xv[i][k] - mean) * rstd;
+            g[i][k] = ok ? dxn[i][k] * gm[i][k] : 0.f;
+            s1 += g[i][k];
+            s2 = fmaf(g[i][k], xh[i][k], s2);
         }
     }
     s1 = warp_sum(s1) / (float)d;
@@ -174,12 +263,11 @@ __global__ void __launch_bounds__(128) head_bwd_rows_kernel(const TX *__restrict
     T *dr = dtok + (int64_t)b * N * d;
 #pragma unroll
     for (int i = 0; i < HEAD_MAXV; ++i) {
-        const int c = (i * 32 + lane) * 8;
-        if (c < d) {
+        if ((i * 32 + lane) * 8 < d) {
             float o[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) o[k] = rstd * (g[i][k] - s1 - xh[i][k] * s2);
-            store8(dr + c, o);
+            store8(dr + cc[i], o);
         }
     }
 }
@@ -198,12 +286,26 @@ __global__ void __launch_bounds__(256) head_bwd_cols_kernel(const TX *__restrict
     const int k = blockIdx.x * 32 + tx;
     float sg = 0.f, sb = 0.f, sc = 0.f;
     if (k < d) {
-        for (int b = ty; b < B; b += 8) {
-            const float xh = (to_f32(tok[(int64_t)b * N * d + k]) - mean_in[b]) * rstd_in[b];
-            const float dv = dxn[(int64_t)b * d + k];
-            sg = fmaf(dv, xh, sg);
-            sb += dv;
-            sc += to_f32(dtok[(int64_t)b * N * d + k]);
+        // four samples in flight per thread (their CLS rows are N * d elements apart: every load is its own HBM round trip)
+        for (int b0 = ty; b0 < B; b0 += 32) {
+            float xv[4], mv[4], rv[4], dv[4], gv[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int b = min(b0 + 8 * j, B - 1);
+                xv[j] = to_f32(tok[(int64_t)b * N * d + k]);
+                mv[j] = mean_in[b];
+                rv[j] = rstd_in[b];
+                dv[j] = dxn[(int64_t)b * d + k];
+                gv[j] = to_f32(dtok[(int64_t)b * N * d + k]);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (b0 + 8 * j < B) {
+                    sg = fmaf(dv[j], (xv[j] - mv[j]) * rv[j], sg);
+                    sb += dv[j];
+                    sc += gv[j];
+                }
+            }
         }
     }
     red[0][ty][tx] = sg; red[1][ty][tx] = sb; red[2][ty][tx] = sc;
@@ -263,11 +365,12 @@ int ecgvit_head_fwd(const void *tok, const float *gamma, const float *beta, cons
                    8 * 32 * HEAD_MAXV);
     ECGVIT_REQUIRE(labels == nullptr || loss != nullptr, "head_fwd: labels given but loss is null");
     ECGVIT_REQUIRE(loss_weight == nullptr || n_weight >= 1, "head_fwd: loss_weight table needs n_weight >= 1");
-    const int grid = B;
+    const dim3 grid((B + HEAD_SPB - 1) / HEAD_SPB, 3);           // 3 class groups per sample group
+    const size_t smem = (size_t)HEAD_SPB * d * sizeof(float);   // <= 32 KB
     if (dtype == ECGVIT_BF16)
-        head_fwd_kernel<bf16><<<grid, 128, 0, as_stream(stream)>>>((const bf16 *)tok, gamma, beta, w, b, xn, mean, rstd, logits, B, N, d, n_class, eps);
+        head_fwd_kernel<bf16><<<grid, 32 * HEAD_SPB, smem, as_stream(stream)>>>((const bf16 *)tok, gamma, beta, w, b, xn, mean, rstd, logits, B, N, d, n_class, eps);
     else if (dtype == ECGVIT_F32 || dtype == ECGVIT_BF16_RES32)   // fp32 tokens (parity mode / fp32 residual stream)
-        head_fwd_kernel<float><<<grid, 128, 0, as_stream(stream)>>>((const float *)tok, gamma, beta, w, b, xn, mean, rstd, logits, B, N, d, n_class, eps);
+        head_fwd_kernel<float><<<grid, 32 * HEAD_SPB, smem, as_stream(stream)>>>((const float *)tok, gamma, beta, w, b, xn, mean, rstd, logits, B, N, d, n_class, eps);
     else return fail(-1, "head_fwd: unknown dtype %d", dtype);
     int rc = check_launch("head_fwd");
     if (rc) return rc;
@@ -298,15 +401,26 @@ int ecgvit_head_bwd(const void *tok, const float *gamma, const float *w, const f
     if (e != cudaSuccess) return fail((int)e, "head_bwd: memset: %s", cudaGetErrorString(e));
     const float coef = grad_scale * (reduction == ECGVIT_REDUCTION_MEAN ? 1.0f / ((float)B * (float)n_class) : 1.0f);
     float *dxn = scratch, *dlog = scratch + (size_t)B * d;
-    const int grid = (B + 3) / 4;
+    const int grid = (B + HEAD_SPB - 1) / HEAD_SPB;
+    // as many weight rows per shared-memory chunk as fit in 216 KB (all of them up to d = 768 x 71 classes)
+    const int ch_classes = std::min(n_class, (216 * 1024) / (d * (int)sizeof(float)));
+    const size_t smem_rows = (size_t)ch_classes * d * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        const int max_smem = 216 * 1024;
+        cudaFuncSetAttribute(head_bwd_rows_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+        cudaFuncSetAttribute(head_bwd_rows_kernel<bf16, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+        cudaFuncSetAttribute(head_bwd_rows_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+        attr_set = true;
+    }
     if (dtype == ECGVIT_BF16) {
-        head_bwd_rows_kernel<bf16><<<grid, 128, 0, s>>>((const bf16 *)tok, gamma, w, labels, mean, rstd, logits, (bf16 *)dtok, dxn, dlog, B, N, d, n_class, coef, grad_scale_dev, loss_weight, n_weight);
+        head_bwd_rows_kernel<bf16><<<grid, 32 * HEAD_SPB, smem_rows, s>>>((const bf16 *)tok, gamma, w, labels, mean, rstd, logits, (bf16 *)dtok, dxn, dlog, B, N, d, n_class, coef, grad_scale_dev, loss_weight, n_weight, ch_classes);
         head_bwd_cols_kernel<bf16><<<(d + 31) / 32, 256, 0, s>>>((const bf16 *)tok, (const bf16 *)dtok, dxn, mean, rstd, dgamma, dbeta, dcolsum, B, N, d);
     } else if (dtype == ECGVIT_BF16_RES32) {
-        head_bwd_rows_kernel<bf16, float><<<grid, 128, 0, s>>>((const float *)tok, gamma, w, labels, mean, rstd, logits, (bf16 *)dtok, dxn, dlog, B, N, d, n_class, coef, grad_scale_dev, loss_weight, n_weight);
+        head_bwd_rows_kernel<bf16, float><<<grid, 32 * HEAD_SPB, smem_rows, s>>>((const float *)tok, gamma, w, labels, mean, rstd, logits, (bf16 *)dtok, dxn, dlog, B, N, d, n_class, coef, grad_scale_dev, loss_weight, n_weight, ch_classes);
         head_bwd_cols_kernel<bf16, float><<<(d + 31) / 32, 256, 0, s>>>((const float *)tok, (const bf16 *)dtok, dxn, mean, rstd, dgamma, dbeta, dcolsum, B, N, d);
     } else if (dtype == ECGVIT_F32) {
-        head_bwd_rows_kernel<float><<<grid, 128, 0, s>>>((const float *)tok, gamma, w, labels, mean, rstd, logits, (float *)dtok, dxn, dlog, B, N, d, n_class, coef, grad_scale_dev, loss_weight, n_weight);
+        head_bwd_rows_kernel<float><<<grid, 32 * HEAD_SPB, smem_rows, s>>>((const float *)tok, gamma, w, labels, mean, rstd, logits, (float *)dtok, dxn, dlog, B, N, d, n_class, coef, grad_scale_dev, loss_weight, n_weight, ch_classes);
         head_bwd_cols_kernel<float><<<(d + 31) / 32, 256, 0, s>>>((const float *)tok, (const float *)dtok, dxn, mean, rstd, dgamma, dbeta, dcolsum, B, N, d);
     } else return fail(-1, "head_bwd: unknown dtype %d", dtype);
     dim3 gw((d + 31) / 32, n_class);
