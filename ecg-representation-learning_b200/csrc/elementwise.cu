@@ -10,55 +10,69 @@ namespace {
 
 // ---------------------------------------------------------------------------------------------------
 // patchify: a[(b*n+w), t*C+c] = x[b, c, w*P+t]     (einops 'b c (h p1) (w p2) -> b (h w) (p1 p2 c)', h=p1=1)
-// one CTA per (b, w): coalesced reads along t per lead, transposed through smem, coalesced writes.
-template <typename T>
-__global__ void patchify_kernel(const float *__restrict__ x, T *__restrict__ a, int C, int64_t x_ld, int n_patch,
-                                int P) {
-    extern __shared__ float tile[];  // [P*C] in output order
-    const int w = blockIdx.x % n_patch;
-    const int b = blockIdx.x / n_patch;
-    const int PC = P * C;
-    const float *xb = x + (int64_t)b * C * x_ld + (int64_t)w * P;
-    for (int i = threadIdx.x; i < PC; i += blockDim.x) {
-        const int c = i / P, t = i - c * P;
-        tile[t * C + c] = xb[(int64_t)c * x_ld + t];
-    }
-    __syncthreads();
-    T *out = a + (int64_t)blockIdx.x * PC;
-    for (int i = threadIdx.x; i < PC; i += blockDim.x) out[i] = from_f32<T>(tile[i]);
-}
-
-// patchify with the reference's input pipeline fused in front of it (preprocess/transform.py, applied per record by
+// with the reference's input pipeline optionally fused in front of it (preprocess/transform.py, applied per record by
 // EcgDataset.__getitem__ in this order): Normalize (x - mean[c]) / std[c]  ->  TimeEndPad (zeros from L_valid on)  ->
 // TimeOut (zeros on [start, start + len) of every lead of sample b).  IEEE subtract / divide, so fp32 results are
 // bit-identical to numpy's; the transformed signal itself is never written to memory.
+//
+// One CTA per (sample, group of WG consecutive windows): every lead contributes WG * P contiguous samples (coalesced
+// reads, four leads in flight per thread), the group is transposed through shared memory into output order, and because
+// the WG output rows are adjacent in `a` they leave as one contiguous run of 16-byte stores.  (One CTA per window with
+// an integer division per element and 2-byte stores took 24 us for 46 MB.)
 template <typename T>
-__global__ void patchify_transform_kernel(const float *__restrict__ x, const float *__restrict__ mean,
-                                          const float *__restrict__ stdev, const int *__restrict__ spans,
-                                          T *__restrict__ a, int C, int64_t x_ld, int L_valid, int n_patch, int P) {
-    extern __shared__ float tile[];  // [P*C] in output order
-    const int w = blockIdx.x % n_patch;
-    const int b = blockIdx.x / n_patch;
+__global__ void __launch_bounds__(256) patchify_kernel(const float *__restrict__ x, const float *__restrict__ mean,
+                                                        const float *__restrict__ stdev, const int *__restrict__ spans,
+                                                        T *__restrict__ a, int C, int64_t x_ld, int L_valid, int n_patch,
+                                                        int P, int WG, float inv_P) {
+    extern __shared__ float tile[];  // [WG][P*C] in output order
+    const int groups = (n_patch + WG - 1) / WG;
+    const int b = blockIdx.x / groups;
+    const int w0 = (blockIdx.x - b * groups) * WG;
+    const int nw = min(WG, n_patch - w0);
     const int PC = P * C;
+    const int span = nw * P;  // time steps of this group
     const float *xb = x + (int64_t)b * C * x_ld;
     int cut0 = 0, cut1 = 0;  // zeroed span of this sample
     if (spans != nullptr) {
         cut0 = spans[2 * b];
         cut1 = cut0 + spans[2 * b + 1];
     }
-    for (int i = threadIdx.x; i < PC; i += blockDim.x) {
-        const int c = i / P, t = i - c * P;
-        const int pos = w * P + t;
-        float v = 0.f;
-        if (pos < L_valid && !(pos >= cut0 && pos < cut1)) {
-            v = xb[(int64_t)c * x_ld + pos];
-            if (mean != nullptr) v = __fdiv_rn(__fsub_rn(v, mean[c]), stdev[c]);
+    for (int tt = threadIdx.x; tt < span; tt += blockDim.x) {
+        const int pos = w0 * P + tt;
+        const int wl = __float2int_rd(((float)tt + 0.5f) * inv_P);  // tt / P (exact: tt + 0.5 is never within 0.5 / P of a multiple)
+        const int t = tt - wl * P;
+        const bool live = pos < L_valid && !(pos >= cut0 && pos < cut1);
+        float *dst = tile + wl * PC + t * C;
+        for (int c0 = 0; c0 < C; c0 += 4) {
+            float v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {   // branch-free: all four loads are issued before the first use
+                const int c = min(c0 + j, C - 1);
+                v[j] = xb[(int64_t)c * x_ld + (live ? pos : 0)];
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = c0 + j;
+                if (c < C) {
+                    float r = 0.f;
+                    if (live) r = mean != nullptr ? __fdiv_rn(__fsub_rn(v[j], mean[c]), stdev[c]) : v[j];
+                    dst[c] = r;
+                }
+            }
         }
-        tile[t * C + c] = v;
     }
     __syncthreads();
-    T *out = a + (int64_t)blockIdx.x * PC;
-    for (int i = threadIdx.x; i < PC; i += blockDim.x) out[i] = from_f32<T>(tile[i]);
+    const int total = nw * PC;
+    T *out = a + ((int64_t)b * n_patch + w0) * PC;
+    if ((PC & 7) == 0) {   // every group starts 16-byte aligned
+        for (int i = threadIdx.x * 8; i < total; i += blockDim.x * 8) {
+            float v[8];
+            load8(tile + i, v);
+            store8(out + i, v);
+        }
+    } else {
+        for (int i = threadIdx.x; i < total; i += blockDim.x) out[i] = from_f32<T>(tile[i]);
+    }
 }
 
 // per-lead tokens (BASELINE.json configs[3]: vit_pytorch ViT(image_size=(C, L), patch_size=(1, P), channels=1) fed
@@ -142,40 +156,57 @@ __global__ void embed_assemble_kernel(const T *__restrict__ e, const float *__re
     }
 }
 
-// backward: grid (token position j, 32-column slab), block = 32 columns x 8 batch groups; the masked gradient rows are
-// copied to `de` on the way and the batch sums are folded through shared memory
+// backward: grid (token position j, 256-column slab), block = 32 lanes x 8 columns each x 8 batch groups; the masked
+// gradient rows are copied to `de` on the way (16-byte accesses, one dropout hash per pair) and the batch sums are folded
+// through shared memory.  (One 2-byte element per thread with a hash per element was instruction bound: 22 us for 40 MB.)
 template <typename T>
 __global__ void __launch_bounds__(256) embed_assemble_bwd_kernel(const T *__restrict__ dtok, T *__restrict__ de,
                                                                   float *__restrict__ dcls, float *__restrict__ dpos,
                                                                   float *__restrict__ dbias, int B, int n_patch, int d,
                                                                   DropoutParams drop) {
-    __shared__ float red[8][33];
+    __shared__ float red[8][256 + 8];
     const int N = n_patch + 1;
     const int j = blockIdx.x;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int col = blockIdx.y * 32 + tx;
+    const int col = (blockIdx.y * 32 + tx) * 8;
     const bool dropping = drop.threshold != 0;
     const uint32_t seed = dropping ? __ldg(drop.seed) : 0u;
-    float s = 0.f;
+    float s[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s[k] = 0.f;
     if (col < d) {
-        for (int b = ty; b < B; b += 8) {
-            const int64_t idx = ((int64_t)b * N + j) * d + col;
-            float gf = to_f32(dtok[idx]);
-            if (dropping) gf *= dropout_one(drop, seed, static_cast<uint32_t>(idx));
-            const T g = from_f32<T>(gf);
-            s += to_f32(g);
-            if (j > 0) de[((int64_t)b * n_patch + (j - 1)) * d + col] = g;
+        // two samples in flight per thread (rows N * d elements apart)
+        for (int b0 = ty; b0 < B; b0 += 16) {
+            float gv[2][8];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) load8(dtok + ((int64_t)min(b0 + 8 * q, B - 1) * N + j) * d + col, gv[q]);
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int b = b0 + 8 * q;
+                if (b < B) {
+                    const int64_t idx = ((int64_t)b * N + j) * d + col;
+                    if (dropping) dropout_apply<8>(drop, seed, static_cast<uint32_t>(idx), gv[q]);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        gv[q][k] = to_f32(from_f32<T>(gv[q][k]));   // the sums are those of the rounded rows
+                        s[k] += gv[q][k];
+                    }
+                    if (j > 0) store8(de + ((int64_t)b * n_patch + (j - 1)) * d + col, gv[q]);
+                }
+            }
         }
     }
-    red[ty][tx] = s;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) red[ty][tx * 8 + k] = s[k];
     __syncthreads();
-    if (ty == 0 && col < d) {
+    const int c = blockIdx.y * 256 + threadIdx.x;   // one column per thread for the fold
+    if (c < d) {
         float t = 0.f;
 #pragma unroll
-        for (int y = 0; y < 8; ++y) t += red[y][tx];
-        dpos[(int64_t)j * d + col] += t;
-        if (j == 0) dcls[col] += t;
-        else atomicAdd(dbias + col, t);
+        for (int y = 0; y < 8; ++y) t += red[y][threadIdx.x];
+        dpos[(int64_t)j * d + c] += t;
+        if (j == 0) dcls[c] += t;
+        else atomicAdd(dbias + c, t);
     }
 }
 
@@ -612,6 +643,14 @@ inline int grid_for(int64_t work_items, int threads, int max_blocks_per_sm = 8) 
 
 using namespace ecgvit;
 
+// windows per CTA of the patch gather: up to 8, as many as fit 48 KB of staging
+static int patchify_group(int n_patch, int P, int C) {
+    int wg = (int)((48 * 1024) / ((size_t)P * C * sizeof(float)));
+    if (wg > 8) wg = 8;
+    if (wg > n_patch) wg = n_patch;
+    return wg < 1 ? 1 : wg;
+}
+
 extern "C" {
 
 int ecgvit_patchify(const float *x, void *a, int B, int C, int64_t x_ld, int n_patch, int P, int dtype,
@@ -619,13 +658,15 @@ int ecgvit_patchify(const float *x, void *a, int B, int C, int64_t x_ld, int n_p
     ECGVIT_REQUIRE(x && a && B > 0 && C > 0 && n_patch > 0 && P > 0, "patchify: bad arguments");
     ECGVIT_REQUIRE(x_ld >= (int64_t)n_patch * P, "patchify: x_ld=%lld shorter than n_patch*P=%d", (long long)x_ld,
                    n_patch * P);
-    const size_t smem = (size_t)P * C * sizeof(float);
-    ECGVIT_REQUIRE(smem <= 48 * 1024, "patchify: patch of %d x %d elements exceeds 48 KB staging", P, C);
-    const int grid = B * n_patch;
+    ECGVIT_REQUIRE((size_t)P * C * sizeof(float) <= 48 * 1024, "patchify: patch of %d x %d elements exceeds 48 KB staging", P, C);
+    const int WG = patchify_group(n_patch, P, C);
+    const size_t smem = (size_t)WG * P * C * sizeof(float);
+    const int grid = B * ((n_patch + WG - 1) / WG);
+    const int L_all = n_patch * P;
     if (dtype == ECGVIT_BF16)
-        patchify_kernel<bf16><<<grid, 256, smem, as_stream(stream)>>>(x, (bf16 *)a, C, x_ld, n_patch, P);
+        patchify_kernel<bf16><<<grid, 256, smem, as_stream(stream)>>>(x, nullptr, nullptr, nullptr, (bf16 *)a, C, x_ld, L_all, n_patch, P, WG, 1.0f / (float)P);
     else if (dtype == ECGVIT_F32)
-        patchify_kernel<float><<<grid, 256, smem, as_stream(stream)>>>(x, (float *)a, C, x_ld, n_patch, P);
+        patchify_kernel<float><<<grid, 256, smem, as_stream(stream)>>>(x, nullptr, nullptr, nullptr, (float *)a, C, x_ld, L_all, n_patch, P, WG, 1.0f / (float)P);
     else return fail(-1, "patchify: unknown dtype %d", dtype);
     return check_launch("patchify");
 }
@@ -638,13 +679,14 @@ int ecgvit_patchify_transform(const float *x, const float *mean, const float *st
                    (long long)x_ld);
     ECGVIT_REQUIRE((int64_t)n_patch * P >= L_valid, "patchify_transform: n_patch*P=%d drops samples of L_valid=%d",
                    n_patch * P, L_valid);
-    const size_t smem = (size_t)P * C * sizeof(float);
-    ECGVIT_REQUIRE(smem <= 48 * 1024, "patchify_transform: patch of %d x %d elements exceeds 48 KB staging", P, C);
-    const int grid = B * n_patch;
+    ECGVIT_REQUIRE((size_t)P * C * sizeof(float) <= 48 * 1024, "patchify_transform: patch of %d x %d elements exceeds 48 KB staging", P, C);
+    const int WG = patchify_group(n_patch, P, C);
+    const size_t smem = (size_t)WG * P * C * sizeof(float);
+    const int grid = B * ((n_patch + WG - 1) / WG);
     if (dtype == ECGVIT_BF16)
-        patchify_transform_kernel<bf16><<<grid, 256, smem, as_stream(stream)>>>(x, mean, stdev, spans, (bf16 *)a, C, x_ld, L_valid, n_patch, P);
+        patchify_kernel<bf16><<<grid, 256, smem, as_stream(stream)>>>(x, mean, stdev, spans, (bf16 *)a, C, x_ld, L_valid, n_patch, P, WG, 1.0f / (float)P);
     else if (dtype == ECGVIT_F32)
-        patchify_transform_kernel<float><<<grid, 256, smem, as_stream(stream)>>>(x, mean, stdev, spans, (float *)a, C, x_ld, L_valid, n_patch, P);
+        patchify_kernel<float><<<grid, 256, smem, as_stream(stream)>>>(x, mean, stdev, spans, (float *)a, C, x_ld, L_valid, n_patch, P, WG, 1.0f / (float)P);
     else return fail(-1, "patchify_transform: unknown dtype %d", dtype);
     return check_launch("patchify_transform");
 }
@@ -705,7 +747,8 @@ int ecgvit_embed_assemble_bwd(const void *dtok, void *de, float *dcls, float *dp
                               int dtype, void *stream) {
     const DropoutParams drop = make_dropout(dropout_p, dropout_stream, dropout_seed);
     ECGVIT_REQUIRE(dtok && de && dcls && dpos && dbias && B > 0 && n_patch > 0 && d > 0, "embed_assemble_bwd: bad arguments");
-    dim3 grid(n_patch + 1, (d + 31) / 32);
+    ECGVIT_REQUIRE(d % 8 == 0, "embed_assemble_bwd: d=%d must be a multiple of 8", d);
+    dim3 grid(n_patch + 1, (d + 255) / 256);
     if (dtype == ECGVIT_BF16)
         embed_assemble_bwd_kernel<bf16><<<grid, 256, 0, as_stream(stream)>>>((const bf16 *)dtok, (bf16 *)de, dcls, dpos, dbias, B, n_patch, d, drop);
     else if (dtype == ECGVIT_F32)
