@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(PKG_DIR, 'libecgvit_b200.so')
 
 F32, BF16, BF16_RES32 = 0, 1, 2  # BF16_RES32: bf16 mode whose residual-stream operand is fp32 (ecgvit_b200.h)
 STATS_FLOATS = 2052  # ECGVIT_STATS_FLOATS
+SUMSQ_MAX_BLOCKS = 2048  # partial slots of the gradient-norm scratch (stats[4:])
 EPI_STORE, EPI_BIAS_RES, EPI_BIAS_GELU, EPI_DGELU, EPI_ATOMIC_F32, EPI_BIAS_RES_F32 = 0, 1, 2, 3, 4, 5
 REDUCTION = {'mean': 0, 'sum': 1, 'none': 2}
 
@@ -71,6 +72,8 @@ SIGNATURES = {
                                                                       c_int, c_void_p],
     'ecgvit_colsum': [c_void_p, c_void_p, c_int, c_int, c_int64, c_int, c_void_p],
     'ecgvit_grad_sumsq': [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p],
+    'ecgvit_grad_sumsq_partial': [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int, c_int, c_void_p],
+    'ecgvit_grad_sumsq_finalize': [c_void_p, c_int, c_void_p],
     'ecgvit_adamw_step': [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int64, c_void_p, c_void_p, c_int,
                           c_void_p],
     'ecgvit_grad_scale_by_clip': [c_void_p, c_int64, c_void_p, c_void_p, c_void_p],

@@ -173,6 +173,28 @@ int ecgvit_grad_sumsq(const void *g, int grad_dtype, int64_t n, const float *hyp
     return check_launch("grad_sumsq_finalize");
 }
 
+int ecgvit_grad_sumsq_partial(const void *g, int grad_dtype, int64_t n, const float *hyper, float *stats,
+                              int first_block, int n_blocks, void *stream) {
+    ECGVIT_REQUIRE(g && hyper && stats && n > 0, "grad_sumsq_partial: bad arguments");
+    ECGVIT_REQUIRE((reinterpret_cast<uintptr_t>(g) & 15) == 0, "grad_sumsq_partial: g must be 16-byte aligned");
+    ECGVIT_REQUIRE(grad_dtype == ECGVIT_F32 || grad_dtype == ECGVIT_BF16, "grad_sumsq_partial: unknown gradient dtype %d", grad_dtype);
+    ECGVIT_REQUIRE(first_block >= 0 && n_blocks >= 1 && first_block + n_blocks <= SUMSQ_MAX_BLOCKS,
+                   "grad_sumsq_partial: partial slots [%d, %d) outside [0, %d)", first_block, first_block + n_blocks,
+                   SUMSQ_MAX_BLOCKS);
+    // the kernel parks the partial of CTA i at stats[4 + i]: offsetting the pointer selects this slice's slots
+    if (grad_dtype == ECGVIT_F32)
+        grad_sumsq_kernel<float><<<n_blocks, 256, 0, as_stream(stream)>>>((const float *)g, n, hyper, stats + first_block);
+    else
+        grad_sumsq_kernel<bf16><<<n_blocks, 256, 0, as_stream(stream)>>>((const bf16 *)g, n, hyper, stats + first_block);
+    return check_launch("grad_sumsq_partial");
+}
+
+int ecgvit_grad_sumsq_finalize(float *stats, int n_blocks, void *stream) {
+    ECGVIT_REQUIRE(stats && n_blocks >= 1 && n_blocks <= SUMSQ_MAX_BLOCKS, "grad_sumsq_finalize: bad arguments");
+    grad_sumsq_finalize_kernel<<<1, 256, 0, as_stream(stream)>>>(stats, n_blocks);
+    return check_launch("grad_sumsq_finalize");
+}
+
 int ecgvit_adamw_step(float *p, float *m, float *v, const void *g, int grad_dtype, void *shadow_bf16, int64_t n,
                       const float *hyper, float *stats, int flags, void *stream) {
     ECGVIT_REQUIRE(p && m && v && g && hyper && stats && n > 0, "adamw_step: bad arguments");

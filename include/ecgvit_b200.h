@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define ECGVIT_ABI_VERSION 6
+#define ECGVIT_ABI_VERSION 7
 
 /* ECGVIT_BF16_RES32: bf16 mode with an fp32 RESIDUAL STREAM (the running sum x / y of the blocks, which deep models such
  * as 'large' need to stay within 1e-2 of the fp32 reference).  Accepted by the entry points that touch the stream, which
@@ -222,6 +222,13 @@ int ecgvit_colsum(const void *x, float *out, int M, int N, int64_t ld, int dtype
 /* `g` is the flat gradient buffer in `grad_dtype`: ECGVIT_F32, or ECGVIT_BF16 when a data-parallel run all-reduced the
  * gradients in bf16 (half the NVLink bytes; the moments and parameters stay fp32 either way). */
 int ecgvit_grad_sumsq(const void *g, int grad_dtype, int64_t n, const float *hyper, float *stats, void *stream);
+/* The same norm, slice by slice: every call reduces one slice of the gradient buffer into its own `n_blocks` partial
+ * slots [first_block, first_block + n_blocks) of the stats scratch (2048 slots in all) and may run as soon as that slice
+ * is final -- e.g. per layer beside the rest of backward -- in any order and on any stream; ecgvit_grad_sumsq_finalize
+ * then folds slots [0, n_blocks) in a fixed order into stats[0..2].  Deterministic for a fixed slicing. */
+int ecgvit_grad_sumsq_partial(const void *g, int grad_dtype, int64_t n, const float *hyper, float *stats,
+                              int first_block, int n_blocks, void *stream);
+int ecgvit_grad_sumsq_finalize(float *stats, int n_blocks, void *stream);
 /* flags: 0 for a whole-buffer update.  ECGVIT_ADAMW_SLICE: the call updates one slice (p, m, v, g, shadow all offset
  * alike) of the flat buffers; the slices of one update may be issued in any order and beside other kernels
  * (short-lived CTAs); exactly one of them carries ECGVIT_ADAMW_FIRST_SLICE and records the norm / the skipped-update

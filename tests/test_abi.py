@@ -30,7 +30,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     for s in _declared_symbols():
         assert hasattr(raw, s), f'{s} declared in the header but not exported'
     assert set(_declared_symbols()) == set(ecg_b200._lib.SIGNATURES), 'ctypes table and header disagree'
-    assert lib.ecgvit_abi_version() == 6
+    assert lib.ecgvit_abi_version() == 7
 
 
 def test_gemm_args_struct_layout_matches_header():

@@ -482,3 +482,42 @@ def test_clip_adamw_read_bf16_gradients(lib):
         assert torch.equal(a, b)                      # bf16 -> fp32 is exact: same arithmetic either way
     want = float((g16.float() * 0.125).norm())
     assert abs(outs[1][4] - want) < 1e-5 * want
+
+
+def test_grad_norm_slice_by_slice_matches_whole_buffer(lib):
+    """ecgvit_grad_sumsq_partial over uneven slices issued in a scrambled order + ecgvit_grad_sumsq_finalize == the
+    one-pass norm == torch's; twice the same bits (no atomics)"""
+    torch.manual_seed(5)
+    n = 3_000_004
+    g = torch.randn(n, device='cuda') * 0.3
+    hyper = torch.zeros(16, device='cuda')
+    hyper.copy_(torch.tensor(L.adamw_hyper(3e-4, 0.9, 0.999, 1e-8, 1e-2, 1, 1.0, 0.5)))   # grad_scale 0.5
+    bounds = [0, 1024, 700_000, 700_064, 2_200_000, n]          # 4-element aligned starts (16-byte aligned pointers)
+    per = 37
+    order = [3, 0, 4, 2, 1]
+    got = []
+    for _ in range(2):
+        stats = torch.full((L.STATS_FLOATS,), float('nan'), device='cuda')
+        for i in order:
+            lo, hi = bounds[i], bounds[i + 1]
+            L.check(lib.ecgvit_grad_sumsq_partial(g.data_ptr() + 4 * lo, L.F32, hi - lo, hyper.data_ptr(), stats.data_ptr(),
+                                                  i * per, per, stream()), 'partial')
+        L.check(lib.ecgvit_grad_sumsq_finalize(stats.data_ptr(), per * (len(bounds) - 1), stream()), 'finalize')
+        torch.cuda.synchronize()
+        got.append(stats[:3].clone())
+    assert torch.equal(got[0], got[1])
+    want = float((g.double() * 0.5).norm())
+    assert abs(float(got[0][2]) - want) < 1e-5 * want
+    assert float(got[0][1]) == 0.0
+    whole = torch.zeros(L.STATS_FLOATS, device='cuda')
+    L.check(lib.ecgvit_grad_sumsq(g.data_ptr(), L.F32, n, hyper.data_ptr(), whole.data_ptr(), stream()), 'sumsq')
+    assert abs(float(whole[2]) - float(got[0][2])) < 1e-5 * want
+    # a non-finite gradient anywhere raises the flag
+    g[2_500_000] = float('inf')
+    stats = torch.zeros(L.STATS_FLOATS, device='cuda')
+    for i in order:
+        lo, hi = bounds[i], bounds[i + 1]
+        L.check(lib.ecgvit_grad_sumsq_partial(g.data_ptr() + 4 * lo, L.F32, hi - lo, hyper.data_ptr(), stats.data_ptr(),
+                                              i * per, per, stream()), 'partial')
+    L.check(lib.ecgvit_grad_sumsq_finalize(stats.data_ptr(), per * (len(bounds) - 1), stream()), 'finalize')
+    assert float(stats[1]) == 1.0
