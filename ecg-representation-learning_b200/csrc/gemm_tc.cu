@@ -68,6 +68,22 @@ int gemm_clusters() {
     return g_gemm_clusters;
 }
 
+// Counters of the in-kernel unit scheduler: one (next unit, clusters done) pair per launch, taken round-robin from a static
+// array.  A kernel leaves its pair at zero when its last cluster runs dry, so a slot can be re-used by any later launch
+// (a replayed CUDA graph re-uses the slots baked into its nodes); 4096 slots keep concurrent launches apart.
+constexpr int kSchedSlots = 4096;
+__device__ int g_sched_ctr[2 * kSchedSlots];
+int *next_sched_slot() {
+    static int *base = nullptr;
+    static unsigned next = 0;
+    if (base == nullptr) {
+        void *p = nullptr;
+        if (cudaGetSymbolAddress(&p, g_sched_ctr) != cudaSuccess) return nullptr;
+        base = static_cast<int *>(p);
+    }
+    return base + 2 * (__atomic_fetch_add(&next, 1u, __ATOMIC_RELAXED) % kSchedSlots);
+}
+
 template <int BN, bool A_MN, bool B_MN, int MODE>
 int launch_pair(const ecgvit_gemm_args *g, int split_k, cudaStream_t stream) {
     constexpr bool kWide = MODE == ECGVIT_EPI_BIAS_RES_F32;   // fp32 residual stream: 128-byte staging rows
@@ -108,8 +124,11 @@ int launch_pair(const ecgvit_gemm_args *g, int split_k, cudaStream_t stream) {
     const int clusters = gemm_clusters();
     const int grid = 2 * (units < clusters ? units : clusters);
     EpiParams ep{g->out, g->out2, g->aux, g->bias, g->ldo, make_dropout(g->dropout_p, g->dropout_stream, g->dropout_seed)};
+    static const int dynamic = [] { const char *e = getenv("ECGVIT_GEMM_DYNAMIC"); return e == nullptr || atoi(e) != 0; }();
+    int *sched = next_sched_slot();
+    if (sched == nullptr) return fail(-4, "gemm_tc2: cannot resolve the scheduler counters");
     cudaError_t le = launch_pdl(kern, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, ta, tb, to, to2, tx, g->M,
-                                g->N, g->K, split_k, ep);
+                                g->N, g->K, split_k, ep, sched, dynamic);
     if (le != cudaSuccess) return fail((int)le, "gemm_tc2 launch: %s", cudaGetErrorString(le));
     return check_launch("gemm_tc2");
 }

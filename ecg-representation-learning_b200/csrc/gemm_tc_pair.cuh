@@ -12,6 +12,15 @@
 //   empty[s]       on BOTH       : leader's tcgen05.commit multicast -> each CTA's producer may refill stage s
 //   tmem_full[a]   on BOTH       : leader's tcgen05.commit multicast -> each CTA's epilogue drains its 128 rows
 //   tmem_empty[a]  on the LEADER : 8 epilogue warps x 2 CTAs arrive (remote arrive from the peer)
+//
+// Work distribution: the first 256 x BN unit of a cluster is static (unit = cluster index); every further unit comes from
+// a global counter.  Warp 3 of the leader fetches the next unit index with one atomicAdd and hands it to every warp of
+// both CTAs through a two-slot shared-memory ring:
+//   sched_full[s]  on BOTH       : the leader's scheduler stores the index into its own slot and arrives; the peer's slot
+//                                  receives it by st.async, which completes 4 expected bytes on the peer's barrier
+//   sched_empty[s] on the LEADER : every consumer warp of both CTAs arrives after reading the slot
+// A cluster that becomes resident late (its SMs were still held by a kernel of the other stream, or by NCCL) therefore
+// takes fewer units instead of making the whole grid wait for its statically assigned share.
 #pragma once
 
 template <int BN, bool B_MN, bool WIDE = false, int TILES = 2> struct PairCfg {
@@ -32,12 +41,13 @@ template <int BN, bool B_MN, bool WIDE = false, int TILES = 2> struct PairCfg {
     static constexpr int EPI_TILE_BYTES = WIDE ? 32 * 128 : 32 * 64;
     static constexpr int EPI_TILES_PER_WARP = TILES;
     static constexpr int EPI_BYTES = EPI_WARPS * EPI_TILES_PER_WARP * EPI_TILE_BYTES;
-    static constexpr int NUM_BARRIERS = 2 * 8 + 4 + EPI_WARPS * EPI_TILES_PER_WARP;
+    static constexpr int SCHED_SLOTS = 2;                                      // unit indices in flight per cluster
+    static constexpr int NUM_BARRIERS = 2 * 8 + 4 + EPI_WARPS * EPI_TILES_PER_WARP + 2 * SCHED_SLOTS;
     static constexpr int PIPE_BUDGET = 232448 - 1024 - 1024 - EPI_BYTES;
     static constexpr int STAGES = (PIPE_BUDGET / STAGE_BYTES) > 8 ? 8 : (PIPE_BUDGET / STAGE_BYTES);
     static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 + 1024;
-    static_assert(NUM_BARRIERS * 8 + 16 <= 1024, "barrier block");
+    static_assert(NUM_BARRIERS * 8 + 16 + 4 * SCHED_SLOTS <= 1024, "barrier block");
     static_assert(BN % 64 == 0, "tile width");
 };
 // the configuration of one (tile width, B layout, epilogue) instantiation
@@ -146,7 +156,8 @@ __global__ void __cluster_dims__(2, 1, 1)
 __launch_bounds__(PairCfgFor<BN, B_MN, MODE>::THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                 const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_out2,
-                const __grid_constant__ CUtensorMap tmap_aux, int M, int N, int K, int split_k, EpiParams ep) {
+                const __grid_constant__ CUtensorMap tmap_aux, int M, int N, int K, int split_k, EpiParams ep,
+                int *__restrict__ sched_ctr, int dynamic) {
     constexpr bool kWide = MODE == ECGVIT_EPI_BIAS_RES_F32;   // (the split-K epilogue has its own fp32 path below)
     using Cfg = PairCfgFor<BN, B_MN, MODE>;
     constexpr bool kHasAux = (MODE == ECGVIT_EPI_BIAS_RES || MODE == ECGVIT_EPI_DGELU || kWide);
@@ -161,7 +172,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     uint64_t *tmem_full_bar = empty_bar + STAGES;
     uint64_t *tmem_empty_bar = tmem_full_bar + 2;
     uint64_t *aux_bar = tmem_empty_bar + 2;  // [epilogue warp][unit]
-    uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(aux_bar + Cfg::EPI_WARPS * Cfg::EPI_TILES_PER_WARP);
+    uint64_t *sched_full = aux_bar + Cfg::EPI_WARPS * Cfg::EPI_TILES_PER_WARP;
+    uint64_t *sched_empty = sched_full + Cfg::SCHED_SLOTS;
+    uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(sched_empty + Cfg::SCHED_SLOTS);
+    volatile int *sched_unit = reinterpret_cast<volatile int *>(tmem_ptr_smem + 2);   // [SCHED_SLOTS]
+    constexpr int kNoUnit = 0x7fffffff;
 
     pdl_launch_dependents();
     const int warp = threadIdx.x >> 5;
@@ -188,6 +203,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             ptx::mbar_init(&tmem_empty_bar[a], 2 * Cfg::EPI_WARPS);
         }
         for (int i = 0; i < Cfg::EPI_WARPS * Cfg::EPI_TILES_PER_WARP; ++i) ptx::mbar_init(&aux_bar[i], 1);
+        for (int i = 0; i < Cfg::SCHED_SLOTS; ++i) {
+            ptx::mbar_init(&sched_full[i], 1);
+            // consumers: TMA producer and epilogue warps of both CTAs, the leader's MMA issuer
+            ptx::mbar_init(&sched_empty[i], 2 * Cfg::EPI_WARPS + 3);
+        }
         ptx::fence_mbar_init();
     }
     if (warp == 2) ptx::tmem_alloc_2sm(tmem_ptr_smem, Cfg::TMEM_COLS);
@@ -202,13 +222,23 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     const int kb_total = (K + BK - 1) / BK;
     const int kb_per_split = (kb_total + split_k - 1) / split_k;
     const int num_units = tiles_m * tiles_n * split_k;
+    // called by a whole consumer warp when it is done with its unit number `n_done - 1`: the index of its next unit
+    auto next_unit = [&](int n_done) -> int {
+        const int slot = (n_done - 1) % Cfg::SCHED_SLOTS;
+        ptx::mbar_wait(&sched_full[slot], ((n_done - 1) / Cfg::SCHED_SLOTS) & 1);
+        const int u = sched_unit[slot];
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_cluster(&sched_empty[slot], 0);
+        return u;
+    };
 
     if (warp == 0) {
         // ================================ TMA producer (both CTAs) ================================
         // the whole warp walks the loop (warp-uniform control flow and addresses); one elected lane issues
         int stage = 0;
         uint32_t phase = 0;
-        for (int u = cluster_id; u < num_units; u += num_clusters) {
+        int it = 0;
+        for (int u = cluster_id; u != kNoUnit; u = next_unit(++it)) {
             const int tile_n = u % tiles_n;
             const int tile_m = (u / tiles_n) % tiles_m;
             const int split = u / (tiles_n * tiles_m);
@@ -254,7 +284,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int u = cluster_id; u < num_units; u += num_clusters, ++it) {
+            for (int u = cluster_id; u != kNoUnit; u = next_unit(++it)) {
                 const int split = u / (tiles_n * tiles_m);
                 const int kb0 = split * kb_per_split;
                 const int kb1 = min(kb0 + kb_per_split, kb_total);
@@ -282,6 +312,30 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                 __syncwarp();
             }
         }
+    } else if (warp == 3) {
+        // ================================ unit scheduler (leader CTA, one thread) =================
+        if (leader && lane == 0) {
+            for (int k = 0;; ++k) {
+                const int slot = k % Cfg::SCHED_SLOTS;
+                ptx::mbar_wait(&sched_empty[slot], ((k / Cfg::SCHED_SLOTS) & 1) ^ 1);
+                // (dynamic == 0: the static round-robin deal, for A/B measurements)
+                int u = dynamic ? num_clusters + atomicAdd(&sched_ctr[0], 1) : cluster_id + (k + 1) * num_clusters;
+                if (u >= num_units) u = kNoUnit;
+                sched_unit[slot] = u;
+                ptx::mbar_arrive(&sched_full[slot]);
+                ptx::mbar_arrive_expect_tx_cluster(&sched_full[slot], 1, 4);
+                ptx::st_async_cluster_u32(const_cast<int *>(&sched_unit[slot]), &sched_full[slot], 1,
+                                          static_cast<uint32_t>(u));
+                if (u == kNoUnit) break;
+            }
+            // the last cluster to run dry re-arms the counters for the next launch that uses this slot
+            __threadfence();
+            if (dynamic && atomicAdd(&sched_ctr[1], 1) == num_clusters - 1) {
+                sched_ctr[0] = 0;
+                sched_ctr[1] = 0;
+                __threadfence();
+            }
+        }
     } else if (warp >= 4) {
         // ================================ epilogue (both CTAs, own 128 rows) ======================
         const int q = warp & 3;              // TMEM lane quadrant this warp may access
@@ -293,7 +347,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         // column tile skips the load), so it is tracked per barrier, not derived from the tile count
         uint32_t aux_phase = 0;
         int it = 0;
-        for (int u = cluster_id; u < num_units; u += num_clusters, ++it) {
+        for (int u = cluster_id; u != kNoUnit; u = next_unit(++it)) {
             const int tile_n = u % tiles_n;
             const int tile_m = (u / tiles_n) % tiles_m;
             const int acc = it & 1;

@@ -206,6 +206,27 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t *bar, uint32_t cta)
         ::"r"(smem_u32(bar)), "r"(cta)
         : "memory");
 }
+// A 32-bit value handed to the same smem offset in CTA `cta` of the cluster: the sender arms the receiver's mbarrier
+// (arrive + expect 4 bytes) and sends the word with st.async, which completes those bytes on that barrier -- the mechanism
+// TMA multicast uses, so the receiver waits with an ordinary CTA-scope try_wait.  (acquire.cluster / release.cluster
+// mbarrier operations work too but compile to MEMBAR + ERRBAR + CCTL.IVALL, an L1 invalidation per wait.)
+__device__ __forceinline__ void mbar_arrive_expect_tx_cluster(uint64_t *bar, uint32_t cta, uint32_t bytes) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.expect_tx.shared::cluster.b64 _, [ra], %2;\n\t}"
+        ::"r"(smem_u32(bar)), "r"(cta), "r"(bytes)
+        : "memory");
+}
+__device__ __forceinline__ void st_async_cluster_u32(const void *local, uint64_t *bar, uint32_t cta, uint32_t v) {
+    asm volatile(
+        "{\n\t.reg .b32 ra, rb;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %2;\n\t"
+        "mapa.shared::cluster.u32 rb, %1, %2;\n\t"
+        "st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.u32 [ra], %3, [rb];\n\t}"
+        ::"r"(smem_u32(local)), "r"(smem_u32(bar)), "r"(cta), "r"(v)
+        : "memory");
+}
 // TMA load issued by either CTA of the pair into ITS OWN smem, completion bytes counted on the LEADER's barrier
 __device__ __forceinline__ void tma_load_2d_2sm(void *dst, const CUtensorMap *m, uint64_t *bar, int c0, int c1) {
     asm volatile(
