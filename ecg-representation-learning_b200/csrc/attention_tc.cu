@@ -631,13 +631,14 @@ int launch_fwd(const void *qkv, void *o, float *lse, int B, int N, int H, float 
 //   packed: an item is one 128-row tile (two problems), one step per item;
 //   long:   an item is one 128-key block of one (batch, head) whose K / V stay in shared memory while the query blocks
 //           stream past (one step each); dK / dV accumulate in TMEM over the steps, dQ of every step is added to an fp32
-//           accumulator in HBM with red.global.add (converted to bf16 afterwards).
+//           accumulator in HBM by TMA reduce-add (converted to bf16 afterwards).
 // Per step, with S / dP / dV / dK / dQ in TMEM (448 columns):
 //   MMA   S = Q K^T, dP = dO V^T                                   (SS, 128 x 128 x 64 each)
 //   warps P = exp2(S sl2 - lse), Pd = P mask, dS = P (dP mask - D) scale  -> bf16 tiles Pd_s, dS_s in shared memory,
 //         laid out [query][key] in 128-byte rows: K-major A operand for dS K and MN-major A operand for Pd^T dO, dS^T Q
 //   MMA   dV += Pd^T dO, dK += dS^T Q, dQ = dS K                   (SS, 128 x 64 x 128 each)
-//   warps drain dQ (and dK, dV after the item's last step) from TMEM straight to HBM (thread = row: full 64-byte runs)
+//   warps drain dQ (and dK, dV after the item's last step) from TMEM into a shared-memory staging area; warp 3 sends the
+//         staged tiles to HBM with TMA stores / TMA reduce-adds
 // The issuer launches the NEXT step's S / dP as soon as the warps hold the current ones in registers, so the tensor
 // core is never waiting for the exponentials of the step it just finished.
 // D = rowsum(dO * O): packed rows are whole in one tile, so D = sum_j Pd_ij dP_ij is formed in the kernel (the two

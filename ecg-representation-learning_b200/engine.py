@@ -7,8 +7,13 @@ Data layout in HBM (T = bf16 in performance mode, fp32 in parity mode; M = B * (
   weight shadow                          : flat bf16 copy of the parameters (GEMM operands), written by AdamW
   a_patch  [B*n_patch, P*C]  T           : gathered patches, time-major / lead-minor features
   per layer: x_in [M,d], ln1 [M,d], qkv [M,3*inner], lse [B,H,N] f32, o [M,inner], y [M,d], ln2 [M,d],
-             u [M,mlp] (pre-GELU), h [M,mlp] (post-GELU), row statistics (mean, rstd) f32
-  backward scratch (shared by all layers): dres0/dres1 [M,d], dln [M,d], d_o [M,inner], dqkv [M,3*inner], du [M,mlp]
+             u [M,mlp] (pre-GELU), h [M,mlp] (post-GELU), row statistics (mean, rstd) f32.  x_in / y are fp32 when the
+             residual stream is fp32 (config.residual_dtype; models deeper than 12 layers).  With
+             config.activation_checkpointing only x_in is kept per layer; two rotating sets hold the rest and backward
+             re-runs the block forward (same dropout masks: they are functions of the step's seed)
+  backward scratch, double-buffered by layer parity (the weight-gradient GEMMs of layer l read it on the side stream while
+             the main stream already writes layer l-1's): dz[2], dy[2] [M,d], dln [M,d], d_o [M,inner], dqkv[2]
+             [M,3*inner], du[2] [M,mlp], dzm[site][2] [M,d] (dropout-masked LayerNorm gradients)
 Everything is row-major with the feature dimension contiguous, so every GEMM operand is either K-major or
 MN-major for TMA without a transposed copy.
 

@@ -35,7 +35,7 @@ def bucket_slices(layer_offsets, total, depth, bucket_layers):
 class BucketedGradReducer:
     def __init__(self, model=None, group=None, bucket_layers=1, flat_g=None, layer_offsets=None, depth=None, bf16=False):
         """bf16=True: every bucket is cast to bf16 (a contiguous slice of `flat_g16`) right before its all-reduce and the
-        optimizer kernels read the reduced bf16 image; the fp32 buffer keeps receiving the split-K red.adds."""
+        optimizer kernels read the reduced bf16 image; the fp32 buffer keeps receiving the split-K partial sums."""
         self.group = group
         if model is not None:
             flat_g = model._flat_g

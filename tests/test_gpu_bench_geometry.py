@@ -141,7 +141,7 @@ def test_step_gemm_dgrad_shapes(N, K):
 @pytest.mark.parametrize('n_out,k_in', [(3072, 768), (768, 3072), (2304, 768), (768, 768), (768, 600)])
 def test_step_gemm_wgrad_shapes_auto_split(n_out, k_in):
     """dW[n_out, k_in] += dY^T X with the contraction over all 13 056 token rows, split-K chosen by the library
-    (fp32 red.add into the gradient buffer): the largest single share of the step"""
+    (fp32 TMA reduce-add into the gradient buffer): the largest single share of the step"""
     lib = L.load()
     rows = M_TOK if k_in != 600 else 256 * 50
     dY, X = _rand((rows, n_out), 5), _rand((rows, k_in), 6)
