@@ -228,7 +228,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         ptx::mbar_wait(&sched_full[slot], ((n_done - 1) / Cfg::SCHED_SLOTS) & 1);
         const int u = sched_unit[slot];
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive_cluster(&sched_empty[slot], 0);
+        // the arrive is made to depend on the value read (never -1), so it cannot be issued while the load of the slot is
+        // still in flight: the scheduler overwrites the slot once every consumer has arrived
+        if (lane == 0 && u != -1) ptx::mbar_arrive_cluster(&sched_empty[slot], 0);
         return u;
     };
 
