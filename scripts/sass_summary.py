@@ -16,7 +16,8 @@ PATTERNS = collections.OrderedDict([
     ('UTCHMMA', r'\bUTCHMMA'), ('UTCHMMA.2CTA', r'\bUTCHMMA\.2CTA'), ('LDTM', r'\bLDTM'), ('STTM', r'\bSTTM'),
     ('UTMALDG', r'\bUTMALDG'), ('UTMASTG', r'\bUTMASTG'), ('UTMAREDG', r'\bUTMAREDG'), ('UBLKCP', r'\bUBLKCP'),
     ('UTCBAR', r'\bUTCBAR'), ('UTCATOMSWS (tmem alloc)', r'\bUTCATOMSWS'), ('HMMA (mma.sync)', r'\bHMMA'),
-    ('LDGSTS (cp.async)', r'\bLDGSTS'), ('MUFU', r'\bMUFU'), ('REDG / RED (global red.add)', r'\bRED(G)?\b'),
+    ('LDGSTS (cp.async)', r'\bLDGSTS'), ('MUFU', r'\bMUFU'), ('REDG / RED (global red.add)', r'(?<![.\w])REDG?\b'), ('ATOMG (global atomic)', r'(?<![.\w])ATOMG?\b'),
+    ('STAS (st.async to the peer CTA)', r'\bSTAS\b'), ('UCGABAR (cluster barrier)', r'\bUCGABAR'),
     ('FFMA2 / FMUL2 / FADD2', r'\bF(FMA|MUL|ADD)2\b'),
 ])
 
